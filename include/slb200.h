@@ -1,0 +1,162 @@
+/*
+ * slb200.h -- C ABI of libslb200.so, the B200 (sm_100a) implementation of the
+ * SemiLagrangian.jl hot path: the 1-D interpolation sweep inside the split advection!
+ * driver, the charge-density reduction and the Fourier Poisson solve that feed it.
+ *
+ * The reference (JuliaVlasov/SemiLagrangian.jl v0.1.2) is pure Julia and has no FFI; these
+ * are the entry points its Julia host layer binds with `ccall` (see INTEGRATION.md and
+ * semilagrangian.jl_b200/julia/SemiLagrangianB200.jl).  Each entry point cites the
+ * reference interface (file:line under the reference's root) it replaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, negative = error (SLB_E_*); the message is
+ *     available from slb_last_error().  Nothing throws across the ABI.
+ *   - arrays are COLUMN-MAJOR, dim 0 fastest (Julia's layout), extents are int64_t.
+ *   - opaque handles own their device memory; host pointers are borrowed for the call.
+ *   - one host thread per context; calls enqueue on the context's stream and return;
+ *     slb_sync() waits.  Functions that return host scalars synchronise themselves.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     SLB_E_CUDA.
+ */
+#ifndef SLB200_H
+#define SLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLB_OK 0
+#define SLB_E_ARG (-1)     /* invalid argument (ArgumentError / DomainError in the reference) */
+#define SLB_E_CUDA (-2)    /* CUDA runtime error, or no device */
+#define SLB_E_ALLOC (-3)   /* out of memory */
+#define SLB_E_UNSUPPORTED (-4)
+
+/* interpolation kinds: AbstractInterpolation subtypes, src/interpolation.jl:18 */
+#define SLB_LAGRANGE 0     /* src/lagrange.jl:58-72    */
+#define SLB_BSPLINE_LU 1   /* src/bsplinelu.jl:253-270 */
+#define SLB_BSPLINE_FFT 2  /* src/bsplinefft.jl:25-45  */
+#define SLB_HERMITE 3      /* src/hermite.jl:99-132    */
+
+/* slb_sweep flags */
+#define SLB_SWEEP_EXACT 1  /* stencil as rounded products summed left to right (bitwise the
+                              reference's `sum(res[...] .* precal)`, src/interpolation.jl:190)
+                              instead of an FMA chain */
+
+#define SLB_MAX_DIMS 6
+#define SLB_MAX_ORDER 63
+
+typedef struct slb_ctx slb_ctx;
+typedef struct slb_grid slb_grid;
+typedef struct slb_interp slb_interp;
+typedef struct slb_poisson slb_poisson;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* One context per process and GPU.  `stream` is a cudaStream_t to adopt (e.g. torch's
+ * current stream) or NULL to create a private non-blocking stream.
+ * Replaces: the `timeopt` back-end selection of Advection (src/advection.jl:2,95). */
+int slb_ctx_create(int device_id, void* stream, slb_ctx** out);
+void slb_ctx_destroy(slb_ctx* ctx);
+const char* slb_last_error(void);
+int slb_sync(slb_ctx* ctx);
+int slb_device_count(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t slb_launch_count(const slb_ctx* ctx);
+/* CUDA-event timer on the context's stream */
+int slb_timer_start(slb_ctx* ctx);
+int slb_timer_stop(slb_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */
+
+/* extra CUDA events on the context's stream (per-kernel timing inside bench.py) */
+int slb_event_create(slb_ctx* ctx, void** ev_out);
+int slb_event_record(slb_ctx* ctx, void* ev);
+int slb_event_elapsed_ms(void* ev_start, void* ev_stop, float* elapsed_ms); /* waits for ev_stop */
+int slb_event_destroy(void* ev);
+
+/* raw device / pinned-host buffers (E fields, rho, shift tables) */
+int slb_malloc(slb_ctx* ctx, int64_t bytes, void** dev_out);
+int slb_free(slb_ctx* ctx, void* dev);
+int slb_host_alloc(int64_t bytes, void** host_out); /* pinned */
+int slb_host_free(void* host);
+int slb_memcpy_h2d(slb_ctx* ctx, void* dev, const void* host, int64_t bytes); /* async on the stream */
+int slb_memcpy_d2h(slb_ctx* ctx, void* host, const void* dev, int64_t bytes); /* async on the stream */
+
+/* ---- grid: the device-resident distribution function -------------------------------- */
+/* Replaces AdvectionData.data + bufdata (src/advection.jl:229-267): `f` and an equally
+ * sized scratch array.  Sweeps are out-of-place front -> back, then the roles swap, so f
+ * never leaves HBM between split stages and no permutedims! is ever needed
+ * (src/advection.jl:372-386). */
+int slb_grid_create(slb_ctx* ctx, int ndims, const int64_t* extents, slb_grid** out);
+/* same, over caller-owned device buffers (e.g. torch tensors); not freed on destroy */
+int slb_grid_create_external(slb_ctx* ctx, int ndims, const int64_t* extents, double* dev_front,
+                             double* dev_back, slb_grid** out);
+void slb_grid_destroy(slb_grid* g);
+int slb_grid_upload(slb_grid* g, const double* host);         /* AdvectionData ctor copy, src/advection.jl:264-267 */
+int slb_grid_download(const slb_grid* g, double* host);       /* getdata, src/advection.jl:317 */
+double* slb_grid_front(const slb_grid* g);                     /* current f (device pointer) */
+double* slb_grid_back(const slb_grid* g);                      /* scratch (device pointer)   */
+int slb_grid_swap(slb_grid* g);
+
+/* ---- interpolation object ------------------------------------------------------------ */
+/* coef: (order+1) rows x ncoef ascending Float64 coefficients, row-major: row j is
+ * `tabfct[j+1]` (src/interpolation.jl:18, :96-98) already rounded to Float64 by the host
+ * (which keeps the reference's exact-rational constructors).  node_vals: B(1..order) for
+ * the B-spline kinds (src/bsplinelu.jl:264, src/bsplinefft.jl:35), else NULL.  n: line
+ * length the object is bound to (B-splines; ignored otherwise).
+ * Errors mirror the reference: even order for SLB_BSPLINE_LU (src/bsplinelu.jl:257-261),
+ * n not a power of two for SLB_BSPLINE_FFT (src/fftbig.jl:57). */
+int slb_interp_create(slb_ctx* ctx, int kind, int order, int64_t n, const double* coef, int ncoef,
+                      const double* node_vals, slb_interp** out);
+void slb_interp_destroy(slb_interp* it);
+
+/* ---- the sweep: one advection! call of a const-shift 1-D state ------------------------ */
+/* Replaces advection! (src/advection.jl:594-657) = getformdata + per-line
+ * getprecal/interpolate! (src/interpolation.jl:175-193, :381-396) + copydata!.
+ * For every line along `dim` with other-dim indices idx[]:
+ *     alpha = alpha_scale * alpha_tab[ sum_d idx[d] * alpha_strides[d] ]      (grid units)
+ *     decint = floor(alpha); w_j = tabfct[j](alpha - decint)
+ *     c = sol(interp, line)   (identity | cyclic banded LU | FFT-diagonal)
+ *     out[i] = sum_j c[(i + decint - order/2 + j) mod n] * w_j
+ * alpha_strides[dim] is ignored; 0 = broadcast.  alpha_tab is a device pointer when
+ * alpha_on_device != 0 (E fields, mesh points kept on the GPU), else a host array of
+ * alpha_len doubles that is copied first.  The (alpha_scale, table) split is exactly how
+ * the plugins build bufcur: (dt/step) * E  (src/poisson.jl:178-189),
+ * (-dt/step) * v  (:191-203), (sign*dt/step) * points (src/rotation.jl:21-31). */
+int slb_sweep(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+              const int64_t* alpha_strides, double alpha_scale, int alpha_on_device, int flags);
+
+/* sol(interp, b) applied to every line along dim (src/interpolation.jl:40,
+ * src/bsplinelu.jl:275-284, src/bsplinefft.jl:49-58); in place on the grid (front buffer
+ * after the call).  Exposed for tests. */
+int slb_presolve(slb_grid* g, int dim, const slb_interp* it);
+
+/* ---- Vlasov-Poisson field solve ------------------------------------------------------ */
+/* compute_charge! (src/util_poisson.jl:68-79): rho = dv * sum over the trailing
+ * (ndims - nsp) dims of f, minus its mean.  rho_dev holds prod(extents[0..nsp)) doubles. */
+int slb_charge_density(slb_grid* g, int nsp, double dv, double* rho_dev);
+/* same without the mean subtraction and over a sub-range; used by the sharded driver,
+ * which all-gathers slabs of rho before removing the mean */
+int slb_charge_density_raw(slb_grid* g, int nsp, double dv, double* rho_dev);
+int slb_subtract_mean(slb_ctx* ctx, double* dev, int64_t n);
+
+/* PoissonConst (src/poisson.jl:35-59): fctv_imag[x] = imag part of fctv_k[x]
+ * (src/poisson.jl:7-15), each prod(extents) doubles, column-major, host pointers. */
+int slb_poisson_create(slb_ctx* ctx, int nsp, const int64_t* extents, const double* const* fctv_imag,
+                       slb_poisson** out);
+void slb_poisson_destroy(slb_poisson* p);
+/* compute_elfield! (src/poisson.jl:139-144): E_x = real(ifft(fctv_k[x] .* fft(rho))).
+ * E_dev: nsp device pointers, each prod(extents) doubles. */
+int slb_poisson_solve(slb_poisson* p, const double* rho_dev, double* const* E_dev);
+
+/* sum(x .^ 2) for compute_ee (src/util_poisson.jl:156-162); deterministic; synchronises */
+int slb_reduce_sumsq(slb_ctx* ctx, const double* dev, int64_t n, double* host_out);
+/* sum(x) (deterministic; synchronises) */
+int slb_reduce_sum(slb_ctx* ctx, const double* dev, int64_t n, double* host_out);
+/* compute_ke (src/util_poisson.jl:41-53): (dsp*dv) * sum(v_square .* sum_sp f); v_square_dev
+ * holds prod(extents[nsp..)) doubles on the device; scale = dsp*dv.  Synchronises. */
+int slb_kinetic_energy(slb_grid* g, int nsp, const double* v_square_dev, double scale, double* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLB200_H */

@@ -1,0 +1,834 @@
+// slb_api.cu -- C ABI of libslb200.so (see include/slb200.h).  Host-side object management
+// and kernel dispatch; all arithmetic lives in the kernels of slb_sweep.cuh, slb_bspline.cuh
+// and slb_field.cuh.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/slb200.h"
+#include "slb_sweep.cuh"
+#include "slb_bspline.cuh"
+#include "slb_field.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? SLB_E_ALLOC : SLB_E_CUDA, "%s: %s",   \
+                        #expr, cudaGetErrorString(e_));                                         \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                             \
+        (ctx)->launches++;                                                           \
+        cudaError_t e_ = cudaGetLastError();                                         \
+        if (e_ != cudaSuccess) return fail(SLB_E_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct slb_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int64_t launches;
+    cudaEvent_t ev0, ev1;
+    double* red_partial;  // 1024 doubles
+    double* red_out;      // 8 doubles
+    double* host_out;     // pinned, 8 doubles
+    void* scratch;        // growable device scratch (alpha tables, partial sums)
+    size_t scratch_bytes;
+    int sm_count;
+};
+
+struct slb_grid {
+    slb_ctx* ctx;
+    int nd;
+    int64_t ext[SLB_MAX_DIMS];
+    int64_t numel;
+    double *front, *back;
+    bool owned;
+};
+
+struct slb_interp {
+    slb_ctx* ctx;
+    int kind, order, nc;
+    int64_t n;
+    std::vector<double> coef;  // (order+1) x nc
+    bool fast;                 // fits the templated kernels
+    CoefTab tab;
+    double* coef_dev;
+    BsplineDev bsp;            // LU factors / circulant symbol on the device (B-spline kinds)
+};
+
+struct slb_poisson {
+    slb_ctx* ctx;
+    int nsp;
+    int64_t ext[SLB_MAX_DIMS];
+    int64_t ntot;
+    double2* tw[SLB_MAX_DIMS];
+    double* mult[SLB_MAX_DIMS];
+    double2 *wa, *wb, *wc;
+};
+
+static int ensure_scratch(slb_ctx* c, size_t bytes)
+{
+    if (bytes <= c->scratch_bytes) return SLB_OK;
+    if (c->scratch) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaFree(c->scratch));
+        c->scratch = nullptr;
+        c->scratch_bytes = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    CUDA_TRY(cudaMalloc(&c->scratch, want));
+    c->scratch_bytes = want;
+    return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" const char* slb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int slb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int slb_ctx_create(int device_id, void* stream, slb_ctx** out)
+{
+    if (!out) return fail(SLB_E_ARG, "slb_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SLB_E_CUDA, "slb_ctx_create: no CUDA device (%s); libslb200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device_id < 0 || device_id >= n) return fail(SLB_E_ARG, "slb_ctx_create: device %d out of range [0,%d)", device_id, n);
+    CUDA_TRY(cudaSetDevice(device_id));
+    slb_ctx* c = new slb_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device_id;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaMalloc(&c->red_partial, 1024 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->red_out, 8 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost(&c->host_out, 8 * sizeof(double)));
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device_id));
+    *out = c;
+    return SLB_OK;
+}
+
+extern "C" void slb_ctx_destroy(slb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaFree(c->red_partial);
+    cudaFree(c->red_out);
+    cudaFreeHost(c->host_out);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int slb_sync(slb_ctx* c)
+{
+    if (!c) return fail(SLB_E_ARG, "slb_sync: ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SLB_OK;
+}
+
+extern "C" int64_t slb_launch_count(const slb_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int slb_timer_start(slb_ctx* c)
+{
+    if (!c) return fail(SLB_E_ARG, "ctx is NULL");
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    return SLB_OK;
+}
+
+extern "C" int slb_timer_stop(slb_ctx* c, float* ms)
+{
+    if (!c || !ms) return fail(SLB_E_ARG, "ctx/ms is NULL");
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return SLB_OK;
+}
+
+extern "C" int slb_event_create(slb_ctx* c, void** ev)
+{
+    if (!c || !ev) return fail(SLB_E_ARG, "slb_event_create: NULL argument");
+    cudaEvent_t e;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventCreate(&e));
+    *ev = (void*)e;
+    return SLB_OK;
+}
+
+extern "C" int slb_event_record(slb_ctx* c, void* ev)
+{
+    if (!c || !ev) return fail(SLB_E_ARG, "slb_event_record: NULL argument");
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)ev, c->stream));
+    return SLB_OK;
+}
+
+extern "C" int slb_event_elapsed_ms(void* e0, void* e1, float* ms)
+{
+    if (!e0 || !e1 || !ms) return fail(SLB_E_ARG, "slb_event_elapsed_ms: NULL argument");
+    CUDA_TRY(cudaEventSynchronize((cudaEvent_t)e1));
+    CUDA_TRY(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1));
+    return SLB_OK;
+}
+
+extern "C" int slb_event_destroy(void* ev)
+{
+    if (ev) CUDA_TRY(cudaEventDestroy((cudaEvent_t)ev));
+    return SLB_OK;
+}
+
+extern "C" int slb_malloc(slb_ctx* c, int64_t bytes, void** out)
+{
+    if (!c || !out || bytes < 0) return fail(SLB_E_ARG, "slb_malloc: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMalloc(out, (size_t)(bytes > 0 ? bytes : 8)));
+    return SLB_OK;
+}
+
+extern "C" int slb_free(slb_ctx* c, void* dev)
+{
+    if (!c) return fail(SLB_E_ARG, "ctx is NULL");
+    if (dev) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaFree(dev));
+    }
+    return SLB_OK;
+}
+
+extern "C" int slb_host_alloc(int64_t bytes, void** out)
+{
+    if (!out || bytes < 0) return fail(SLB_E_ARG, "slb_host_alloc: bad argument");
+    CUDA_TRY(cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 8)));
+    return SLB_OK;
+}
+
+extern "C" int slb_host_free(void* host)
+{
+    if (host) CUDA_TRY(cudaFreeHost(host));
+    return SLB_OK;
+}
+
+extern "C" int slb_memcpy_h2d(slb_ctx* c, void* dev, const void* host, int64_t bytes)
+{
+    if (!c || !dev || !host || bytes < 0) return fail(SLB_E_ARG, "slb_memcpy_h2d: bad argument");
+    CUDA_TRY(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    return SLB_OK;
+}
+
+extern "C" int slb_memcpy_d2h(slb_ctx* c, void* host, const void* dev, int64_t bytes)
+{
+    if (!c || !dev || !host || bytes < 0) return fail(SLB_E_ARG, "slb_memcpy_d2h: bad argument");
+    CUDA_TRY(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// grid
+// ------------------------------------------------------------------------------------------
+static int grid_init(slb_ctx* c, int nd, const int64_t* ext, slb_grid** out)
+{
+    if (!c || !ext || !out) return fail(SLB_E_ARG, "slb_grid_create: NULL argument");
+    if (nd < 1 || nd > SLB_MAX_DIMS) return fail(SLB_E_ARG, "slb_grid_create: ndims=%d not in [1,%d]", nd, SLB_MAX_DIMS);
+    int64_t numel = 1;
+    for (int d = 0; d < nd; ++d) {
+        if (ext[d] < 1 || ext[d] > (int64_t)1 << 30) return fail(SLB_E_ARG, "slb_grid_create: extent[%d]=%lld invalid", d, (long long)ext[d]);
+        numel *= ext[d];
+        if (numel > ((int64_t)1 << 40)) return fail(SLB_E_ARG, "slb_grid_create: grid too large");
+    }
+    slb_grid* g = new slb_grid();
+    g->ctx = c;
+    g->nd = nd;
+    for (int d = 0; d < nd; ++d) g->ext[d] = ext[d];
+    g->numel = numel;
+    g->front = g->back = nullptr;
+    g->owned = false;
+    *out = g;
+    return SLB_OK;
+}
+
+extern "C" int slb_grid_create(slb_ctx* c, int nd, const int64_t* ext, slb_grid** out)
+{
+    int rc = grid_init(c, nd, ext, out);
+    if (rc) return rc;
+    slb_grid* g = *out;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(&g->front, g->numel * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->back, g->numel * sizeof(double));
+    if (e != cudaSuccess) {
+        if (g->front) cudaFree(g->front);
+        delete g;
+        *out = nullptr;
+        cudaGetLastError();
+        return fail(SLB_E_ALLOC, "slb_grid_create: cudaMalloc of 2 x %lld bytes failed: %s",
+                    (long long)(g->numel * 8), cudaGetErrorString(e));
+    }
+    g->owned = true;
+    return SLB_OK;
+}
+
+extern "C" int slb_grid_create_external(slb_ctx* c, int nd, const int64_t* ext, double* front, double* back, slb_grid** out)
+{
+    if (!front || !back || front == back) return fail(SLB_E_ARG, "slb_grid_create_external: need two distinct device buffers");
+    int rc = grid_init(c, nd, ext, out);
+    if (rc) return rc;
+    (*out)->front = front;
+    (*out)->back = back;
+    return SLB_OK;
+}
+
+extern "C" void slb_grid_destroy(slb_grid* g)
+{
+    if (!g) return;
+    if (g->owned) {
+        cudaStreamSynchronize(g->ctx->stream);
+        cudaFree(g->front);
+        cudaFree(g->back);
+    }
+    delete g;
+}
+
+extern "C" int slb_grid_upload(slb_grid* g, const double* host)
+{
+    if (!g || !host) return fail(SLB_E_ARG, "slb_grid_upload: NULL argument");
+    CUDA_TRY(cudaMemcpyAsync(g->front, host, g->numel * sizeof(double), cudaMemcpyHostToDevice, g->ctx->stream));
+    return SLB_OK;
+}
+
+extern "C" int slb_grid_download(const slb_grid* g, double* host)
+{
+    if (!g || !host) return fail(SLB_E_ARG, "slb_grid_download: NULL argument");
+    CUDA_TRY(cudaMemcpyAsync(host, g->front, g->numel * sizeof(double), cudaMemcpyDeviceToHost, g->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->ctx->stream));
+    return SLB_OK;
+}
+
+extern "C" double* slb_grid_front(const slb_grid* g) { return g ? g->front : nullptr; }
+extern "C" double* slb_grid_back(const slb_grid* g) { return g ? g->back : nullptr; }
+extern "C" int slb_grid_swap(slb_grid* g)
+{
+    if (!g) return fail(SLB_E_ARG, "grid is NULL");
+    double* t = g->front;
+    g->front = g->back;
+    g->back = t;
+    return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// interpolation object
+// ------------------------------------------------------------------------------------------
+extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, const double* coef, int nc,
+                                 const double* node_vals, slb_interp** out)
+{
+    if (!c || !coef || !out) return fail(SLB_E_ARG, "slb_interp_create: NULL argument");
+    *out = nullptr;
+    if (kind < SLB_LAGRANGE || kind > SLB_HERMITE) return fail(SLB_E_ARG, "slb_interp_create: unknown kind %d", kind);
+    if (order < 1 || order > SLB_MAX_ORDER) return fail(SLB_E_ARG, "slb_interp_create: order=%d not in [1,%d]", order, SLB_MAX_ORDER);
+    if (nc < 1 || nc > 2 * SLB_MAX_ORDER + 4) return fail(SLB_E_ARG, "slb_interp_create: ncoef=%d invalid", nc);
+    bool bs = (kind == SLB_BSPLINE_LU || kind == SLB_BSPLINE_FFT);
+    if (bs) {
+        if (!node_vals) return fail(SLB_E_ARG, "slb_interp_create: B-spline kinds need node_vals");
+        // src/bsplinelu.jl:257-261; even orders are singular for BSplineFFT as well
+        if (order % 2 == 0) return fail(SLB_E_ARG, "order=%d BSpline for even order is not implemented n=%lld", order, (long long)n);
+        if (kind == SLB_BSPLINE_FFT && (n < 1 || (n & (n - 1)) != 0))
+            return fail(SLB_E_ARG, "BSplineFFT: n=%lld must be a power of two (src/fftbig.jl:57)", (long long)n);
+        if (n < order + 1) return fail(SLB_E_ARG, "B-spline: n=%lld must exceed order=%d", (long long)n, order);
+    }
+    slb_interp* it = new slb_interp();
+    it->ctx = c;
+    it->kind = kind;
+    it->order = order;
+    it->nc = nc;
+    it->n = n;
+    it->coef.assign(coef, coef + (size_t)(order + 1) * nc);
+    it->fast = (order + 1 <= SLB_P1MAX && order + 1 >= 2 && nc <= SLB_NCMAX);
+    memset(&it->tab, 0, sizeof(it->tab));
+    if (it->fast)
+        for (int j = 0; j <= order; ++j)
+            for (int k = 0; k < nc; ++k) it->tab.c[j * SLB_NCMAX + k] = coef[(size_t)j * nc + k];
+    it->coef_dev = nullptr;
+    memset(&it->bsp, 0, sizeof(it->bsp));
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(&it->coef_dev, it->coef.size() * sizeof(double));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(it->coef_dev, it->coef.data(), it->coef.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        delete it;
+        cudaGetLastError();
+        return fail(SLB_E_CUDA, "slb_interp_create: %s", cudaGetErrorString(e));
+    }
+    if (bs) {
+        std::string msg;
+        int rc = bspline_build(kind, order, n, node_vals, &it->bsp, msg);
+        if (rc) {
+            cudaFree(it->coef_dev);
+            delete it;
+            return fail(rc, "slb_interp_create: %s", msg.c_str());
+        }
+    }
+    *out = it;
+    return SLB_OK;
+}
+
+extern "C" void slb_interp_destroy(slb_interp* it)
+{
+    if (!it) return;
+    cudaStreamSynchronize(it->ctx->stream);
+    cudaFree(it->coef_dev);
+    bspline_free(&it->bsp);
+    delete it;
+}
+
+// ------------------------------------------------------------------------------------------
+// sweep dispatch
+// ------------------------------------------------------------------------------------------
+struct View {
+    long long inner, outer;
+    int n;
+};
+
+static View make_view(const slb_grid* g, int dim)
+{
+    View v;
+    v.inner = 1;
+    v.outer = 1;
+    for (int d = 0; d < dim; ++d) v.inner *= g->ext[d];
+    for (int d = dim + 1; d < g->nd; ++d) v.outer *= g->ext[d];
+    v.n = (int)g->ext[dim];
+    return v;
+}
+
+template <int P1>
+static void launch_strided(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
+                           const slb_interp* it, const OutMap& om, bool exact)
+{
+    long long nlines = v.inner * v.outer;
+    unsigned blocks = (unsigned)((nlines + 127) / 128);
+    if (exact)
+        k_sweep_strided<P1, true><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om);
+    else
+        k_sweep_strided<P1, false><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om);
+}
+
+template <int P1, int R>
+static void launch_contig_r(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
+                            const slb_interp* it, bool exact)
+{
+    long long nlines = v.outer;
+    long long nb = (nlines + 7) / 8;
+    long long cap = (long long)c->sm_count * 64;
+    unsigned blocks = (unsigned)(nb < cap ? nb : cap);
+    if (exact)
+        k_sweep_contig<P1, R, true><<<blocks, 256, 0, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc);
+    else
+        k_sweep_contig<P1, R, false><<<blocks, 256, 0, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc);
+}
+
+template <int P1>
+static void launch_contig(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
+                          const slb_interp* it, bool exact)
+{
+    if (v.n >= 96)
+        launch_contig_r<P1, 4>(c, in, out, v, am, it, exact);
+    else if (v.n >= 48)
+        launch_contig_r<P1, 2>(c, in, out, v, am, it, exact);
+    else
+        launch_contig_r<P1, 1>(c, in, out, v, am, it, exact);
+}
+
+#define SLB_FOR_P1(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
+
+// stencil pass in -> out along `dim`; `in` already holds sol(interp, f)
+static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const double* in, double* out,
+                          const AlphaMap& am, int flags, const OutMap* omp)
+{
+    slb_ctx* c = g->ctx;
+    View v = make_view(g, dim);
+    bool exact = (flags & SLB_SWEEP_EXACT) != 0;
+    OutMap om;
+    if (omp)
+        om = *omp;
+    else {
+        om.kc = v.n;
+        om.kblk = 0;
+        om.bstride = (long long)v.n * v.inner;
+    }
+    int P1 = it->order + 1;
+    if (it->fast) {
+        if (dim == 0 && !omp) {
+            switch (P1) {
+#define X(P) case P: launch_contig<P>(c, in, out, v, am, it, exact); break;
+                SLB_FOR_P1(X)
+#undef X
+            }
+        } else {
+            switch (P1) {
+#define X(P) case P: launch_strided<P>(c, in, out, v, am, it, om, exact); break;
+                SLB_FOR_P1(X)
+#undef X
+            }
+        }
+    } else {
+        if (omp) return fail(SLB_E_UNSUPPORTED, "re-shard output mapping needs order+1 <= %d", SLB_P1MAX);
+        long long nlines = v.inner * v.outer;
+        unsigned blocks = (unsigned)((nlines + 127) / 128);
+        k_sweep_generic<<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->coef_dev, P1, it->nc, exact ? 1 : 0);
+    }
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+static int build_alpha_map(slb_grid* g, int dim, const double* alpha_tab, int64_t alpha_len,
+                           const int64_t* astr, double scale, int on_device, AlphaMap* am)
+{
+    slb_ctx* c = g->ctx;
+    if (!alpha_tab || alpha_len < 1 || !astr) return fail(SLB_E_ARG, "slb_sweep: alpha table missing");
+    int64_t maxoff = 0;
+    for (int d = 0; d < g->nd; ++d) {
+        if (d == dim) continue;
+        if (astr[d] < 0) return fail(SLB_E_ARG, "slb_sweep: negative alpha stride");
+        maxoff += astr[d] * (g->ext[d] - 1);
+    }
+    if (maxoff >= alpha_len) return fail(SLB_E_ARG, "slb_sweep: alpha table too short (%lld needed, %lld given)", (long long)maxoff + 1, (long long)alpha_len);
+    const double* tab = alpha_tab;
+    if (!on_device) {
+        int rc = ensure_scratch(c, (size_t)alpha_len * sizeof(double));
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->scratch, alpha_tab, (size_t)alpha_len * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        tab = (const double*)c->scratch;
+    }
+    memset(am, 0, sizeof(*am));
+    am->tab = tab;
+    am->scale = scale;
+    int nlo = 0, nhi = 0;
+    bool lo_dep = false;
+    for (int d = 0; d < dim; ++d) lo_dep |= (astr[d] != 0);
+    if (lo_dep)
+        for (int d = 0; d < dim; ++d) {
+            am->ext_lo[nlo] = (unsigned)g->ext[d];
+            am->str_lo[nlo] = astr[d];
+            nlo++;
+        }
+    int last = dim;
+    for (int d = dim + 1; d < g->nd; ++d)
+        if (astr[d] != 0) last = d;
+    for (int d = dim + 1; d <= last; ++d) {
+        am->ext_hi[nhi] = (unsigned)g->ext[d];
+        am->str_hi[nhi] = astr[d];
+        nhi++;
+    }
+    am->nlo = nlo;
+    am->nhi = nhi;
+    return SLB_OK;
+}
+
+static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+                      const int64_t* astr, double scale, int on_device, int flags, const OutMap* omp)
+{
+    if (!g || !it) return fail(SLB_E_ARG, "slb_sweep: NULL argument");
+    if (dim < 0 || dim >= g->nd) return fail(SLB_E_ARG, "slb_sweep: dim=%d out of range", dim);
+    slb_ctx* c = g->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    View v = make_view(g, dim);
+    bool bs = (it->kind == SLB_BSPLINE_LU || it->kind == SLB_BSPLINE_FFT);
+    if (bs && it->n != v.n) return fail(SLB_E_ARG, "slb_sweep: B-spline object built for n=%lld, line length is %d", (long long)it->n, v.n);
+    if (v.inner >= ((long long)1 << 31) || v.outer >= ((long long)1 << 31)) return fail(SLB_E_UNSUPPORTED, "slb_sweep: view too large");
+    AlphaMap am;
+    int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, on_device, &am);
+    if (rc) return rc;
+    const double* src = g->front;
+    if (bs) {
+        // c = sol(interp, line) for every line: front -> back -> (stencil) -> front
+        rc = bspline_presolve(c->stream, &it->bsp, g->front, g->back, v.inner, v.n, v.outer, &c->launches);
+        if (rc) return fail(rc, "slb_sweep: B-spline pre-solve launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (omp) return fail(SLB_E_UNSUPPORTED, "re-shard output mapping with B-splines is not implemented");
+        rc = launch_stencil(g, dim, it, g->back, g->front, am, flags, nullptr);
+        return rc;  // result is in front: no swap
+    }
+    rc = launch_stencil(g, dim, it, src, g->back, am, flags, omp);
+    if (rc) return rc;
+    return slb_grid_swap(g);
+}
+
+extern "C" int slb_sweep(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+                         const int64_t* astr, double scale, int on_device, int flags)
+{
+    return sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, nullptr);
+}
+
+extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)
+{
+    if (!g || !it) return fail(SLB_E_ARG, "slb_presolve: NULL argument");
+    if (dim < 0 || dim >= g->nd) return fail(SLB_E_ARG, "slb_presolve: dim out of range");
+    bool bs = (it->kind == SLB_BSPLINE_LU || it->kind == SLB_BSPLINE_FFT);
+    if (!bs) return SLB_OK;  // sol(interp, b) = b, src/interpolation.jl:40
+    View v = make_view(g, dim);
+    if (it->n != v.n) return fail(SLB_E_ARG, "slb_presolve: B-spline object built for n=%lld, line length is %d", (long long)it->n, v.n);
+    slb_ctx* c = g->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = bspline_presolve(c->stream, &it->bsp, g->front, g->back, v.inner, v.n, v.outer, &c->launches);
+    if (rc) return fail(rc, "slb_presolve: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return slb_grid_swap(g);
+}
+
+// ------------------------------------------------------------------------------------------
+// charge density, reductions
+// ------------------------------------------------------------------------------------------
+static int reduce_to_dev(slb_ctx* c, const double* dev, int64_t n, int mode, double scale, double* out_dev)
+{
+    long long nb = (n + 256 * 8 - 1) / (256 * 8);
+    if (nb > 1024) nb = 1024;
+    if (nb < 1) nb = 1;
+    if (mode == 1)
+        k_reduce_partial<1><<<(unsigned)nb, 256, 0, c->stream>>>(dev, n, c->red_partial);
+    else
+        k_reduce_partial<0><<<(unsigned)nb, 256, 0, c->stream>>>(dev, n, c->red_partial);
+    LAUNCH_CHECK(c);
+    k_reduce_final<<<1, 256, 0, c->stream>>>(c->red_partial, (int)nb, scale, out_dev);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+static int reduce_to_host(slb_ctx* c, const double* dev, int64_t n, int mode, double* host_out)
+{
+    if (!c || !dev || !host_out || n < 1) return fail(SLB_E_ARG, "slb_reduce: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = reduce_to_dev(c, dev, n, mode, 1.0, c->red_out);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->host_out, c->red_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *host_out = c->host_out[0];
+    return SLB_OK;
+}
+
+extern "C" int slb_reduce_sumsq(slb_ctx* c, const double* dev, int64_t n, double* host_out) { return reduce_to_host(c, dev, n, 1, host_out); }
+extern "C" int slb_reduce_sum(slb_ctx* c, const double* dev, int64_t n, double* host_out) { return reduce_to_host(c, dev, n, 0, host_out); }
+
+extern "C" int slb_subtract_mean(slb_ctx* c, double* dev, int64_t n)
+{
+    if (!c || !dev || n < 1) return fail(SLB_E_ARG, "slb_subtract_mean: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = reduce_to_dev(c, dev, n, 0, 1.0 / (double)n, c->red_out + 1);
+    if (rc) return rc;
+    k_sub_scalar<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(dev, n, c->red_out + 1);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+extern "C" int slb_charge_density_raw(slb_grid* g, int nsp, double dv, double* rho_dev)
+{
+    if (!g || !rho_dev) return fail(SLB_E_ARG, "slb_charge_density: NULL argument");
+    if (nsp < 1 || nsp >= g->nd) return fail(SLB_E_ARG, "slb_charge_density: nsp=%d must be in [1,%d)", nsp, g->nd);
+    slb_ctx* c = g->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    long long ns = 1, nv = 1;
+    for (int d = 0; d < nsp; ++d) ns *= g->ext[d];
+    for (int d = nsp; d < g->nd; ++d) nv *= g->ext[d];
+    long long xt = (ns + 31) / 32;
+    // enough blocks to fill the machine a few times over, at least 64 velocity rows per block
+    long long want = (long long)c->sm_count * 16;
+    long long nchunk = (want + xt - 1) / xt;
+    long long maxchunk = (nv + 63) / 64;
+    if (nchunk > maxchunk) nchunk = maxchunk;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 65535) nchunk = 65535;
+    long long chunk = (nv + nchunk - 1) / nchunk;
+    nchunk = (nv + chunk - 1) / chunk;
+    int rc = ensure_scratch(c, (size_t)(nchunk * ns) * sizeof(double));
+    if (rc) return rc;
+    double* partial = (double*)c->scratch;
+    dim3 grid((unsigned)xt, (unsigned)nchunk), block(32, 8);
+    k_charge_partial<<<grid, block, 0, c->stream>>>(g->front, ns, nv, chunk, partial);
+    LAUNCH_CHECK(c);
+    k_charge_final<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(partial, ns, (int)nchunk, dv, rho_dev);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+extern "C" int slb_charge_density(slb_grid* g, int nsp, double dv, double* rho_dev)
+{
+    int rc = slb_charge_density_raw(g, nsp, dv, rho_dev);
+    if (rc) return rc;
+    long long ns = 1;
+    for (int d = 0; d < nsp; ++d) ns *= g->ext[d];
+    return slb_subtract_mean(g->ctx, rho_dev, ns);
+}
+
+extern "C" int slb_kinetic_energy(slb_grid* g, int nsp, const double* vsq_dev, double scale, double* host_out)
+{
+    if (!g || !vsq_dev || !host_out) return fail(SLB_E_ARG, "slb_kinetic_energy: NULL argument");
+    if (nsp < 1 || nsp >= g->nd) return fail(SLB_E_ARG, "slb_kinetic_energy: nsp out of range");
+    slb_ctx* c = g->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    long long ns = 1, nv = 1;
+    for (int d = 0; d < nsp; ++d) ns *= g->ext[d];
+    for (int d = nsp; d < g->nd; ++d) nv *= g->ext[d];
+    if (nv > 0x7fffffffLL) return fail(SLB_E_UNSUPPORTED, "slb_kinetic_energy: velocity grid too large");
+    int rc = ensure_scratch(c, (size_t)nv * sizeof(double));
+    if (rc) return rc;
+    double* partial = (double*)c->scratch;
+    k_ke_partial<<<(unsigned)nv, 256, 0, c->stream>>>(g->front, ns, vsq_dev, partial);
+    LAUNCH_CHECK(c);
+    rc = reduce_to_dev(c, partial, nv, 0, scale, c->red_out);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->host_out, c->red_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *host_out = c->host_out[0];
+    return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Poisson
+// ------------------------------------------------------------------------------------------
+extern "C" void slb_poisson_destroy(slb_poisson* p)
+{
+    if (!p) return;
+    cudaStreamSynchronize(p->ctx->stream);
+    for (int d = 0; d < SLB_MAX_DIMS; ++d) {
+        if (p->tw[d]) cudaFree(p->tw[d]);
+        if (p->mult[d]) cudaFree(p->mult[d]);
+    }
+    if (p->wa) cudaFree(p->wa);
+    if (p->wb) cudaFree(p->wb);
+    if (p->wc) cudaFree(p->wc);
+    delete p;
+}
+
+extern "C" int slb_poisson_create(slb_ctx* c, int nsp, const int64_t* ext, const double* const* fctv_imag, slb_poisson** out)
+{
+    if (!c || !ext || !fctv_imag || !out) return fail(SLB_E_ARG, "slb_poisson_create: NULL argument");
+    *out = nullptr;
+    if (nsp < 1 || nsp > 3) return fail(SLB_E_ARG, "slb_poisson_create: nsp=%d not in [1,3]", nsp);
+    CUDA_TRY(cudaSetDevice(c->device));
+    slb_poisson* p = new slb_poisson();
+    memset(p, 0, sizeof(*p));
+    p->ctx = c;
+    p->nsp = nsp;
+    p->ntot = 1;
+    for (int d = 0; d < nsp; ++d) {
+        if (ext[d] < 1 || ext[d] > 65536) {
+            delete p;
+            return fail(SLB_E_ARG, "slb_poisson_create: extent[%d] invalid", d);
+        }
+        p->ext[d] = ext[d];
+        p->ntot *= ext[d];
+    }
+    cudaError_t e = cudaSuccess;
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    for (int d = 0; d < nsp && e == cudaSuccess; ++d) {
+        int n = (int)ext[d];
+        std::vector<double2> tw(n);
+        for (int m = 0; m < n; ++m) {  // tw[m] = exp(-2 pi i m / n)
+            long double ang = PI2 * (long double)m / (long double)n;
+            tw[m] = make_double2((double)cosl(ang), (double)(-sinl(ang)));
+        }
+        e = cudaMalloc(&p->tw[d], n * sizeof(double2));
+        if (e == cudaSuccess) e = cudaMemcpy(p->tw[d], tw.data(), n * sizeof(double2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&p->mult[d], p->ntot * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(p->mult[d], fctv_imag[d], p->ntot * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&p->wa, p->ntot * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->wb, p->ntot * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->wc, p->ntot * sizeof(double2));
+    if (e != cudaSuccess) {
+        slb_poisson_destroy(p);
+        cudaGetLastError();
+        return fail(SLB_E_CUDA, "slb_poisson_create: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return SLB_OK;
+}
+
+extern "C" int slb_poisson_solve(slb_poisson* p, const double* rho_dev, double* const* E_dev)
+{
+    if (!p || !rho_dev || !E_dev) return fail(SLB_E_ARG, "slb_poisson_solve: NULL argument");
+    slb_ctx* c = p->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    long long ntot = p->ntot;
+    unsigned blocks = (unsigned)((ntot + 127) / 128);
+    // forward transform over every space dim: rho -> wa (spectrum)
+    double2* cur = p->wa;
+    double2* nxt = p->wb;
+    long long inner = 1;
+    for (int d = 0; d < p->nsp; ++d) {
+        int n = (int)p->ext[d];
+        if (d == 0)
+            k_dft_dim<true, false><<<blocks, 128, 0, c->stream>>>(rho_dev, cur, inner, n, ntot, p->tw[d]);
+        else {
+            k_dft_dim<false, false><<<blocks, 128, 0, c->stream>>>(cur, nxt, inner, n, ntot, p->tw[d]);
+            double2* t = cur; cur = nxt; nxt = t;
+        }
+        LAUNCH_CHECK(c);
+        inner *= n;
+    }
+    double2* spec = cur;
+    double2* w1 = (spec == p->wa) ? p->wb : p->wa;
+    double2* w2 = p->wc;
+    for (int x = 0; x < p->nsp; ++x) {
+        if (!E_dev[x]) return fail(SLB_E_ARG, "slb_poisson_solve: E_dev[%d] is NULL", x);
+        k_mult_imag<<<(unsigned)((ntot + 255) / 256), 256, 0, c->stream>>>(spec, p->mult[x], w1, ntot);
+        LAUNCH_CHECK(c);
+        double2 *a = w1, *b = w2;
+        inner = 1;
+        for (int d = 0; d < p->nsp; ++d) {
+            int n = (int)p->ext[d];
+            k_dft_dim<false, true><<<blocks, 128, 0, c->stream>>>(a, b, inner, n, ntot, p->tw[d]);
+            LAUNCH_CHECK(c);
+            double2* t = a; a = b; b = t;
+            inner *= n;
+        }
+        k_real_part<<<(unsigned)((ntot + 255) / 256), 256, 0, c->stream>>>(a, E_dev[x], ntot);
+        LAUNCH_CHECK(c);
+    }
+    return SLB_OK;
+}

@@ -1,0 +1,188 @@
+"""ctypes binding of libslb200.so (include/slb200.h).  The product path has no CPU
+fallback: a missing library or a missing CUDA device raises immediately."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libslb200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int64_p = C.POINTER(C.c_int64)
+c_void_pp = C.POINTER(C.c_void_p)
+
+# every symbol include/slb200.h declares: (name, restype, argtypes)
+SIGNATURES = [
+    ("slb_ctx_create", C.c_int, [C.c_int, C.c_void_p, c_void_pp]),
+    ("slb_ctx_destroy", None, [C.c_void_p]),
+    ("slb_last_error", C.c_char_p, []),
+    ("slb_sync", C.c_int, [C.c_void_p]),
+    ("slb_device_count", C.c_int, []),
+    ("slb_launch_count", C.c_int64, [C.c_void_p]),
+    ("slb_timer_start", C.c_int, [C.c_void_p]),
+    ("slb_timer_stop", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    ("slb_event_create", C.c_int, [C.c_void_p, c_void_pp]),
+    ("slb_event_record", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_event_elapsed_ms", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    ("slb_event_destroy", C.c_int, [C.c_void_p]),
+    ("slb_malloc", C.c_int, [C.c_void_p, C.c_int64, c_void_pp]),
+    ("slb_free", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_host_alloc", C.c_int, [C.c_int64, c_void_pp]),
+    ("slb_host_free", C.c_int, [C.c_void_p]),
+    ("slb_memcpy_h2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    ("slb_memcpy_d2h", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    ("slb_grid_create", C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_void_pp]),
+    ("slb_grid_create_external", C.c_int, [C.c_void_p, C.c_int, c_int64_p, C.c_void_p, C.c_void_p, c_void_pp]),
+    ("slb_grid_destroy", None, [C.c_void_p]),
+    ("slb_grid_upload", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_grid_download", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_grid_front", C.c_void_p, [C.c_void_p]),
+    ("slb_grid_back", C.c_void_p, [C.c_void_p]),
+    ("slb_grid_swap", C.c_int, [C.c_void_p]),
+    ("slb_interp_create", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, c_double_p, C.c_int, c_double_p, c_void_pp]),
+    ("slb_interp_destroy", None, [C.c_void_p]),
+    ("slb_sweep", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int]),
+    ("slb_presolve", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("slb_charge_density", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    ("slb_charge_density_raw", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    ("slb_subtract_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    ("slb_poisson_create", C.c_int, [C.c_void_p, C.c_int, c_int64_p, C.POINTER(c_double_p), c_void_pp]),
+    ("slb_poisson_destroy", None, [C.c_void_p]),
+    ("slb_poisson_solve", C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
+    ("slb_reduce_sumsq", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
+    ("slb_reduce_sum", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
+    ("slb_kinetic_energy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, c_double_p]),
+]
+
+SLB_SWEEP_EXACT = 1
+
+
+class SlbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libslb200.so; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SlbError(
+                f"{LIB_PATH} is missing: build it with semilagrangian.jl_b200/build.sh "
+                "(or __graft_entry__.build()).  There is no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SIGNATURES:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().slb_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)  # ArgumentError / DomainError of the reference
+        raise SlbError(f"libslb200 error {rc}: {msg}")
+
+
+def i64(seq):
+    return (C.c_int64 * len(seq))(*[int(x) for x in seq])
+
+
+def dptr(a):
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64
+    return a.ctypes.data_as(c_double_p)
+
+
+class Context:
+    """One per process and GPU (slb_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().slb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        check(lib().slb_sync(self.h))
+
+    def launch_count(self):
+        return int(lib().slb_launch_count(self.h))
+
+    def timer_start(self):
+        check(lib().slb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().slb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def event(self):
+        e = C.c_void_p()
+        check(lib().slb_event_create(self.h, C.byref(e)))
+        return e
+
+    def record(self, ev):
+        check(lib().slb_event_record(self.h, ev))
+
+    @staticmethod
+    def elapsed_ms(e0, e1):
+        ms = C.c_float()
+        check(lib().slb_event_elapsed_ms(e0, e1, C.byref(ms)))
+        return ms.value
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        check(lib().slb_malloc(self.h, int(nbytes), C.byref(p)))
+        return p
+
+    def free(self, p):
+        check(lib().slb_free(self.h, p))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        p = self.malloc(arr.nbytes)
+        check(lib().slb_memcpy_h2d(self.h, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        self.sync()
+        return p
+
+    def to_host(self, p, n):
+        out = np.empty(int(n), dtype=np.float64)
+        check(lib().slb_memcpy_d2h(self.h, out.ctypes.data_as(C.c_void_p), p, out.nbytes))
+        self.sync()
+        return out
+
+    def close(self):
+        if self.h:
+            lib().slb_ctx_destroy(self.h)
+            self.h = None
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        n = lib().slb_device_count()
+        if n == 0:
+            raise SlbError("no CUDA device visible: libslb200 has no CPU fallback")
+        _default_ctx = Context(dev % n)
+    return _default_ctx
+
+
+def pinned_empty(shape, order="F"):
+    """float64 numpy array backed by pinned host memory (cudaHostAlloc)."""
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    check(lib().slb_host_alloc(n * 8, C.byref(p)))
+    buf = (C.c_double * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.float64).reshape(shape, order=order)
+    return arr, p

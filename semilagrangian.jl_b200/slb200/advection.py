@@ -1,0 +1,217 @@
+"""Advection / AdvectionData / advection! -- host mirror of src/advection.jl.
+
+The split-step state machine (StateAdv, state schedule, coefficient schedule, nextstate!)
+is the reference's, unchanged in behaviour (src/advection.jl:10-20, :88-140, :152-163,
+:358-367).  What changes is where the data lives: AdvectionData owns a device-resident grid
+(slb_grid: f plus an equally sized scratch array, the counterpart of `data` + `bufdata`,
+src/advection.jl:264-267) and `advection(advd)` (== advection!, :594-704) is a single
+slb_sweep call -- no permutedims!, no per-line host loop, f never leaves HBM.
+
+Displacement providers (AbstractExtDataAdv, src/advection.jl:172, docs/src/extdataadv.md):
+`initcoef(advd)` is kept; the per-line callback `getalpha(parext, advd, indext)` cannot run
+on the device, so a provider instead implements
+    alpha_table(advd) -> (table, strides, scale, on_device)
+meaning  alpha(line) = scale * table[sum_d idx_d * strides[d]]  over the line's other-dim
+indices -- which is exactly how the reference's own providers index their `bufcur` arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .splitting import strangsplit
+
+
+def modone(ind, n):
+    """src/util.jl:73"""
+    return (ind - 1) % n + 1
+
+
+def invperm(p):
+    q = [0] * len(p)
+    for i, v in enumerate(p):
+        q[v - 1] = i + 1
+    return q
+
+
+class StateAdv:
+    """src/advection.jl:10-20 (perm is 1-based, as in the reference API)"""
+
+    def __init__(self, ind, perm, ndims, stcoef, isconstdec):
+        perm = [int(v) for v in perm]
+        if sorted(perm) != list(range(1, len(perm) + 1)):
+            raise ValueError(f"state {ind}: perm={perm} is not a permutation")
+        self.ind, self.perm, self.invp = ind, perm, invperm(perm)
+        self.ndims, self.stcoef, self.isconstdec = int(ndims), int(stcoef), bool(isconstdec)
+
+
+class AbstractExtDataAdv:
+    """Displacement provider interface (src/advection.jl:172, :221-224)."""
+
+    def initcoef(self, advd):
+        raise NotImplementedError
+
+    def alpha_table(self, advd):
+        raise NotImplementedError
+
+
+class Advection:
+    """Advection(t_mesh, t_interp, dt_base, states; tab_coef=strangsplit(dt_base))
+    -- src/advection.jl:73-141.  `states` = [(perm, ndims, stcoef, isconstdec), ...]."""
+
+    def __init__(self, t_mesh, t_interp, dt_base, states, tab_coef=None, ctx=None):
+        N = len(t_mesh)
+        if len(t_interp) != N:
+            raise ValueError(f"size of vector of Interpolation must be equal to N={N}")
+        self.N = N
+        self.sizeall = tuple(len(m) for m in t_mesh)
+        self.t_mesh = tuple(t_mesh)
+        self.t_interp = list(t_interp)
+        self.dt_base = float(dt_base)
+        self.states = [StateAdv(i + 1, *s) for i, s in enumerate(states)]
+        for s in self.states:
+            if len(s.perm) != N:
+                raise ValueError("state permutation length must equal the number of dimensions")
+        self.tab_coef = [float(c) for c in (strangsplit(self.dt_base) if tab_coef is None else tab_coef)]
+        self.maxcoef = max(s.stcoef for s in self.states)
+        restcoef = len(self.tab_coef) % self.maxcoef
+        nbstatesplus = sum(1 for s in self.states if s.stcoef == restcoef)
+        self.nbstates = (len(self.tab_coef) // self.maxcoef) * len(self.states) + nbstatesplus
+        self.ctx = ctx
+
+    # src/advection.jl:150-163
+    def getst(self, x):
+        return self.states[modone(x, len(self.states)) - 1]
+
+    def getstcoef(self, x):
+        return ((x - 1) // len(self.states)) * self.maxcoef + self.getst(x).stcoef
+
+    def getcur_t(self, x):
+        return self.tab_coef[self.getstcoef(x) - 1]
+
+    def getinterp(self, x):
+        st = self.getst(x)
+        return [self.t_interp[d - 1] for d in st.perm[: st.ndims]]
+
+
+def sizeall(adv):
+    return adv.sizeall
+
+
+class AdvectionData:
+    """AdvectionData(adv, data, parext; time_init=0) -- src/advection.jl:229-313.
+    Copies `data` to the device (the reference copies it too, :264-267)."""
+
+    def __init__(self, adv, data, parext, time_init=0.0, ctx=None):
+        data = np.asarray(data)
+        if tuple(data.shape) != adv.sizeall:
+            raise ValueError(f"size(data)={tuple(data.shape)} it must be {adv.sizeall}")
+        self.adv = adv
+        self.ctx = ctx or adv.ctx or _lib.default_context()
+        self.state_gen = 1
+        self.time_cur = float(time_init)
+        self.parext = parext
+        self.flags = 0
+        h = C.c_void_p()
+        _lib.check(_lib.lib().slb_grid_create(self.ctx.h, adv.N, _lib.i64(adv.sizeall), C.byref(h)))
+        self.grid = h
+        self.upload(data)
+        # mesh nodes stay on the device: shift tables for space sweeps (src/poisson.jl:191-203)
+        self._points_dev = {}
+
+    # -- data movement ---------------------------------------------------------------
+    def upload(self, data):
+        host = np.asfortranarray(data, dtype=np.float64)
+        _lib.check(_lib.lib().slb_grid_upload(self.grid, host.ctypes.data_as(C.c_void_p)))
+        self.ctx.sync()
+
+    def getdata(self, out=None):
+        """getdata(advd) (src/advection.jl:317): a host copy of the device-resident array."""
+        if out is None:
+            out = np.empty(self.adv.sizeall, dtype=np.float64, order="F")
+        assert out.flags.f_contiguous and out.dtype == np.float64
+        _lib.check(_lib.lib().slb_grid_download(self.grid, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def points_dev(self, dim0):
+        p = self._points_dev.get(dim0)
+        if p is None:
+            p = self.ctx.to_device(self.adv.t_mesh[dim0].points)
+            self._points_dev[dim0] = p
+        return p
+
+    # -- accessors, src/advection.jl:315-336 -------------------------------------------
+    def getst(self):
+        return self.adv.getst(self.state_gen)
+
+    def getstcoef(self):
+        return self.adv.getstcoef(self.state_gen)
+
+    def getcur_t(self):
+        return self.adv.getcur_t(self.state_gen)
+
+    def getinterp(self):
+        return self.adv.getinterp(self.state_gen)
+
+    def _getcurrentindice(self):
+        return self.getst().perm[0]
+
+    def nextstate(self):
+        """nextstate! -- src/advection.jl:358-367"""
+        if self.state_gen < self.adv.nbstates:
+            self.state_gen += 1
+            return True
+        self.state_gen = 1
+        self.time_cur += self.adv.dt_base
+        return False
+
+    def close(self):
+        if self.grid:
+            _lib.lib().slb_grid_destroy(self.grid)
+            self.grid = None
+        for p in self._points_dev.values():
+            self.ctx.free(p)
+        self._points_dev = {}
+        if hasattr(self.parext, "close"):
+            self.parext.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def getdata(advd):
+    return advd.getdata()
+
+
+def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0):
+    """One slb_sweep on advd's grid (kernel seam).  table: device pointer (c_void_p) when
+    on_device else a float64 numpy array."""
+    n = advd.adv.sizeall[dim0]
+    h = interp.handle(advd.ctx, n)
+    if on_device:
+        ptr, length = table
+    else:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        ptr, length = table.ctypes.data_as(C.c_void_p), table.size
+    _lib.check(
+        _lib.lib().slb_sweep(advd.grid, int(dim0), h, ptr, int(length), _lib.i64(strides), float(scale), 1 if on_device else 0, int(flags))
+    )
+
+
+def advection(advd):
+    """advection!(advd) -- src/advection.jl:594-704.  One split stage; returns True while
+    more stages remain in the current time step."""
+    st = advd.getst()
+    if st.ndims != 1 or not st.isconstdec:
+        raise NotImplementedError(
+            "only const-shift 1-D states (ndims=1, isconstdec=true) are on the B200 path (SURVEY.md 8a/8f)"
+        )
+    interp = advd.getinterp()[0]
+    ext = advd.parext
+    ext.initcoef(advd)  # src/advection.jl:407-408
+    table, strides, scale, on_device = ext.alpha_table(advd)
+    sweep(advd, st.perm[0] - 1, interp, table, strides, scale, on_device, advd.flags)
+    return advd.nextstate()

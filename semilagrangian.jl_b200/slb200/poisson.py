@@ -1,0 +1,200 @@
+"""Vlasov-Poisson displacement provider -- host mirror of src/poisson.jl + src/util_poisson.jl.
+
+PoissonConst/PoissonVar (src/poisson.jl:35-95), initcoef! (:164-205), getalpha (:210-224),
+compute_charge! (src/util_poisson.jl:68-79), compute_elfield! (src/poisson.jl:139-144),
+compute_ee / compute_ke / getenergy* (src/util_poisson.jl:41-53, :156-183).
+rho, E and the mesh nodes live on the device; a velocity sweep reads E directly
+(alpha = (dt/dv) * E[x]) and a space sweep reads the velocity nodes (alpha = (-dt/dx) * v).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .advection import AbstractExtDataAdv
+from .mesh import vec_k_fft
+
+
+def _get_fctv_k_imag(adv):
+    """Imaginary parts of fctv_k (src/poisson.jl:7-15): k_x / |k|^2, zero mode 0."""
+    nsp = adv.N // 2
+    v_k = [vec_k_fft(m) for m in adv.t_mesh[:nsp]]
+    sz = [len(m) for m in adv.t_mesh[:nsp]]
+    s = np.zeros(sz, order="F")
+    for x in range(nsp):
+        shape = [1] * nsp
+        shape[x] = sz[x]
+        s = s + (v_k[x] ** 2).reshape(shape)
+    with np.errstate(divide="ignore"):
+        inv = 1.0 / s
+    inv.reshape(-1, order="F")[0] = 0.0
+    out = []
+    for x in range(nsp):
+        shape = [1] * nsp
+        shape[x] = sz[x]
+        out.append(np.asfortranarray(v_k[x].reshape(shape) * inv))
+    return out
+
+
+def dotprod(vs):
+    """src/util.jl:59-67"""
+    n = len(vs)
+    res = np.ones([1] * n)
+    for i, v in enumerate(vs):
+        shape = [1] * n
+        shape[i] = len(v)
+        res = res * np.asarray(v, dtype=np.float64).reshape(shape)
+    return np.asfortranarray(res)
+
+
+class PoissonVar(AbstractExtDataAdv):
+    """getpoissonvar(adv): PoissonConst + PoissonVar, StdPoisson (src/poisson.jl:35-107)."""
+
+    def __init__(self, adv, ctx=None):
+        N = adv.N
+        if N % 2 != 0:
+            raise ValueError(f"N={N} must be a multiple of 2")
+        self.adv = adv
+        self.ctx = ctx or adv.ctx or _lib.default_context()
+        self.Nsp = self.Nv = N // 2
+        self.sp_ext = adv.sizeall[: self.Nsp]
+        self.nsp_tot = int(np.prod(self.sp_ext))
+        self.fctv_imag = _get_fctv_k_imag(adv)
+        self.v_square = dotprod([m.points for m in adv.t_mesh[self.Nsp:]]) ** 2  # src/poisson.jl:51
+        L = _lib.lib()
+        self._keep = [np.ascontiguousarray(a.reshape(-1, order="F")) for a in self.fctv_imag]
+        arr = (_lib.c_double_p * self.Nsp)(*[_lib.dptr(a) for a in self._keep])
+        h = C.c_void_p()
+        _lib.check(L.slb_poisson_create(self.ctx.h, self.Nsp, _lib.i64(self.sp_ext), arr, C.byref(h)))
+        self.plan = h
+        self.rho_dev = self.ctx.malloc(self.nsp_tot * 8)
+        self.E_dev = [self.ctx.malloc(self.nsp_tot * 8) for _ in range(self.Nsp)]
+        self.vsq_dev = self.ctx.to_device(self.v_square.reshape(-1, order="F"))
+        self.has_field = False
+        self._sweep = None
+
+    # src/poisson.jl:119-125 -> src/util_poisson.jl:68-79
+    def compute_charge(self, advd):
+        dv = 1.0
+        for m in self.adv.t_mesh[self.Nsp:]:
+            dv = dv * m.step
+        _lib.check(_lib.lib().slb_charge_density(advd.grid, self.Nsp, dv, self.rho_dev))
+
+    # src/poisson.jl:139-144
+    def compute_elfield(self):
+        arr = (C.c_void_p * self.Nsp)(*[p.value for p in self.E_dev])
+        _lib.check(_lib.lib().slb_poisson_solve(self.plan, self.rho_dev, arr))
+        self.has_field = True
+
+    @property
+    def rho(self):
+        return self.ctx.to_host(self.rho_dev, self.nsp_tot).reshape(self.sp_ext, order="F")
+
+    @property
+    def t_elfield(self):
+        if not self.has_field:
+            return None
+        return tuple(self.ctx.to_host(p, self.nsp_tot).reshape(self.sp_ext, order="F") for p in self.E_dev)
+
+    def isvelocity(self, advd):  # src/poisson.jl:155-158
+        return advd.getst().perm[0] > self.Nsp
+
+    def initcoef(self, advd):
+        """initcoef!(pv, advd) -- src/poisson.jl:164-205"""
+        st = advd.getst()
+        adv = advd.adv
+        dt = advd.getcur_t()
+        Nsp, N = self.Nsp, adv.N
+        strides = [0] * N
+        if self.isvelocity(advd):
+            if (Nsp + 1) in st.perm[: st.ndims]:
+                self.compute_charge(advd)
+                self.compute_elfield()
+            if not self.has_field:
+                raise RuntimeError("velocity state before any field solve (state order must start with dim Nsp+1)")
+            d = st.perm[0]
+            # bufcur_v = (dt / step(mesh_d)) * E_{d-Nsp}; indexed by ind.I[end-Nsp+1:end], i.e. E's
+            # axis i is the grid dim perm[N-Nsp+i]  (src/poisson.jl:178-189, :216-219)
+            stride = 1
+            for i in range(Nsp):
+                g = st.perm[N - Nsp + i]
+                strides[g - 1] = stride
+                stride *= self.sp_ext[i]
+            self._sweep = ((self.E_dev[d - 1 - Nsp], self.nsp_tot), strides, dt / adv.t_mesh[d - 1].step, True)
+        else:
+            # tupleind / bufcur_sp, src/poisson.jl:191-203 (invp where perm is meant: identical for
+            # the involutive permutations every reference driver uses)
+            tupleind = st.perm[st.invp[0] + Nsp - 1] - st.ndims
+            g = st.perm[st.ndims + tupleind - 1]
+            src_dim = st.invp[0] + Nsp
+            strides[g - 1] = 1
+            self._sweep = (
+                (advd.points_dev(src_dim - 1), adv.sizeall[src_dim - 1]),
+                strides,
+                -dt / adv.t_mesh[st.invp[0] - 1].step,
+                True,
+            )
+
+    def alpha_table(self, advd):
+        return self._sweep
+
+    def close(self):
+        if getattr(self, "plan", None):
+            _lib.lib().slb_poisson_destroy(self.plan)
+            self.plan = None
+            for p in [self.rho_dev, self.vsq_dev] + list(self.E_dev):
+                self.ctx.free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def getpoissonvar(adv, ctx=None):
+    return PoissonVar(adv, ctx=ctx)
+
+
+def compute_ee(advd):
+    """compute_ee(advd) -- src/util_poisson.jl:156-162: dx * sum_d sum(E_d .^ 2), with the
+    field of the last compute_elfield! (the reference does not recompute it)."""
+    pv = advd.parext
+    dx = 1.0
+    for m in advd.adv.t_mesh[: pv.Nsp]:
+        dx = dx * m.step
+    tot = 0.0
+    for p in pv.E_dev:
+        v = C.c_double()
+        _lib.check(_lib.lib().slb_reduce_sumsq(advd.ctx.h, p, pv.nsp_tot, C.byref(v)))
+        tot = tot + v.value
+    return dx * tot
+
+
+def compute_ke(advd):
+    """compute_ke(advd) -- src/util_poisson.jl:41-53"""
+    pv = advd.parext
+    adv = advd.adv
+    dsp = 1.0
+    for m in adv.t_mesh[: pv.Nsp]:
+        dsp *= m.step
+    dv = 1.0
+    for m in adv.t_mesh[pv.Nsp:]:
+        dv *= m.step
+    v = C.c_double()
+    _lib.check(_lib.lib().slb_kinetic_energy(advd.grid, pv.Nsp, pv.vsq_dev, dsp * dv, C.byref(v)))
+    return v.value
+
+
+def getenergy(advd):
+    """src/util_poisson.jl:167-175"""
+    pv = advd.parext
+    pv.compute_charge(advd)
+    pv.compute_elfield()
+    ee = compute_ee(advd)
+    ke = compute_ke(advd)
+    return ee, ke, ee + ke
+
+
+def getenergyall(advd):
+    return getenergy(advd)[2]

@@ -1,0 +1,243 @@
+"""GPU parity of the split advection driver, the charge density, the Poisson solve and the
+energy diagnostics against the oracle model (oracle/refmodel.py), on the BASELINE configs'
+shapes (reduced where the oracle would take minutes).
+
+Tolerances (BASELINE.json north_star): <= 1e-12 relative max-abs per sweep / per field,
+<= 1e-10 on Landau-damping electric-energy histories.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _landau_1d1v(M, nx, nv, interp_f, eps=0.001, kx=0.5, dt=0.1):
+    mx = M.UniformMesh(0.0, 2 * math.pi / kx, nx)
+    mv = M.UniformMesh(-6.0, 6.0, nv)
+    states = [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)]
+    adv = M.Advection((mx, mv), [interp_f(nx), interp_f(nv)], dt, states)
+    f = M.dotprod((eps * np.cos(kx * mx.points) + 1, np.exp(-mv.points**2 / 2) / math.sqrt(2 * math.pi)))
+    pv = M.getpoissonvar(adv)
+    return adv, M.AdvectionData(adv, f, pv), pv
+
+
+def _run(M, advd, nbdt, adv_fn):
+    el = []
+    for _ in range(nbdt):
+        while adv_fn(advd):
+            pass
+        el.append(M.compute_ee(advd))
+    return np.array(el)
+
+
+def test_landau_1d1v_history_config1():
+    """C1: Vlasov-Poisson 1D1V 128x256, Lagrange 9, Strang (examples/vlasov-poisson-1d1v.jl)."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    _, advd_g, _ = _landau_1d1v(S, 128, 256, lambda n: S.Lagrange(9))
+    _, advd_o, _ = _landau_1d1v(R, 128, 256, lambda n: R.Lagrange(9))
+    nb = 100
+    el_g = _run(S, advd_g, nb, S.advection)
+    el_o = _run(R, advd_o, nb, R.advection)
+    assert abs(advd_g.time_cur - advd_o.time_cur) == 0.0
+    err = np.max(np.abs(el_g - el_o)) / np.max(np.abs(el_o))
+    assert err <= 1e-10, err
+    assert relerr(advd_g.getdata(), advd_o.data) <= 1e-11
+    # physics: Landau damping rate for k = 0.5 is -0.1533; fit the envelope of log(ee)
+    t = 0.1 * np.arange(1, nb + 1)
+    peaks = [i for i in range(1, nb - 1) if el_g[i] > el_g[i - 1] and el_g[i] > el_g[i + 1]]
+    slope = np.polyfit(t[peaks], np.log(el_g[peaks]), 1)[0]
+    assert abs(slope / 2 + 0.1533) < 0.01, slope
+
+
+def _vp_2d2v(M, sz, interps, dt=0.1, eps=0.5):
+    m1 = M.UniformMesh(0.0, 4 * math.pi, sz[0])
+    m2 = M.UniformMesh(0.0, 4 * math.pi, sz[1])
+    v1 = M.UniformMesh(-6.0, 6.0, sz[2])
+    v2 = M.UniformMesh(-6.0, 6.0, sz[3])
+    tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+    adv = M.Advection((m1, m2, v1, v2), interps, dt, tabst)
+    fsp = lambda x: eps * np.cos(x / 2) + 1
+    fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+    f = M.dotprod((fsp(m1.points), fsp(m2.points), fv(v1.points), fv(v2.points)))
+    pv = M.getpoissonvar(adv)
+    return adv, M.AdvectionData(adv, f, pv), pv
+
+
+@pytest.mark.parametrize("sz,kind,order,nsteps", [((32, 32, 32, 32), "lagrange", 7, 3), ((16, 20, 24, 12), "lagrange", 9, 2),
+                                                  ((32, 32, 32, 32), "bspline_fft", 11, 2), ((32, 16, 32, 16), "bspline_lu", 5, 2)])
+def test_vlasov_poisson_2d2v_steps(sz, kind, order, nsteps):
+    """C3/C4 shapes reduced (examples/vlasov-poisson-2d2v.jl): every stage of every step is
+    compared, plus rho, E, ee, ke."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    def mk(M):
+        def one(n):
+            return {"lagrange": lambda: M.Lagrange(order), "bspline_fft": lambda: M.BSplineFFT(order, n),
+                    "bspline_lu": lambda: M.BSplineLU(order, n)}[kind]()
+        return [one(n) for n in sz]
+
+    adv_g, advd_g, pv_g = _vp_2d2v(S, sz, mk(S))
+    adv_o, advd_o, pv_o = _vp_2d2v(R, sz, mk(R))
+    assert adv_g.nbstates == adv_o.nbstates == 6
+    for step in range(nsteps):
+        more = True
+        while more:
+            assert advd_g.state_gen == advd_o.state_gen
+            more = S.advection(advd_g)
+            more_o = R.advection(advd_o)
+            assert more == more_o
+            assert relerr(advd_g.getdata(), advd_o.data) <= 1e-12 * (1 + 6 * step + advd_g.state_gen + 6)
+        assert relerr(pv_g.rho, pv_o.rho) <= 1e-11
+        for eg, eo in zip(pv_g.t_elfield, pv_o.t_elfield):
+            assert relerr(eg, eo) <= 1e-11
+        ee_g, ee_o = S.compute_ee(advd_g), R.compute_ee(advd_o)
+        assert abs(ee_g - ee_o) <= 1e-11 * abs(ee_o)
+        ke_g, ke_o = S.compute_ke(advd_g), R.compute_ke(advd_o)
+        assert abs(ke_g - ke_o) <= 1e-12 * abs(ke_o)
+    eg = S.getenergy(advd_g)
+    eo = R.getenergy(advd_o)
+    assert np.allclose(eg, eo, rtol=1e-11, atol=0)
+
+
+def test_field_solve_pieces_random():
+    """compute_charge! / compute_elfield! on random data (test/test_poisson.jl:38-108 shape)."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    rng = np.random.default_rng(20240611)
+    sz = (16, 24, 10, 14)
+    meshes = lambda M: (M.UniformMesh(-1.0, 3.0, sz[0]), M.UniformMesh(0.0, 5.0, sz[1]), M.UniformMesh(-3.0, 1.0, sz[2]), M.UniformMesh(-9.0, 7.0, sz[3]))
+    tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+    f = np.asfortranarray(rng.random(sz))
+    out = {}
+    for name, M in (("g", S), ("o", R)):
+        adv = M.Advection(meshes(M), [M.Lagrange(3)] * 4, 0.1, tabst)
+        pv = M.getpoissonvar(adv)
+        advd = M.AdvectionData(adv, f, pv)
+        pv.compute_charge(advd)
+        pv.compute_elfield()
+        out[name] = (np.array(pv.rho), [np.array(e) for e in pv.t_elfield], M.compute_ee(advd), M.compute_ke(advd))
+    assert relerr(out["g"][0], out["o"][0]) <= 1e-12
+    assert abs(np.sum(out["g"][0])) < 1e-10  # zero mean
+    for eg, eo in zip(out["g"][1], out["o"][1]):
+        assert relerr(eg, eo) <= 1e-12
+    assert abs(out["g"][2] - out["o"][2]) <= 1e-12 * abs(out["o"][2])
+    assert abs(out["g"][3] - out["o"][3]) <= 1e-12 * abs(out["o"][3])
+
+
+def _rotation(M, sz, interps, nbdt):
+    """test/test_rotation.jl:41-89"""
+    mx = M.UniformMesh(-5.0, 5.0, sz[0])
+    my = M.UniformMesh(-6.0, 4.5, sz[1])
+    dt = 2 * math.pi / nbdt
+    states = [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)]
+    adv = M.Advection((mx, my), interps, dt, states, tab_coef=M.magicsplit(dt))
+    X, Y = np.meshgrid(mx.points, my.points, indexing="ij")
+    f = np.asfortranarray(np.exp(-2 * (X**2 + (Y + 1.2) ** 2)))
+    return adv, M.AdvectionData(adv, f, M.getrotationvar(adv)), f
+
+
+@pytest.mark.parametrize("kind,order,sz", [("lagrange", 5, (400, 300)), ("hermite", 5, (400, 300)), ("bspline_lu", 5, (128, 256)),
+                                           ("bspline_fft", 5, (128, 256)), ("bspline_lu", 5, (1024, 1024))])
+def test_rotation_config2(kind, order, sz):
+    """C2 (rotation, B-spline LU 5, 1024x1024) and the reference's rotation tests
+    (test/test_rotation.jl:237-252): full turn in 11 steps with magicsplit returns the
+    initial Gaussian (error < 1e-3) and matches the oracle stage by stage."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    def mk(M):
+        return [{"lagrange": lambda n: M.Lagrange(order), "hermite": lambda n: M.Hermite(order),
+                 "bspline_lu": lambda n: M.BSplineLU(order, n), "bspline_fft": lambda n: M.BSplineFFT(order, n)}[kind](n) for n in sz]
+
+    nbdt = 11
+    _, advd_g, f0 = _rotation(S, sz, mk(S), nbdt)
+    _, advd_o, _ = _rotation(R, sz, mk(R), nbdt)
+    for _ in range(nbdt):
+        while S.advection(advd_g):
+            pass
+        while R.advection(advd_o):
+            pass
+    out = advd_g.getdata()
+    assert relerr(out, advd_o.data) <= 1e-11
+    assert np.max(np.abs(out - f0)) < 1e-3
+
+
+@pytest.mark.parametrize("kind,order,sz,tol", [("lagrange", 5, (200, 300), 1e-3), ("bspline_lu", 5, (128, 64), 1e-6)])
+def test_translation(kind, order, sz, tol):
+    """test/test_translation.jl:42-101,139-190: periodic function translated with Strang splitting."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    def build(M):
+        m1 = M.UniformMesh(0.0, 1.0, sz[0])
+        m2 = M.UniformMesh(0.0, 1.0, sz[1])
+        dt, v = 0.01, (30.0, -20.0)  # shifts in grid units per unit time
+        interps = [M.Lagrange(order) if kind == "lagrange" else M.BSplineLU(order, n) for n in sz]
+        adv = M.Advection((m1, m2), interps, dt, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)], tab_coef=M.strangsplit(dt))
+        X, Y = np.meshgrid(m1.points, m2.points, indexing="ij")
+        f = np.asfortranarray(np.exp(-(np.sin(2 * np.pi * X) + np.sin(2 * np.pi * Y))))
+        return adv, M.AdvectionData(adv, f, M.gettranslationvar(v)), (m1, m2, dt, v)
+
+    _, advd_g, (m1, m2, dt, v) = build(S)
+    _, advd_o, _ = build(R)
+    nb = 20
+    for _ in range(nb):
+        while S.advection(advd_g):
+            pass
+        while R.advection(advd_o):
+            pass
+    out = advd_g.getdata()
+    assert relerr(out, advd_o.data) <= 1e-11
+    X, Y = np.meshgrid(m1.points, m2.points, indexing="ij")
+    sx, sy = nb * dt * v[0] * m1.step, nb * dt * v[1] * m2.step
+    exact = np.exp(-(np.sin(2 * np.pi * (X + sx)) + np.sin(2 * np.pi * (Y + sy))))
+    assert np.max(np.abs(out - exact)) < tol
+
+
+def test_full_size_properties_128_4():
+    """Size-independent properties at BASELINE's full size (2D2V 128^4, Lagrange 7), where the
+    oracle is too slow for a point-wise check of every sweep: (i) integer shifts are exact
+    circular shifts, (ii) a sampled slab of one fractional sweep per dim matches the oracle,
+    (iii) the charge density of a product-form f is known in closed form."""
+    import slb200 as S
+    from oracle import refmodel as R
+    from helpers import DeviceGrid, oracle_sweep
+
+    n = 128
+    rng = np.random.default_rng(20240611)
+    a = [rng.random(n) + 0.5 for _ in range(4)]
+    f = S.dotprod(a)  # 2.1 GB product-form array: any slab is cheap to rebuild on the host
+    g = DeviceGrid(f)
+    it, oit = S.Lagrange(7), R.Lagrange(7)
+    sl = (slice(5, 9), slice(17, 19), slice(60, 63), slice(100, 102))
+    for dim in range(4):
+        # (i) integer shift by 3 along dim == roll
+        g.sweep(dim, it, np.array([3.0]), [0, 0, 0, 0])
+        out = g.get()
+        assert np.array_equal(out, np.roll(f, -3, axis=dim)), dim
+        g.sweep(dim, it, np.array([-3.0]), [0, 0, 0, 0])
+        # (ii) fractional, index-dependent shift on a slab containing whole lines along dim
+        other = (dim + 1) % 4
+        tab = rng.uniform(-6, 6, n)
+        astride = [0] * 4
+        astride[other] = 1
+        g.sweep(dim, it, tab, astride)
+        out = g.get()
+        idx = list(sl)
+        idx[dim] = slice(None)
+        sub = np.asfortranarray(f[tuple(idx)])
+        subtab = tab[idx[other]] if idx[other] != slice(None) else tab
+        ref = oracle_sweep(sub, dim, oit, np.ascontiguousarray(subtab), astride)
+        assert relerr(out[tuple(idx)], ref) <= 1e-12, dim
+        # undo: restore f for the next dim
+        g.close()
+        g = DeviceGrid(f)
+    g.close()
