@@ -1,0 +1,159 @@
+"""Host-side logic of the product mirror (no GPU): state schedule, splitting tables, meshes,
+weight tables and the bordered-LU B-spline solver, checked against the oracle and against the
+reference's own known answers (test/test_advection.jl:58-158, test/test_mesh.jl:57-67,
+test/test_util.jl:14-43)."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+import slb200 as S
+from oracle import refmodel as R, tables as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("M", [S, R], ids=["product", "oracle"])
+def test_state_schedule_6d(M):
+    """test/test_advection.jl:58-158: 3D3V grid, Strang, space states have stcoef 1."""
+    szsp, szv = (2, 4, 8), (4, 8, 4)
+    ms = tuple(M.UniformMesh(-1.0, 3.0, n) for n in szsp) + tuple(M.UniformMesh(-3.0, 1.0, n) for n in szv)
+    states = [([1, 2, 3, 6, 5, 4], 1, 1, True), ([2, 1, 3, 4, 6, 5], 1, 1, True), ([3, 2, 1, 4, 5, 6], 1, 1, True),
+              ([4, 5, 6, 1, 2, 3], 1, 2, True), ([5, 4, 6, 1, 2, 3], 1, 2, True), ([6, 5, 4, 1, 2, 3], 1, 2, True)]
+    adv = M.Advection(ms, [M.Lagrange(3) for _ in range(6)], 0.125, states)
+    assert adv.sizeall == szsp + szv
+    assert adv.nbstates == 9 and adv.maxcoef == 2
+    assert adv.getcur_t(1) == adv.tab_coef[0] == adv.tab_coef[2]
+    assert adv.getcur_t(4) == adv.tab_coef[1]
+    t_coef = [1, 1, 1, 2, 2, 2, 3, 3, 3, 1]
+    t_indice = [1, 2, 3, 4, 5, 6, 1, 2, 3, 1]
+    t_result = [True] * 8 + [False, True]
+
+    class Dummy:  # the state machine alone: no device data needed
+        pass
+
+    advd = M.AdvectionData.__new__(M.AdvectionData)
+    advd.adv, advd.state_gen, advd.time_cur = adv, 1, 0.0
+    for i in range(10):
+        assert advd.getstcoef() == t_coef[i]
+        assert advd.state_gen == i % 9 + 1
+        assert advd._getcurrentindice() == t_indice[i]
+        assert advd.getcur_t() == adv.tab_coef[t_coef[i] - 1]
+        assert advd.getinterp()[0] is adv.t_interp[t_indice[i] - 1]
+        assert advd.nextstate() == t_result[i]
+    assert advd.time_cur == 0.125
+
+
+def test_schedules_of_the_baseline_configs():
+    m = S.UniformMesh(0.0, 1.0, 8)
+    it = S.Lagrange(3)
+    a1 = S.Advection((m, m), [it, it], 0.1, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)])
+    assert a1.nbstates == 3
+    assert [(a1.getst(g).perm[0], a1.getcur_t(g)) for g in (1, 2, 3)] == [(1, 0.05), (2, 0.1), (1, 0.05)]
+    tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+    a2 = S.Advection((m,) * 4, [it] * 4, 0.1, tabst)
+    assert a2.nbstates == 6
+    assert [(a2.getst(g).perm[0], a2.getcur_t(g)) for g in range(1, 7)] == [(3, 0.05), (4, 0.05), (1, 0.1), (2, 0.1), (3, 0.05), (4, 0.05)]
+    with pytest.raises(ValueError):
+        S.Advection((m, m), [it], 0.1, [([1, 2], 1, 1, True)])
+
+
+def test_splitting_tables():
+    dt = 0.1
+    for name in ("nosplit", "standardsplit", "strangsplit", "magicsplit", "triplejumpsplit"):
+        assert getattr(S, name)(dt) == getattr(R, name)(dt), name
+    assert S.strangsplit(dt) == [0.05, 0.1, 0.05]
+    assert S.magicsplit(dt) == [math.tan(0.05), math.sin(0.1), math.tan(0.05)]
+    tj = S.triplejumpsplit(dt)
+    assert len(tj) == 7 and abs(sum(tj[0::2]) - dt) < 1e-15 and abs(sum(tj[1::2]) - dt) < 1e-15
+    o6 = S.order6split(dt)
+    assert len(o6) == 23 and abs(sum(o6) - 2 * dt) < 1e-15 and o6 == o6[::-1]
+    h = S.hamsplit_3_11(dt)
+    assert len(h) == 11 and h == h[::-1]
+    assert abs(sum(h[1::2]) - dt) < 1e-15  # the a_i sum to 1
+
+
+def test_mesh_and_wavenumbers():
+    # test/test_mesh.jl:57-67
+    for M in (S, R):
+        mesh = M.UniformMesh(-1.0, 1.0, 64)
+        ref = np.roll(np.arange(-32, 32), 32) * (2 * math.pi / 2.0)
+        assert np.array_equal(M.vec_k_fft(mesh), ref)
+        assert mesh.step == 2.0 / 64 and mesh.width == 2.0
+        assert np.array_equal(mesh.points, -1.0 + np.arange(64) / 32)
+    a, b = S.UniformMesh(0.0, 4 * math.pi, 128), R.UniformMesh(0.0, 4 * math.pi, 128)
+    assert np.array_equal(a.points, b.points) and a.step == b.step
+    assert S.stop(a) == 4 * math.pi or abs(S.stop(a) - 4 * math.pi) < 1e-14
+    c = S.UniformMesh(-6.0, 4.5, 1022)  # non-dyadic: exact rational nodes rounded once
+    assert abs(c.points[-1] + c.step - 4.5) < 1e-14
+
+
+def test_weight_tables_match_oracle_tables():
+    from slb200 import interp as I
+
+    for o in range(1, 14):
+        assert np.array_equal(S.Lagrange(o).tabfct, np.array(T.to_float64_table(T.lagrange_tabfct_rat(o))))
+    for o in (3, 5, 7, 9, 11, 13):
+        b = S.BSplineLU(o, 64)
+        assert np.array_equal(b.tabfct, np.array(T.to_float64_table(T.bspline_tabfct_rat(o))))
+        assert list(b.nodes) == [float(x) for x in T.bspline_node_values_rat(o)]
+    for o in (5, 9, 13):
+        assert np.array_equal(S.Hermite(o).tabfct, np.array(T.to_float64_table(T.hermite_tabfct_rat(o))))
+    assert np.array_equal(S.Hermite(7, flbis=True).tabfct, np.array(T.to_float64_table(T.hermite_tabfct_rat(7, True))))
+    assert I.get_kl_ku(5) == (2, 2) and I.get_kl_ku(6) == (2, 3)
+    assert S.get_order(S.Lagrange(9)) == 9
+    # host getprecal agrees with the oracle's FMA Horner to the last bits
+    w = S.Lagrange(9).getprecal(0.3)
+    assert np.max(np.abs(w - R.Lagrange(9).getprecal(0.3))) < 1e-15 and abs(w.sum() - 1) < 1e-14
+
+
+@pytest.mark.parametrize("order,n", [(3, 16), (5, 128), (5, 1024), (9, 30), (11, 128), (11, 256), (13, 64)])
+def test_bordered_lu_solver_host(order, n):
+    """The exact routine the B-spline kernels run (slb_bspline.cuh: bspline_factor +
+    bspline_solve_line), executed on the host, equals the reference's cyclic LU solve."""
+    so = os.path.join(ROOT, "semilagrangian.jl_b200", "lib", "libslb200_hosttest.so")
+    L = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    L.slbt_bspline_solve_host.argtypes = [C.c_int, C.c_longlong, dp, dp, dp]
+    rng = np.random.default_rng(5431221)
+    nodes = np.array([float(x) for x in T.bspline_node_values_rat(order)])
+    b = rng.random(n)
+    x = np.empty(n)
+    assert L.slbt_bspline_solve_host(order, n, nodes.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp)) == 0
+    ref = R.BSplineLU(order, n).sol(b)
+    assert np.max(np.abs(x - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+def test_driver_level_oracle_kats():
+    """Oracle driver pinned by the reference's integration tests: rotation returns to the
+    start (test/test_rotation.jl:237-252, err < 1e-3) and Poisson pieces are consistent
+    (test/test_poisson.jl:38-108)."""
+    sz = (200, 150)
+    mx, my = R.UniformMesh(-5.0, 5.0, sz[0]), R.UniformMesh(-6.0, 4.5, sz[1])
+    nbdt = 11
+    dt = 2 * math.pi / nbdt
+    adv = R.Advection((mx, my), [R.Lagrange(5), R.Lagrange(5)], dt, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)], tab_coef=R.magicsplit(dt))
+    X, Y = np.meshgrid(mx.points, my.points, indexing="ij")
+    f0 = np.asfortranarray(np.exp(-2 * (X**2 + (Y + 1.2) ** 2)))
+    advd = R.AdvectionData(adv, f0, R.getrotationvar(adv))
+    for _ in range(nbdt):
+        while R.advection(advd):
+            pass
+    assert np.max(np.abs(advd.data - f0)) < 1e-3
+    # Poisson: E from the plugin solves d/dx E = rho spectrally in 1-D
+    nx, nv = 64, 32
+    mx, mv = R.UniformMesh(0.0, 4 * math.pi, nx), R.UniformMesh(-6.0, 6.0, nv)
+    adv = R.Advection((mx, mv), [R.Lagrange(5)] * 2, 0.1, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)])
+    f = R.dotprod((1 + 0.1 * np.cos(0.5 * mx.points), np.exp(-mv.points**2 / 2) / math.sqrt(2 * math.pi)))
+    pv = R.getpoissonvar(adv)
+    advd = R.AdvectionData(adv, f, pv)
+    pv.compute_charge(advd)
+    pv.compute_elfield()
+    assert abs(pv.rho.sum()) < 1e-12
+    assert np.max(np.abs(pv.rho - 0.1 * np.cos(0.5 * mx.points))) < 1e-8  # int of the Gaussian ~ 1
+    E = pv.t_elfield[0]
+    # reference convention (src/poisson.jl:8,139-144): E_hat = (i k / |k|^2) rho_hat  ->  E = -(A/k) sin(kx)
+    assert np.max(np.abs(E + 0.2 * np.sin(0.5 * mx.points) * (pv.rho.max() / 0.1))) < 1e-8
+    assert abs(R.compute_ee(advd) - mx.step * np.sum(E**2)) < 1e-15
