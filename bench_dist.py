@@ -1,0 +1,119 @@
+"""Sharded arm of bench.py (N > 1): 2D2V 128^4 grid domain-decomposed over the ranks
+(strong scaling), re-sharded twice per Strang step with an NCCL all-to-all over NVLink
+(slb200.distributed).  Launched by torchrun; rank 0 prints the JSON line."""
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run_distributed(args, B):
+    import torch
+    import torch.distributed as dist
+
+    import slb200 as S
+    from slb200.distributed import ShardedAdvectionData, slab
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    n = args.size
+    adv, vecs = B.vp2d2v_setup(S, n, args.order, args.interp)
+    lo, hi = slab(n, world, rank)
+    a, b, c, d = vecs
+    loc = np.empty((n, hi - lo, n, n), order="F")
+    B.fill_product(loc, (a, b[lo:hi], c, d))
+    sh = ShardedAdvectionData(adv, loc)
+    del loc
+    cells_per_step = 6 * n**4
+
+    def step():
+        while sh.advection():
+            pass
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sh.ctx.launch_count()
+    ex0 = sh.n_exchanges
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = sh.ctx.launch_count() - launches0
+    nex = sh.n_exchanges - ex0
+    clocks = sampler.stop() if rank == 0 else None
+    ee = sh.compute_ee()
+
+    # sweep-only and exchange-only timings (explain the step time)
+    def timed(fn, reps=5):
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_a2a = timed(lambda: dist.all_to_all_single(sh.bufs[1 - sh.cur], sh.bufs[sh.cur]))
+    nbytes_local = n**4 * 8 // world
+
+    # e2e: host slab in, host slab out, every step (pinned host memory)
+    host = torch.empty(n**4 // world, dtype=torch.float64).pin_memory()
+    host.copy_(sh.bufs[sh.cur])
+    e2e_steps = max(1, min(args.steps, 3))
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sh.bufs[sh.cur].copy_(host, non_blocking=True)
+        step()
+        _ = sh.compute_ee()
+        host.copy_(sh.bufs[sh.cur], non_blocking=True)
+        torch.cuda.synchronize()
+    dist.barrier()
+    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    e2e_val = cells_per_step * e2e_steps / float(wall.item()) / 1e9
+
+    if rank == 0:
+        peak, peak_src = B.read_peaks()
+        value = cells_per_step * args.steps / (ms_total * 1e-3) / 1e9
+        line = {
+            "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": dict(B.workload_config(args), parallelism=f"x2/v2 slabs over {world} GPUs, 2 all-to-all re-shards per step"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": B.UNIT, "h2d_bytes_per_step": nbytes_local * world, "d2h_bytes_per_step": nbytes_local * world + 8 * world,
+                    "steps": e2e_steps, "note": "every rank uploads its slab from pinned host memory, full Strang step, reads back ee and its slab"},
+            "gpu_launches": int(launches), "exchanges_per_step": nex / args.steps,
+            "all_to_all_ms": ms_a2a, "all_to_all_GBps_per_gpu": nbytes_local * (world - 1) / world / (ms_a2a * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "whole step (6 sweeps + 2 rho passes per rank)", "achieved": value * 1e9 * (112.0 / 6.0) / world / 1e9,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": value * (112.0 / 6.0) / world / peak, "traffic": None},
+            "last_ee": ee,
+        }
+        print(json.dumps(line))
+    sh.close()
+    dist.destroy_process_group()
+    return 0

@@ -125,6 +125,21 @@ void slb_interp_destroy(slb_interp* it);
 int slb_sweep(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
               const int64_t* alpha_strides, double alpha_scale, int alpha_on_device, int flags);
 
+/* ---- sweeps fused with the multi-GPU re-shard -------------------------------- */
+/* A 2D2V grid sharded over P ranks alternates between two slab layouts; the all-to-all between
+ * them (replacing mpibroadcast, src/mpiinterface.jl:17-38) moves contiguous blocks only when the
+ * sweep before it writes, or the sweep after it reads, a BLOCK-MAJOR array: nblocks consecutive
+ * sub-arrays, each with extent[bdim] / nblocks along bdim.
+ *   SLB_RESHARD_OUT_BLOCKED: the output is written block-major along the swept dim (bdim == dim > 0);
+ *                            after the exchange that dim is the sharded one.
+ *   SLB_RESHARD_IN_BLOCKED : the input (front buffer) is block-major along bdim != dim; dim must be 0. */
+#define SLB_RESHARD_NONE 0
+#define SLB_RESHARD_OUT_BLOCKED 1
+#define SLB_RESHARD_IN_BLOCKED 2
+int slb_sweep_ex(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+                 const int64_t* alpha_strides, double alpha_scale, int alpha_on_device, int flags,
+                 int reshard_mode, int bdim, int nblocks);
+
 /* sol(interp, b) applied to every line along dim (src/interpolation.jl:40,
  * src/bsplinelu.jl:275-284, src/bsplinefft.jl:49-58); in place on the grid (front buffer
  * after the call).  Exposed for tests. */

@@ -462,35 +462,38 @@ static void launch_strided(slb_ctx* c, const double* in, double* out, const View
 
 template <int P1, int R>
 static void launch_contig_r(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
-                            const slb_interp* it, bool exact)
+                            const slb_interp* it, bool exact, const InMap& im)
 {
     long long nlines = v.outer;
-    long long nb = (nlines + 7) / 8;
-    long long cap = (long long)c->sm_count * 64;
-    unsigned blocks = (unsigned)(nb < cap ? nb : cap);
+    // lines per warp: up to 16 consecutive lines, but keep >= ~8 resident-warp waves of work
+    long long lpw = nlines / ((long long)c->sm_count * 32 * 8);
+    if (lpw > 16) lpw = 16;
+    if (lpw < 1) lpw = 1;
+    long long nwarps = (nlines + lpw - 1) / lpw;
+    unsigned blocks = (unsigned)((nwarps + 7) / 8);
     if (exact)
-        k_sweep_contig<P1, R, true><<<blocks, 256, 0, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc);
+        k_sweep_contig<P1, R, true><<<blocks, 256, 0, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc, im, (int)lpw);
     else
-        k_sweep_contig<P1, R, false><<<blocks, 256, 0, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc);
+        k_sweep_contig<P1, R, false><<<blocks, 256, 0, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc, im, (int)lpw);
 }
 
 template <int P1>
 static void launch_contig(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
-                          const slb_interp* it, bool exact)
+                          const slb_interp* it, bool exact, const InMap& im)
 {
     if (v.n >= 96)
-        launch_contig_r<P1, 4>(c, in, out, v, am, it, exact);
+        launch_contig_r<P1, 4>(c, in, out, v, am, it, exact, im);
     else if (v.n >= 48)
-        launch_contig_r<P1, 2>(c, in, out, v, am, it, exact);
+        launch_contig_r<P1, 2>(c, in, out, v, am, it, exact, im);
     else
-        launch_contig_r<P1, 1>(c, in, out, v, am, it, exact);
+        launch_contig_r<P1, 1>(c, in, out, v, am, it, exact, im);
 }
 
 #define SLB_FOR_P1(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 
 // stencil pass in -> out along `dim`; `in` already holds sol(interp, f)
 static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const double* in, double* out,
-                          const AlphaMap& am, int flags, const OutMap* omp)
+                          const AlphaMap& am, int flags, const OutMap* omp, const InMap* imp = nullptr)
 {
     slb_ctx* c = g->ctx;
     View v = make_view(g, dim);
@@ -504,10 +507,16 @@ static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const doub
         om.bstride = (long long)v.n * v.inner;
     }
     int P1 = it->order + 1;
+    InMap im;
+    memset(&im, 0, sizeof(im));
+    if (imp) {
+        if (dim != 0 || !it->fast || omp) return fail(SLB_E_UNSUPPORTED, "blocked input is implemented for fast-path sweeps along dim 0 only");
+        im = *imp;
+    }
     if (it->fast) {
         if (dim == 0 && !omp) {
             switch (P1) {
-#define X(P) case P: launch_contig<P>(c, in, out, v, am, it, exact); break;
+#define X(P) case P: launch_contig<P>(c, in, out, v, am, it, exact, im); break;
                 SLB_FOR_P1(X)
 #undef X
             }
@@ -526,6 +535,37 @@ static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const doub
     }
     LAUNCH_CHECK(c);
     return SLB_OK;
+}
+
+// Compress dims [d0, d1) into terms idx = (x / div) % ext: zero-stride dims are dropped (their
+// extent only advances div), neighbours whose strides are layout-compatible are merged, and
+// a term that reaches the top of the group needs no modulo (ext = 0).
+static int compress_terms(const slb_grid* g, const int64_t* astr, int d0, int d1, AlphaTerm* out)
+{
+    int nt = 0;
+    unsigned long long div = 1;
+    int d = d0;
+    while (d < d1) {
+        if (astr[d] == 0) {
+            div *= (unsigned long long)g->ext[d];
+            ++d;
+            continue;
+        }
+        unsigned long long ext = (unsigned long long)g->ext[d];
+        long long stride = astr[d];
+        int e = d + 1;
+        while (e < d1 && astr[e] == stride * (long long)ext) {
+            ext *= (unsigned long long)g->ext[e];
+            ++e;
+        }
+        out[nt].div = (unsigned)div;
+        out[nt].stride = stride;
+        out[nt].ext = (e >= d1) ? 0u : (unsigned)ext;  // top of the group: (x / div) is already < ext
+        nt++;
+        div *= ext;
+        d = e;
+    }
+    return nt;
 }
 
 static int build_alpha_map(slb_grid* g, int dim, const double* alpha_tab, int64_t alpha_len,
@@ -550,30 +590,14 @@ static int build_alpha_map(slb_grid* g, int dim, const double* alpha_tab, int64_
     memset(am, 0, sizeof(*am));
     am->tab = tab;
     am->scale = scale;
-    int nlo = 0, nhi = 0;
-    bool lo_dep = false;
-    for (int d = 0; d < dim; ++d) lo_dep |= (astr[d] != 0);
-    if (lo_dep)
-        for (int d = 0; d < dim; ++d) {
-            am->ext_lo[nlo] = (unsigned)g->ext[d];
-            am->str_lo[nlo] = astr[d];
-            nlo++;
-        }
-    int last = dim;
-    for (int d = dim + 1; d < g->nd; ++d)
-        if (astr[d] != 0) last = d;
-    for (int d = dim + 1; d <= last; ++d) {
-        am->ext_hi[nhi] = (unsigned)g->ext[d];
-        am->str_hi[nhi] = astr[d];
-        nhi++;
-    }
-    am->nlo = nlo;
-    am->nhi = nhi;
+    am->nlo = compress_terms(g, astr, 0, dim, am->lo);
+    am->nhi = compress_terms(g, astr, dim + 1, g->nd, am->hi);
     return SLB_OK;
 }
 
 static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
-                      const int64_t* astr, double scale, int on_device, int flags, const OutMap* omp)
+                      const int64_t* astr, double scale, int on_device, int flags, const OutMap* omp,
+                      const InMap* imp = nullptr)
 {
     if (!g || !it) return fail(SLB_E_ARG, "slb_sweep: NULL argument");
     if (dim < 0 || dim >= g->nd) return fail(SLB_E_ARG, "slb_sweep: dim=%d out of range", dim);
@@ -591,11 +615,11 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         // c = sol(interp, line) for every line: front -> back -> (stencil) -> front
         rc = bspline_presolve(c->stream, &it->bsp, g->front, g->back, v.inner, v.n, v.outer, &c->launches);
         if (rc) return fail(rc, "slb_sweep: B-spline pre-solve launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (omp) return fail(SLB_E_UNSUPPORTED, "re-shard output mapping with B-splines is not implemented");
+        if (omp || imp) return fail(SLB_E_UNSUPPORTED, "re-shard mappings with B-splines are not implemented");
         rc = launch_stencil(g, dim, it, g->back, g->front, am, flags, nullptr);
         return rc;  // result is in front: no swap
     }
-    rc = launch_stencil(g, dim, it, src, g->back, am, flags, omp);
+    rc = launch_stencil(g, dim, it, src, g->back, am, flags, omp, imp);
     if (rc) return rc;
     return slb_grid_swap(g);
 }
@@ -604,6 +628,38 @@ extern "C" int slb_sweep(slb_grid* g, int dim, const slb_interp* it, const doubl
                          const int64_t* astr, double scale, int on_device, int flags)
 {
     return sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, nullptr);
+}
+
+extern "C" int slb_sweep_ex(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+                            const int64_t* astr, double scale, int on_device, int flags, int reshard_mode, int bdim,
+                            int nblocks)
+{
+    if (reshard_mode == SLB_RESHARD_NONE || nblocks <= 1)
+        return sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, nullptr);
+    if (!g) return fail(SLB_E_ARG, "slb_sweep_ex: NULL grid");
+    if (dim < 0 || dim >= g->nd || bdim < 0 || bdim >= g->nd) return fail(SLB_E_ARG, "slb_sweep_ex: dim out of range");
+    if (g->ext[bdim] % nblocks != 0) return fail(SLB_E_ARG, "slb_sweep_ex: extent %lld of dim %d is not divisible by %d blocks", (long long)g->ext[bdim], bdim, nblocks);
+    View v = make_view(g, dim);
+    if (reshard_mode == SLB_RESHARD_OUT_BLOCKED) {
+        if (bdim != dim || dim == 0) return fail(SLB_E_UNSUPPORTED, "SLB_RESHARD_OUT_BLOCKED: the blocked dim must be the swept dim, and not dim 0");
+        OutMap om;
+        om.kc = (int)(g->ext[dim] / nblocks);
+        om.kblk = g->numel / nblocks;
+        om.bstride = (long long)om.kc * v.inner;
+        return sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, &om);
+    }
+    if (reshard_mode == SLB_RESHARD_IN_BLOCKED) {
+        if (dim != 0 || bdim == 0) return fail(SLB_E_UNSUPPORTED, "SLB_RESHARD_IN_BLOCKED: implemented for sweeps along dim 0 with another dim blocked");
+        InMap im;
+        unsigned long long L = 1;
+        for (int d = 1; d < bdim; ++d) L *= (unsigned long long)g->ext[d];
+        im.L = (unsigned)L;
+        im.q_ext = (unsigned)g->ext[bdim];
+        im.c = (unsigned)(g->ext[bdim] / nblocks);
+        im.blk_lines = (g->numel / g->ext[0]) / nblocks;
+        return sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, nullptr, &im);
+    }
+    return fail(SLB_E_ARG, "slb_sweep_ex: unknown reshard mode %d", reshard_mode);
 }
 
 extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)
@@ -756,7 +812,7 @@ extern "C" int slb_poisson_create(slb_ctx* c, int nsp, const int64_t* ext, const
     p->nsp = nsp;
     p->ntot = 1;
     for (int d = 0; d < nsp; ++d) {
-        if (ext[d] < 1 || ext[d] > 65536) {
+        if (ext[d] < 1 || ext[d] > 1024) {  // k_dft_line stages line + twiddles in 48 KB of shared memory
             delete p;
             return fail(SLB_E_ARG, "slb_poisson_create: extent[%d] invalid", d);
         }
@@ -789,45 +845,57 @@ extern "C" int slb_poisson_create(slb_ctx* c, int nsp, const int64_t* ext, const
     return SLB_OK;
 }
 
+// one DFT pass over dim d of the space grid
+template <bool REAL_IN, bool INVERSE, bool MULT, bool REAL_OUT>
+static void dft_pass(slb_poisson* p, int d, const void* in, void* out, const double* mult)
+{
+    long long inner = 1;
+    for (int q = 0; q < d; ++q) inner *= p->ext[q];
+    int n = (int)p->ext[d];
+    unsigned nlines = (unsigned)(p->ntot / n);
+    int threads = n >= 256 ? 256 : (n >= 128 ? 128 : 64);
+    size_t smem = 2 * (size_t)n * sizeof(double2);
+    k_dft_line<REAL_IN, INVERSE, MULT, REAL_OUT><<<nlines, threads, smem, p->ctx->stream>>>(in, out, inner, n, p->tw[d], mult);
+}
+
 extern "C" int slb_poisson_solve(slb_poisson* p, const double* rho_dev, double* const* E_dev)
 {
     if (!p || !rho_dev || !E_dev) return fail(SLB_E_ARG, "slb_poisson_solve: NULL argument");
     slb_ctx* c = p->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    long long ntot = p->ntot;
-    unsigned blocks = (unsigned)((ntot + 127) / 128);
-    // forward transform over every space dim: rho -> wa (spectrum)
+    const int nsp = p->nsp;
+    for (int x = 0; x < nsp; ++x)
+        if (!E_dev[x]) return fail(SLB_E_ARG, "slb_poisson_solve: E_dev[%d] is NULL", x);
+    // forward transform over every space dim: rho -> spectrum
     double2* cur = p->wa;
     double2* nxt = p->wb;
-    long long inner = 1;
-    for (int d = 0; d < p->nsp; ++d) {
-        int n = (int)p->ext[d];
-        if (d == 0)
-            k_dft_dim<true, false><<<blocks, 128, 0, c->stream>>>(rho_dev, cur, inner, n, ntot, p->tw[d]);
-        else {
-            k_dft_dim<false, false><<<blocks, 128, 0, c->stream>>>(cur, nxt, inner, n, ntot, p->tw[d]);
-            double2* t = cur; cur = nxt; nxt = t;
-        }
+    dft_pass<true, false, false, false>(p, 0, rho_dev, cur, nullptr);
+    LAUNCH_CHECK(c);
+    for (int d = 1; d < nsp; ++d) {
+        dft_pass<false, false, false, false>(p, d, cur, nxt, nullptr);
         LAUNCH_CHECK(c);
-        inner *= n;
+        double2* t = cur; cur = nxt; nxt = t;
     }
     double2* spec = cur;
-    double2* w1 = (spec == p->wa) ? p->wb : p->wa;
+    double2* w1 = nxt;
     double2* w2 = p->wc;
-    for (int x = 0; x < p->nsp; ++x) {
-        if (!E_dev[x]) return fail(SLB_E_ARG, "slb_poisson_solve: E_dev[%d] is NULL", x);
-        k_mult_imag<<<(unsigned)((ntot + 255) / 256), 256, 0, c->stream>>>(spec, p->mult[x], w1, ntot);
+    // per component: E_x = real(ifft(i * mult_x .* spectrum)); the multiplier is applied while the
+    // first inverse pass loads its input, the last pass stores the real part only
+    for (int x = 0; x < nsp; ++x) {
+        if (nsp == 1) {
+            dft_pass<false, true, true, true>(p, 0, spec, E_dev[x], p->mult[x]);
+            LAUNCH_CHECK(c);
+            continue;
+        }
+        dft_pass<false, true, true, false>(p, 0, spec, w1, p->mult[x]);
         LAUNCH_CHECK(c);
         double2 *a = w1, *b = w2;
-        inner = 1;
-        for (int d = 0; d < p->nsp; ++d) {
-            int n = (int)p->ext[d];
-            k_dft_dim<false, true><<<blocks, 128, 0, c->stream>>>(a, b, inner, n, ntot, p->tw[d]);
+        for (int d = 1; d < nsp - 1; ++d) {
+            dft_pass<false, true, false, false>(p, d, a, b, nullptr);
             LAUNCH_CHECK(c);
             double2* t = a; a = b; b = t;
-            inner *= n;
         }
-        k_real_part<<<(unsigned)((ntot + 255) / 256), 256, 0, c->stream>>>(a, E_dev[x], ntot);
+        dft_pass<false, true, false, true>(p, nsp - 1, a, E_dev[x], nullptr);
         LAUNCH_CHECK(c);
     }
     return SLB_OK;

@@ -107,62 +107,63 @@ __global__ void k_sub_scalar(double* __restrict__ x, long long n, const double* 
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: direct DFT along one dim of a small N-D array (the space grid: <= 256^2 / 1024 points
-// per dim).  out(a,k,b) = sum_j in(a,j,b) * tw[(j*k) mod n], tw[m] = exp(-+2 pi i m/n).
+// K5: direct DFT along one dim of the (small) space grid: <= 256^2 / 1024 points per dim.
+//   out(a,k,b) = sum_j in(a,j,b) * tw[(j*k) mod n],   tw[m] = exp(-+2 pi i m/n)
 // Convention of src/fftbig.jl:162-176 (FFTW): forward exp(-i..) unnormalised; inverse 1/n.
+// One block per line: the line and the twiddle table are staged in shared memory, thread k
+// accumulates output k.  Fusions: MULT applies fctv_k = i*m (src/poisson.jl:8,14) to the input
+// on the fly; REAL_OUT stores only the real part (the E field, src/poisson.jl:142).
+// The first version (one thread per output reading global memory) took 16-52 us per pass on
+// a 128^2 grid under ncu: 8% of a Strang step.
 // ------------------------------------------------------------------------------------------
-template <bool REAL_IN, bool INVERSE>
-__global__ void __launch_bounds__(128)
-k_dft_dim(const void* __restrict__ in_, double2* __restrict__ out, long long inner, int n, long long total,
-          const double2* __restrict__ tw)
+template <bool REAL_IN, bool INVERSE, bool MULT, bool REAL_OUT>
+__global__ void __launch_bounds__(256)
+k_dft_line(const void* __restrict__ in_, void* __restrict__ out_, long long inner, int n,
+           const double2* __restrict__ tw, const double* __restrict__ mult)
 {
-    long long id = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (id >= total) return;
-    long long a = id % inner;
-    long long r = id / inner;
-    int k = (int)(r % n);
-    long long b = r / n;
-    long long base = a + inner * (long long)n * b;
-    double sr = 0.0, si = 0.0;
-    int m = 0;
-    for (int j = 0; j < n; ++j) {
-        double2 t = __ldg(tw + m);
-        double ti = INVERSE ? -t.y : t.y;
-        if (REAL_IN) {
-            double v = __ldg(reinterpret_cast<const double*>(in_) + base + inner * j);
-            sr = fma(v, t.x, sr);
-            si = fma(v, ti, si);
-        } else {
-            double2 v = __ldg(reinterpret_cast<const double2*>(in_) + base + inner * j);
-            sr += v.x * t.x - v.y * ti;
-            si += v.x * ti + v.y * t.x;
+    extern __shared__ double2 dsm[];
+    double2* line = dsm;
+    double2* twd = dsm + n;
+    const long long ln = blockIdx.x;
+    const long long a = ln % inner, b = ln / inner;
+    const long long base = a + inner * (long long)n * b;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double2 t = __ldg(tw + j);
+        if (INVERSE) t.y = -t.y;
+        twd[j] = t;
+        double2 v;
+        if (REAL_IN)
+            v = make_double2(__ldg(reinterpret_cast<const double*>(in_) + base + inner * j), 0.0);
+        else
+            v = __ldg(reinterpret_cast<const double2*>(in_) + base + inner * j);
+        if (MULT) {
+            double mm = __ldg(mult + base + inner * j);
+            v = make_double2(-v.y * mm, v.x * mm);
         }
-        m += k;
-        if (m >= n) m -= n;
+        line[j] = v;
     }
-    if (INVERSE) {
-        double s = 1.0 / (double)n;
-        sr *= s;
-        si *= s;
+    __syncthreads();
+    const double scale = INVERSE ? 1.0 / (double)n : 1.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double sr = 0.0, si = 0.0;
+        int m = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            double2 t = twd[m];
+            double2 v = line[j];
+            sr = fma(v.x, t.x, sr);
+            sr = fma(-v.y, t.y, sr);
+            si = fma(v.x, t.y, si);
+            si = fma(v.y, t.x, si);
+            m += k;
+            if (m >= n) m -= n;
+        }
+        long long o = base + inner * k;
+        if (REAL_OUT)
+            reinterpret_cast<double*>(out_)[o] = sr * scale;
+        else
+            reinterpret_cast<double2*>(out_)[o] = make_double2(sr * scale, si * scale);
     }
-    out[id] = make_double2(sr, si);
-}
-
-// D = (i * m) .* C   (fctv_k is purely imaginary: src/poisson.jl:8,14)
-__global__ void k_mult_imag(const double2* __restrict__ c, const double* __restrict__ m, double2* __restrict__ d,
-                            long long n)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double2 v = c[i];
-    double mm = m[i];
-    d[i] = make_double2(-v.y * mm, v.x * mm);
-}
-
-__global__ void k_real_part(const double2* __restrict__ c, double* __restrict__ e, long long n)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) e[i] = c[i].x;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -32,13 +32,19 @@ struct CoefTab {  // weight polynomials, passed by value -> constant bank, unifo
     double c[SLB_P1MAX * SLB_NCMAX];
 };
 
-// alpha = scale * tab[ sum_d idx_d * stride_d ] over the dims below (lo) / above (hi) the swept one
+// alpha = scale * tab[ sum_d idx_d * stride_d ] over the dims below (lo) / above (hi) the swept one.
+// The host compresses the per-dim (extent, stride) list into terms idx = (x / div) % ext (zero-stride
+// dims dropped, layout-compatible neighbours merged, ext == 0: no modulo needed), so the usual
+// Vlasov cases cost at most one 32-bit division per line.
+struct AlphaTerm {
+    unsigned div, ext;
+    long long stride;
+};
 struct AlphaMap {
     const double* tab;
     double scale;
     int nlo, nhi;
-    unsigned ext_lo[SLB_MAXD], ext_hi[SLB_MAXD];
-    long long str_lo[SLB_MAXD], str_hi[SLB_MAXD];
+    AlphaTerm lo[SLB_MAXD], hi[SLB_MAXD];
 };
 
 // Generalised addressing of the swept index k on the OUTPUT side (multi-GPU re-shard fused
@@ -49,21 +55,42 @@ struct OutMap {
     long long bstride;  // offset between consecutive outer indices b (plain: n * inner)
 };
 
-__device__ __forceinline__ long long slb_alpha_off(const AlphaMap& m, unsigned long long a, unsigned long long b)
+// Generalised addressing of the INPUT lines of a contiguous-dim sweep (multi-GPU re-shard fused
+// into the sweep prologue): the input is stored block-major along a non-swept dim `bdim` (as an
+// all-to-all leaves it): line (lo, q, hi) with q the index along bdim lives at line index
+//   (q / c) * blk_lines + lo + L * ((q % c) + c * hi).          c == 0: plain layout.
+struct InMap {
+    unsigned L, q_ext, c;
+    long long blk_lines;
+};
+
+__device__ __forceinline__ long long slb_in_line(const InMap& im, long long line)
+{
+    if (im.c == 0) return line;
+    unsigned l = (unsigned)line;
+    unsigned lo = im.L > 1 ? l % im.L : 0u;
+    unsigned t = im.L > 1 ? l / im.L : l;
+    unsigned q = t % im.q_ext;
+    unsigned hi = t / im.q_ext;
+    unsigned blk = q / im.c;
+    unsigned qi = q - blk * im.c;
+    return (long long)blk * im.blk_lines + lo + (long long)im.L * (qi + (long long)im.c * hi);
+}
+
+__device__ __forceinline__ long long slb_alpha_off(const AlphaMap& m, unsigned a, unsigned b)
 {
     long long off = 0;
-    // the host trims zero-stride dims: nlo == 0 when alpha does not depend on the inner index
 #pragma unroll 1
     for (int d = 0; d < m.nlo; ++d) {
-        unsigned long long q = a / m.ext_lo[d];
-        off += (long long)(a - q * m.ext_lo[d]) * m.str_lo[d];
-        a = q;
+        unsigned q = m.lo[d].div > 1 ? a / m.lo[d].div : a;
+        if (m.lo[d].ext) q %= m.lo[d].ext;
+        off += (long long)q * m.lo[d].stride;
     }
 #pragma unroll 1
     for (int d = 0; d < m.nhi; ++d) {
-        unsigned long long q = b / m.ext_hi[d];
-        off += (long long)(b - q * m.ext_hi[d]) * m.str_hi[d];
-        b = q;
+        unsigned q = m.hi[d].div > 1 ? b / m.hi[d].div : b;
+        if (m.hi[d].ext) q %= m.hi[d].ext;
+        off += (long long)q * m.hi[d].stride;
     }
     return off;
 }
@@ -73,9 +100,14 @@ __device__ __forceinline__ void slb_split(double alpha, int n, int half, double&
 {
     double fl = floor(alpha);
     t = alpha - fl;
-    long long d = (long long)fl - half;
-    long long r = d % n;
-    s0 = (int)(r < 0 ? r + n : r);
+    if (fabs(fl) < 1.0e9) {  // the usual case: 32-bit arithmetic
+        int r = ((int)fl - half) % n;
+        s0 = r < 0 ? r + n : r;
+    } else {
+        long long d = (long long)fl - half;
+        long long r = d % n;
+        s0 = (int)(r < 0 ? r + n : r);
+    }
 }
 
 template <int P1, bool EXACT>
@@ -108,7 +140,7 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
     long long b = gid / inner;
     long long a = gid - b * inner;
 
-    double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, (unsigned long long)a, (unsigned long long)b));
+    double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, (unsigned)a, (unsigned)b));
     double t;
     int s0;
     slb_split(alpha, n, (P1 - 1) / 2, t, s0);
@@ -195,102 +227,154 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
 // ------------------------------------------------------------------------------------------
 template <int R>
 struct ContigCfg {
-    // row pitch (doubles) of the [e mod R][e div R] staging tile; chosen so that both the
-    // staging stores (lanes = consecutive e) and the window loads (lanes = consecutive
-    // columns) touch every bank pair exactly twice per 32 x 8 B request (the minimum).
-    static constexpr int PITCH = (R == 4) ? 40 : (R == 2 ? 48 : 32 + SLB_P1MAX);
+    // row pitch (doubles) of the [e mod R][e div R] staging tile.  64-bit shared accesses are
+    // served per half-warp: the 16 lanes e = 16h..16h+15 of a staging store hit rows e % R and
+    // columns e / R, so PITCH = 16/R * (odd) (mod 16) spreads them over all 16 bank pairs
+    // (ncu on the first version, PITCH 40 for R = 4: 3.7 wavefronts per store instead of 2).
+    // Window loads read consecutive columns of one row and are conflict-free for any pitch.
+    static constexpr int PITCH = (R == 4) ? 36 : (R == 2 ? 40 : 32 + SLB_P1MAX);
 };
 
 template <int P1, int R, bool EXACT>
 __global__ void __launch_bounds__(256)
 k_sweep_contig(const double* __restrict__ in, double* __restrict__ out, int n, long long nlines, AlphaMap am,
-               const double* __restrict__ coef, int nc)
+               const double* __restrict__ coef, int nc, InMap im, int lpw)
 {
     constexpr int WARPS = 8;
-    constexpr int SEG = 32 * R;           // outputs per warp pass
-    constexpr int W = SEG + P1 - 1;       // inputs staged per pass
+    constexpr int SEG = 32 * R;           // outputs per work item
+    constexpr int W = SEG + P1 - 1;       // inputs staged per work item
     constexpr int NLD = (W + 31) / 32;
+    constexpr int LASTW = W - 32 * (NLD - 1);  // active lanes of the last staging load
     constexpr int PITCH = ContigCfg<R>::PITCH;
     constexpr int NX = R + P1 - 1;
     __shared__ double sm[WARPS][R * PITCH];
+    __shared__ double scoef[SLB_NCMAX * P1];  // weight polynomials, [k][j]: lane j reads conflict-free
 
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     double* tile = sm[wid];
+    for (int i = threadIdx.x; i < nc * P1; i += blockDim.x) scoef[i] = __ldg(coef + (i % P1) * nc + i / P1);
+    __syncthreads();
 
-    for (long long line = (long long)blockIdx.x * WARPS + wid; line < nlines; line += (long long)gridDim.x * WARPS) {
-        double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, 0ull, (unsigned long long)line));
-        double t;
-        int s0;
-        slb_split(alpha, n, (P1 - 1) / 2, t, s0);
+    // each warp owns `lpw` consecutive lines; a work item is one segment of SEG outputs of one
+    // line, and the inputs of the next item are prefetched into registers while the current
+    // one is computed.  Consecutive lines often share alpha (Vlasov space sweeps: alpha depends
+    // on one velocity index only), so weights are recomputed only when alpha changes -- the
+    // device counterpart of the reference's CachePrecal memo (src/interpolation.jl:381-389).
+    const long long l0 = ((long long)blockIdx.x * WARPS + wid) * lpw;
+    if (l0 >= nlines) return;
+    const long long l1 = l0 + lpw < nlines ? l0 + lpw : nlines;
+    const bool wrap2 = (W <= 2 * n);  // two conditional subtractions bring any staged index into [0, n)
 
-        // lane j evaluates weight polynomial j, then the warp broadcasts
-        double wl = 0.0;
-        if (lane < P1) {
-            const double* c = coef + lane * nc;
-            wl = __ldg(c + nc - 1);
-            for (int k = nc - 2; k >= 0; --k) wl = fma(t, wl, __ldg(c + k));
-        }
-        double w[P1];
+    auto getalpha = [&](long long ln) { return am.scale * __ldg(am.tab + slb_alpha_off(am, 0u, (unsigned)ln)); };
+    auto load = [&](long long ln, int sg0, int s0_, double (&v)[NLD]) {
+        const double* lin = in + slb_in_line(im, ln) * n;
+        int g0 = s0_ + sg0;
+        g0 -= (g0 >= n) ? n : 0;
+        g0 += lane;
 #pragma unroll
-        for (int j = 0; j < P1; ++j) w[j] = __shfl_sync(0xffffffffu, wl, j);
-
-        const double* lin = in + line * n;
-        double* lout = out + line * n;
-
-        for (int seg0 = 0; seg0 < n; seg0 += SEG) {
-            int g0 = s0 + seg0;
-            if (g0 >= n) g0 -= n;
-#pragma unroll
-            for (int c = 0; c < NLD; ++c) {
-                int e = lane + 32 * c;
-                if (e < W) {
-                    int g = g0 + e;
-                    if (g >= n) {
-                        g -= n;
-                        if (g >= n) g %= n;
-                    }
-                    tile[(e % R) * PITCH + e / R] = __ldg(lin + g);
-                }
-            }
-            __syncwarp();
-            double x[NX];
-#pragma unroll
-            for (int jj = 0; jj < NX; ++jj) x[jj] = tile[(jj % R) * PITCH + lane + jj / R];
-            double o[R];
-#pragma unroll
-            for (int m = 0; m < R; ++m) {
-                double acc;
-                if (EXACT) {
-                    acc = __dmul_rn(x[m], w[0]);
-#pragma unroll
-                    for (int j = 1; j < P1; ++j) acc = __dadd_rn(acc, __dmul_rn(x[m + j], w[j]));
-                } else {
-                    acc = x[m] * w[0];
-#pragma unroll
-                    for (int j = 1; j < P1; ++j) acc = fma(x[m + j], w[j], acc);
-                }
-                o[m] = acc;
-            }
-            int i0 = seg0 + R * lane;
-            double* dst = lout + i0;
-            if (i0 + R <= n && ((reinterpret_cast<uintptr_t>(dst) & (R * 8 - 1)) == 0)) {
-                if (R == 4) {
-                    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(o[0]), "d"(o[1 % R]),
-                                 "d"(o[2 % R]), "d"(o[3 % R])
-                                 : "memory");
-                } else if (R == 2) {
-                    *reinterpret_cast<double2*>(dst) = make_double2(o[0], o[1 % R]);
-                } else {
-                    dst[0] = o[0];
-                }
+        for (int q = 0; q < NLD; ++q) {
+            int g = g0 + 32 * q;
+            if (wrap2) {
+                g -= (g >= n) ? n : 0;
+                g -= (g >= n) ? n : 0;
             } else {
-#pragma unroll
-                for (int m = 0; m < R; ++m)
-                    if (i0 + m < n) dst[m] = o[m];
+                g %= n;
             }
-            __syncwarp();
+            if (q < NLD - 1 || lane < LASTW)
+                v[q] = __ldg(lin + g);
+            else
+                v[q] = 0.0;
         }
+    };
+
+    long long line = l0;
+    int seg0 = 0, s0;
+    double alpha = getalpha(line), t;
+    slb_split(alpha, n, (P1 - 1) / 2, t, s0);
+    double v[NLD];
+    load(line, seg0, s0, v);
+    double w[P1];
+    double memo_alpha = 0.0;
+    bool have_w = false;
+
+    while (true) {
+        long long nline = line;
+        int nseg0 = seg0 + SEG, ns0 = s0;
+        double nalpha = alpha, nt = t;
+        if (nseg0 >= n) {
+            nseg0 = 0;
+            nline = line + 1;
+        }
+        const bool has_next = nline < l1;
+        double vn[NLD];
+        if (has_next) {
+            if (nline != line) {
+                nalpha = getalpha(nline);
+                if (nalpha != alpha) slb_split(nalpha, n, (P1 - 1) / 2, nt, ns0);
+            }
+            load(nline, nseg0, ns0, vn);
+        }
+        if (!have_w || alpha != memo_alpha) {
+            // lane j evaluates weight polynomial j (Horner, FMA), then the warp broadcasts
+            const int jl = lane < P1 ? lane : 0;
+            double wl = scoef[(nc - 1) * P1 + jl];
+            for (int k = nc - 2; k >= 0; --k) wl = fma(t, wl, scoef[k * P1 + jl]);
+#pragma unroll
+            for (int j = 0; j < P1; ++j) w[j] = __shfl_sync(0xffffffffu, wl, j);
+            memo_alpha = alpha;
+            have_w = true;
+        }
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int e = lane + 32 * q;
+            if (q < NLD - 1 || lane < LASTW) tile[(e % R) * PITCH + e / R] = v[q];
+        }
+        __syncwarp();
+        double x[NX];
+#pragma unroll
+        for (int jj = 0; jj < NX; ++jj) x[jj] = tile[(jj % R) * PITCH + lane + jj / R];
+        double o[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            double acc;
+            if (EXACT) {
+                acc = __dmul_rn(x[m], w[0]);
+#pragma unroll
+                for (int j = 1; j < P1; ++j) acc = __dadd_rn(acc, __dmul_rn(x[m + j], w[j]));
+            } else {
+                acc = x[m] * w[0];
+#pragma unroll
+                for (int j = 1; j < P1; ++j) acc = fma(x[m + j], w[j], acc);
+            }
+            o[m] = acc;
+        }
+        const int i0 = seg0 + R * lane;
+        double* dst = out + line * n + i0;
+        if (i0 + R <= n && ((reinterpret_cast<uintptr_t>(dst) & (R * 8 - 1)) == 0)) {
+            if (R == 4) {
+                asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(o[0]), "d"(o[1 % R]),
+                             "d"(o[2 % R]), "d"(o[3 % R])
+                             : "memory");
+            } else if (R == 2) {
+                *reinterpret_cast<double2*>(dst) = make_double2(o[0], o[1 % R]);
+            } else {
+                dst[0] = o[0];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                if (i0 + m < n) dst[m] = o[m];
+        }
+        __syncwarp();
+        if (!has_next) break;
+        line = nline;
+        seg0 = nseg0;
+        s0 = ns0;
+        alpha = nalpha;
+        t = nt;
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) v[q] = vn[q];
     }
 }
 
@@ -305,7 +389,7 @@ k_sweep_generic(const double* __restrict__ in, double* __restrict__ out, long lo
     if (gid >= nlines) return;
     long long b = gid / inner;
     long long a = gid - b * inner;
-    double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, (unsigned long long)a, (unsigned long long)b));
+    double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, (unsigned)a, (unsigned)b));
     double t;
     int s0;
     slb_split(alpha, n, (np - 1) / 2, t, s0);

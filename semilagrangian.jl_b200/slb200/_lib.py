@@ -43,6 +43,7 @@ SIGNATURES = [
     ("slb_interp_create", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, c_double_p, C.c_int, c_double_p, c_void_pp]),
     ("slb_interp_destroy", None, [C.c_void_p]),
     ("slb_sweep", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int]),
+    ("slb_sweep_ex", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("slb_presolve", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("slb_charge_density", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     ("slb_charge_density_raw", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
@@ -56,6 +57,7 @@ SIGNATURES = [
 ]
 
 SLB_SWEEP_EXACT = 1
+SLB_RESHARD_NONE, SLB_RESHARD_OUT_BLOCKED, SLB_RESHARD_IN_BLOCKED = 0, 1, 2
 
 
 class SlbError(RuntimeError):

@@ -1,0 +1,323 @@
+"""Sharded 2D2V driver: one process per GPU, torch.distributed (NCCL over NVLink) plumbing.
+
+Replaces the reference's MPI back-end (src/mpiinterface.jl:1-38, src/advection.jl:116-123,
+:269-292, :381-384), whose strategy is replicated data + work split + an all-gather by P
+broadcasts after EVERY sweep.  Here the 4-D grid f[x1,x2,v1,v2] is domain-decomposed in slabs
+and re-sharded with one all-to-all only when the sharded dimension must be swept:
+
+    layout B (shard x2): local [n1, n2/P, n3, n4]  -> sweeps along v1, v2; rho is a local reduction
+    layout A (shard v2): local [n1, n2, n3, n4/P]  -> sweeps along x1, x2
+
+A Strang step  v1 v2 | x1 x2 | v1 v2  needs two exchanges.  Neither needs a pack/unpack pass:
+  B -> A : a layout-B slab is already contiguous per destination (v2 is the slowest dim); the
+           received blocks form an array that is block-major along x2, which the x1 sweep reads
+           directly (slb_sweep_ex, SLB_RESHARD_IN_BLOCKED).
+  A -> B : the x2 sweep writes its output block-major along x2 (SLB_RESHARD_OUT_BLOCKED), so
+           each destination's block is contiguous; the received blocks concatenate along v2
+           into the standard layout-B slab.
+rho slabs are all-gathered (n1*n2/P doubles per rank) and the Poisson solve is replicated.
+
+The pure index bookkeeping (block-major packing, slab ranges, split sizes) is kept free of CUDA
+so that world_size-2 gloo tests on CPU cover it (tests/test_distributed_cpu.py).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .advection import modone  # noqa: F401  (re-exported for symmetry with advection.py)
+
+LAYOUT_A, LAYOUT_B = "A", "B"  # A: shard dim 3 (v2); B: shard dim 1 (x2)
+SHARD_DIM = {LAYOUT_A: 3, LAYOUT_B: 1}
+
+
+# ---------------------------------------------------------------------------------------------
+# pure layout algebra (numpy) -- shared by the CPU tests and the GPU driver's checks
+# ---------------------------------------------------------------------------------------------
+def splititr(nb, lgtot):
+    """src/util.jl:26-32: split 1..lgtot into nb contiguous ranges (1-based, inclusive)."""
+    lg, r = divmod(lgtot, nb)
+    out = [(x * (lg + 1) + 1, (x + 1) * (lg + 1)) for x in range(r)]
+    out += [(x * lg + r + 1, (x + 1) * lg + r) for x in range(r, nb)]
+    return out
+
+
+def splitvec(nb, v):
+    """src/util.jl:34-36"""
+    return [v[a - 1:b] for a, b in splititr(nb, len(v))]
+
+
+def slab(n, nranks, rank):
+    """[lo, hi) of rank's slab along a dim of extent n (equal slabs)."""
+    if n % nranks != 0:
+        raise ValueError(f"extent {n} is not divisible by {nranks} ranks")
+    c = n // nranks
+    return rank * c, (rank + 1) * c
+
+
+def local_shape(global_shape, layout, nranks):
+    s = list(global_shape)
+    d = SHARD_DIM[layout]
+    if s[d] % nranks != 0:
+        raise ValueError(f"extent {s[d]} of dim {d} is not divisible by {nranks} ranks")
+    s[d] //= nranks
+    return tuple(s)
+
+
+def to_block_major(arr, bdim, nblocks):
+    """Flat array holding `arr` (Fortran order) block-major along bdim: what a sweep with
+    SLB_RESHARD_OUT_BLOCKED writes / what SLB_RESHARD_IN_BLOCKED reads."""
+    c = arr.shape[bdim] // nblocks
+    parts = []
+    for s in range(nblocks):
+        idx = [slice(None)] * arr.ndim
+        idx[bdim] = slice(s * c, (s + 1) * c)
+        parts.append(np.asarray(arr[tuple(idx)]).reshape(-1, order="F"))
+    return np.concatenate(parts)
+
+
+def from_block_major(flat, shape, bdim, nblocks):
+    """inverse of to_block_major"""
+    shape = tuple(shape)
+    c = shape[bdim] // nblocks
+    bshape = list(shape)
+    bshape[bdim] = c
+    bl = int(np.prod(bshape))
+    out = np.empty(shape, dtype=flat.dtype, order="F")
+    for s in range(nblocks):
+        idx = [slice(None)] * len(shape)
+        idx[bdim] = slice(s * c, (s + 1) * c)
+        out[tuple(idx)] = flat[s * bl:(s + 1) * bl].reshape(bshape, order="F")
+    return out
+
+
+def exchange(dist, out_flat, in_flat, group=None):
+    """The re-shard collective: equal-split all-to-all of flat buffers (torch tensors on any
+    backend: nccl on the GPUs, gloo in the CPU tests)."""
+    dist.all_to_all_single(out_flat, in_flat, group=group)
+
+
+def reshard_B_to_A_reference(local_B, nranks, dist, torch, group=None):
+    """Host-side (CPU tensor) restatement of the B -> A exchange: returns the standard
+    layout-A slab.  Used by the gloo tests to pin the block conventions the kernels rely on."""
+    n1, c2, n3, n4 = local_B.shape
+    send = torch.from_numpy(np.ascontiguousarray(local_B.reshape(-1, order="F")))
+    recv = torch.empty_like(send)
+    exchange(dist, recv, send, group)
+    # received: nranks blocks, block s = [n1, c2, n3, c4] of rank s -> block-major along x2
+    return from_block_major(recv.numpy(), (n1, c2 * nranks, n3, n4 // nranks), 1, nranks)
+
+
+def reshard_A_to_B_reference(local_A, nranks, dist, torch, group=None):
+    """Host-side restatement of the A -> B exchange: returns the standard layout-B slab."""
+    n1, n2, n3, c4 = local_A.shape
+    send = torch.from_numpy(to_block_major(local_A, 1, nranks))
+    recv = torch.empty_like(send)
+    exchange(dist, recv, send, group)
+    # received blocks r = [n1, c2, n3, c4(r)] concatenate along the slowest dim
+    return recv.numpy().reshape((n1, n2 // nranks, n3, c4 * nranks), order="F")
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU driver
+# ---------------------------------------------------------------------------------------------
+class ShardedAdvectionData:
+    """Sharded counterpart of AdvectionData + PoissonVar for 2D2V Vlasov-Poisson
+    (4 states of examples/vlasov-poisson-2d2v.jl: v1, v2, x1, x2 with ndims = 1).
+
+    `data_local_B`: this rank's layout-B slab, shape [n1, n2/P, n3, n4] (numpy, Fortran order).
+    """
+
+    def __init__(self, adv, data_local_B, rank=None, world=None, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.P = dist.get_world_size(group) if world is None else world
+        if adv.N != 4:
+            raise ValueError("the sharded driver covers 2D2V grids (N = 4)")
+        for st in adv.states:
+            if st.ndims != 1 or not st.isconstdec:
+                raise NotImplementedError("const-shift 1-D states only")
+        self.adv = adv
+        self.gshape = adv.sizeall
+        n1, n2, n3, n4 = self.gshape
+        if n2 % self.P or n4 % self.P:
+            raise ValueError(f"n2={n2} and n4={n4} must be divisible by the number of ranks {self.P}")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx = _lib.Context(self.device.index, stream=stream)
+        self.nloc = n1 * n2 * n3 * n4 // self.P
+        self.bufs = [torch.empty(self.nloc, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.cur = 0  # index of the buffer holding f
+        self.layout = LAYOUT_B
+        self.blocked = False  # True while cur holds a block-major (just exchanged) layout-A array
+        shp = local_shape(self.gshape, LAYOUT_B, self.P)
+        if tuple(data_local_B.shape) != shp:
+            raise ValueError(f"local slab shape {tuple(data_local_B.shape)} must be {shp}")
+        host = torch.from_numpy(np.ascontiguousarray(np.asfortranarray(data_local_B).reshape(-1, order="F")))
+        self.bufs[0].copy_(host)
+        self._grids = {}
+        self.state_gen = 1
+        self.time_cur = 0.0
+        self.flags = 0
+        # Poisson pieces (replicated solve)
+        from .poisson import _get_fctv_k_imag
+
+        self.Nsp = 2
+        self.fctv = [np.ascontiguousarray(a.reshape(-1, order="F")) for a in _get_fctv_k_imag(adv)]
+        arr = (_lib.c_double_p * 2)(*[_lib.dptr(a) for a in self.fctv])
+        h = C.c_void_p()
+        _lib.check(_lib.lib().slb_poisson_create(self.ctx.h, 2, _lib.i64((n1, n2)), arr, C.byref(h)))
+        self.plan = h
+        self.rho_local = torch.empty(n1 * n2 // self.P, dtype=torch.float64, device=self.device)
+        self.rho = torch.empty(n1 * n2, dtype=torch.float64, device=self.device)
+        self.E = [torch.empty(n1 * n2, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.points = [torch.from_numpy(np.ascontiguousarray(m.points)).to(self.device) for m in adv.t_mesh]
+        self.has_field = False
+        self.n_exchanges = 0
+
+    # ---- grid handles over the two buffers ---------------------------------------------
+    def _grid(self, layout):
+        key = (layout, self.cur)
+        g = self._grids.get(key)
+        if g is None:
+            shp = local_shape(self.gshape, layout, self.P)
+            g = C.c_void_p()
+            _lib.check(_lib.lib().slb_grid_create_external(
+                self.ctx.h, 4, _lib.i64(shp), C.c_void_p(self.bufs[self.cur].data_ptr()),
+                C.c_void_p(self.bufs[1 - self.cur].data_ptr()), C.byref(g)))
+            self._grids[key] = g
+        return g
+
+    def _exchange(self):
+        self.dist.all_to_all_single(self.bufs[1 - self.cur], self.bufs[self.cur], group=self.group)
+        self.cur = 1 - self.cur
+        self.n_exchanges += 1
+
+    # ---- state machine (src/advection.jl:152-158, :358-367) ------------------------------
+    def getst(self):
+        return self.adv.getst(self.state_gen)
+
+    def getcur_t(self):
+        return self.adv.getcur_t(self.state_gen)
+
+    def nextstate(self):
+        if self.state_gen < self.adv.nbstates:
+            self.state_gen += 1
+            return True
+        self.state_gen = 1
+        self.time_cur += self.adv.dt_base
+        return False
+
+    # ---- field solve (src/poisson.jl:119-144) ---------------------------------------------
+    def compute_field(self):
+        if self.layout != LAYOUT_B or self.blocked:
+            raise RuntimeError("the charge density is a local reduction in layout B only")
+        adv = self.adv
+        dv = adv.t_mesh[2].step * adv.t_mesh[3].step
+        L = _lib.lib()
+        _lib.check(L.slb_charge_density_raw(self._grid(LAYOUT_B), 2, dv, C.c_void_p(self.rho_local.data_ptr())))
+        if self.P > 1:
+            self.dist.all_gather_into_tensor(self.rho, self.rho_local, group=self.group)
+        else:
+            self.rho.copy_(self.rho_local)
+        _lib.check(L.slb_subtract_mean(self.ctx.h, C.c_void_p(self.rho.data_ptr()), self.rho.numel()))
+        arr = (C.c_void_p * 2)(*[e.data_ptr() for e in self.E])
+        _lib.check(L.slb_poisson_solve(self.plan, C.c_void_p(self.rho.data_ptr()), arr))
+        self.has_field = True
+
+    def compute_ee(self):
+        """src/util_poisson.jl:156-162 (replicated: every rank returns the same value)"""
+        adv = self.adv
+        dx = adv.t_mesh[0].step * adv.t_mesh[1].step
+        tot = 0.0
+        for e in self.E:
+            v = C.c_double()
+            _lib.check(_lib.lib().slb_reduce_sumsq(self.ctx.h, C.c_void_p(e.data_ptr()), e.numel(), C.byref(v)))
+            tot += v.value
+        return dx * tot
+
+    # ---- one advection! call ---------------------------------------------------------------
+    def advection(self):
+        adv, st = self.adv, self.getst()
+        d = st.perm[0] - 1
+        dt = self.getcur_t()
+        n1, n2, n3, n4 = self.gshape
+        c2, c4 = n2 // self.P, n4 // self.P
+        need = LAYOUT_A if d < 2 else LAYOUT_B
+        interp = adv.t_interp[d]
+        L = _lib.lib()
+        mode, bdim = _lib.SLB_RESHARD_NONE, 0
+        if need != self.layout:
+            if not (need == LAYOUT_A and d == 0):
+                raise NotImplementedError("unsupported state order for the fused re-shard (needs x1 first after v-sweeps)")
+            if self.P > 1:
+                self._exchange()            # B -> A: received array is block-major along x2
+                mode, bdim = _lib.SLB_RESHARD_IN_BLOCKED, 1
+            self.layout = LAYOUT_A
+        strides = [0, 0, 0, 0]
+        if d >= 2:  # velocity sweep: alpha = (dt/dv_d) * E_{d-2}[x1, x2l + r*c2]   (src/poisson.jl:178-189)
+            if d == 2:
+                self.compute_field()
+            if not self.has_field:
+                raise RuntimeError("velocity state before any field solve")
+            strides[0], strides[1] = 1, n1
+            tab = self.E[d - 2].data_ptr() + 8 * self.rank * c2 * n1
+            tlen = c2 * n1
+            scale = dt / adv.t_mesh[d].step
+        else:       # space sweep: alpha = (-dt/dx_d) * v_{d+2}   (src/poisson.jl:191-203)
+            src = d + 2
+            strides[src] = 1
+            off = self.rank * c4 if src == 3 else 0
+            tab = self.points[src].data_ptr() + 8 * off
+            tlen = c4 if src == 3 else self.gshape[src]
+            scale = -dt / adv.t_mesh[d].step
+        # the last space sweep before velocity sweeps writes its output block-major along x2
+        nxt = adv.getst(self.state_gen + 1 if self.state_gen < adv.nbstates else 1).perm[0] - 1
+        reshard_after = (self.layout == LAYOUT_A and nxt >= 2)
+        if reshard_after and self.P > 1:
+            if d != 1 or mode != _lib.SLB_RESHARD_NONE:
+                raise NotImplementedError("unsupported state order for the fused re-shard (needs x2 last before v-sweeps)")
+            mode, bdim = _lib.SLB_RESHARD_OUT_BLOCKED, 1
+        g = self._grid(self.layout)
+        h = interp.handle(self.ctx, self.gshape[d])
+        _lib.check(L.slb_sweep_ex(g, d, h, C.c_void_p(tab), tlen, _lib.i64(strides), float(scale), 1, int(self.flags),
+                                  mode, bdim, self.P))
+        _lib.check(L.slb_grid_swap(g))  # keep the handle's orientation; the driver tracks `cur`
+        self.cur = 1 - self.cur
+        if reshard_after:
+            if self.P > 1:
+                self._exchange()            # A -> B: blocks concatenate along v2 into the layout-B slab
+            self.layout = LAYOUT_B
+        return self.nextstate()
+
+    # ---- data access ----------------------------------------------------------------------
+    def getdata_local(self):
+        """this rank's slab in the current layout (numpy, Fortran order); valid between steps"""
+        self.torch.cuda.synchronize(self.device)
+        flat = self.bufs[self.cur].cpu().numpy()
+        return flat.reshape(local_shape(self.gshape, self.layout, self.P), order="F")
+
+    def gather_global(self):
+        """full array on every rank (tests only)"""
+        loc = self.getdata_local()
+        t = self.torch.from_numpy(np.ascontiguousarray(loc.reshape(-1, order="F"))).to(self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.P)]
+        if self.P > 1:
+            self.dist.all_gather(out, t, group=self.group)
+        else:
+            out = [t]
+        d = SHARD_DIM[self.layout]
+        shp = local_shape(self.gshape, self.layout, self.P)
+        parts = [o.cpu().numpy().reshape(shp, order="F") for o in out]
+        return np.asfortranarray(np.concatenate(parts, axis=d))
+
+    def close(self):
+        for g in self._grids.values():
+            _lib.lib().slb_grid_destroy(g)
+        self._grids = {}
+        if self.plan:
+            _lib.lib().slb_poisson_destroy(self.plan)
+            self.plan = None

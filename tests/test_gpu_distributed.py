@@ -1,0 +1,96 @@
+"""GPU checks of the re-shard-fused sweeps (slb_sweep_ex) on ONE device, plus the sharded
+driver with a single rank (P = 1 degenerates to the plain driver).  Multi-rank runs are
+exercised by bench.py --gpus N and tools/check_sharded.py under torchrun."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from helpers import DeviceGrid, make_pair, oracle_sweep, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _sweep_ex(f_flat_or_arr, shape, dim, interp, tab, astride, mode, bdim, nblocks):
+    from slb200 import _lib
+
+    ctx = _lib.default_context()
+    g = DeviceGrid(np.zeros(shape, order="F"))
+    flat = np.ascontiguousarray(f_flat_or_arr.reshape(-1, order="F"))
+    _lib.check(_lib.lib().slb_grid_upload(g.h, flat.ctypes.data_as(C.c_void_p)))
+    tab = np.ascontiguousarray(tab, dtype=np.float64)
+    h = interp.handle(ctx, shape[dim])
+    _lib.check(_lib.lib().slb_sweep_ex(g.h, dim, h, tab.ctypes.data_as(C.c_void_p), tab.size, _lib.i64(astride), 1.0, 0, 0,
+                                       mode, bdim, nblocks))
+    out = g.get()
+    g.close()
+    return out
+
+
+@pytest.mark.parametrize("nblocks", [2, 4, 8])
+def test_out_blocked_equals_block_major_of_plain_sweep(nblocks):
+    from slb200 import distributed as D, _lib
+
+    rng = np.random.default_rng(1)
+    shape = (32, 64, 6, 4)
+    f = np.asfortranarray(rng.random(shape))
+    interp, ointerp = make_pair("lagrange", 7, shape[1])
+    tab = rng.uniform(-6, 6, shape[3])
+    ref = oracle_sweep(f, 1, ointerp, tab, [0, 0, 0, 1])
+    out = _sweep_ex(f, shape, 1, interp, tab, [0, 0, 0, 1], _lib.SLB_RESHARD_OUT_BLOCKED, 1, nblocks)
+    got = D.from_block_major(out.reshape(-1, order="F"), shape, 1, nblocks)
+    assert relerr(got, ref) <= 1e-12
+
+
+@pytest.mark.parametrize("nblocks", [2, 4, 8])
+def test_in_blocked_reads_block_major_input(nblocks):
+    from slb200 import distributed as D, _lib
+
+    rng = np.random.default_rng(2)
+    shape = (128, 16, 5, 3)
+    f = np.asfortranarray(rng.random(shape))
+    interp, ointerp = make_pair("lagrange", 7, shape[0])
+    tab = rng.uniform(-6, 6, shape[2])
+    ref = oracle_sweep(f, 0, ointerp, tab, [0, 0, 1, 0])
+    fb = D.to_block_major(f, 1, nblocks)
+    out = _sweep_ex(fb, shape, 0, interp, tab, [0, 0, 1, 0], _lib.SLB_RESHARD_IN_BLOCKED, 1, nblocks)
+    assert relerr(out, ref) <= 1e-12
+    # blocked along dim 2 (L > 1 path)
+    fb2 = D.to_block_major(f, 2, 5)
+    out2 = _sweep_ex(fb2, shape, 0, interp, tab, [0, 0, 1, 0], _lib.SLB_RESHARD_IN_BLOCKED, 2, 5)
+    assert relerr(out2, ref) <= 1e-12
+
+
+def test_sharded_driver_single_rank_matches_plain_driver():
+    """P = 1: the sharded driver must reproduce the plain AdvectionData history."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    import slb200 as S
+    from slb200.distributed import ShardedAdvectionData
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    n = 16
+    ms = (S.UniformMesh(0.0, 4 * math.pi, n), S.UniformMesh(0.0, 4 * math.pi, n), S.UniformMesh(-6.0, 6.0, n), S.UniformMesh(-6.0, 6.0, n))
+    tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+    adv = S.Advection(ms, [S.Lagrange(7)] * 4, 0.1, tabst)
+    fsp = lambda x: 0.5 * np.cos(x / 2) + 1
+    fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+    f = S.dotprod((fsp(ms[0].points), fsp(ms[1].points), fv(ms[2].points), fv(ms[3].points)))
+    plain = S.AdvectionData(adv, f, S.getpoissonvar(adv))
+    sh = ShardedAdvectionData(adv, f)
+    for _ in range(2):
+        while S.advection(plain):
+            pass
+        while sh.advection():
+            pass
+        assert abs(sh.compute_ee() - S.compute_ee(plain)) <= 1e-13 * abs(S.compute_ee(plain))
+    assert relerr(sh.gather_global(), plain.getdata()) <= 1e-13
+    sh.close()
+    dist.destroy_process_group()
