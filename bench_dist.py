@@ -48,10 +48,10 @@ def run_distributed(args, B):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     dist.barrier()
-    e0.record()
+    e0.record(sh.stream)  # events on the stream the sweeps and collectives run on
     for _ in range(args.steps):
         step()
-    e1.record()
+    e1.record(sh.stream)
     torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -67,10 +67,11 @@ def run_distributed(args, B):
         torch.cuda.synchronize()
         dist.barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(reps):
-            fn()
-        a1.record()
+        with torch.cuda.stream(sh.stream):
+            a0.record(sh.stream)
+            for _ in range(reps):
+                fn()
+            a1.record(sh.stream)
         torch.cuda.synchronize()
         t = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -81,16 +82,19 @@ def run_distributed(args, B):
 
     # e2e: host slab in, host slab out, every step (pinned host memory)
     host = torch.empty(n**4 // world, dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
     host.copy_(sh.bufs[sh.cur])
     e2e_steps = max(1, min(args.steps, 3))
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sh.bufs[sh.cur].copy_(host, non_blocking=True)
+        with torch.cuda.stream(sh.stream):
+            sh.bufs[sh.cur].copy_(host, non_blocking=True)
         step()
         _ = sh.compute_ee()
-        host.copy_(sh.bufs[sh.cur], non_blocking=True)
+        with torch.cuda.stream(sh.stream):
+            host.copy_(sh.bufs[sh.cur], non_blocking=True)
         torch.cuda.synchronize()
     dist.barrier()
     wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")

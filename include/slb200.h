@@ -153,6 +153,14 @@ int slb_charge_density(slb_grid* g, int nsp, double dv, double* rho_dev);
  * which all-gathers slabs of rho before removing the mean */
 int slb_charge_density_raw(slb_grid* g, int nsp, double dv, double* rho_dev);
 int slb_subtract_mean(slb_ctx* ctx, double* dev, int64_t n);
+/* Charge density without a dedicated pass over f: when `linesum_dev` is set (nlines doubles), every
+ * fast-path sweep along a dim > 0 also stores, per line, the sum of the line's outputs.  After a
+ * sweep along a VELOCITY dim those sums are f reduced over that dim, so
+ * slb_charge_density_from(linesums viewed as [nsp_total, nv_total / n_dim]) equals compute_charge!
+ * of the swept array (src/util_poisson.jl:68-79) at 1/n_dim of the traffic.  NULL disables. */
+int slb_grid_set_linesum(slb_grid* g, double* linesum_dev);
+int slb_charge_density_from(slb_ctx* ctx, const double* f_dev, int64_t nsp_total, int64_t nv_total, double dv,
+                            double* rho_dev, int subtract_mean);
 
 /* PoissonConst (src/poisson.jl:35-59): fctv_imag[x] = imag part of fctv_k[x]
  * (src/poisson.jl:7-15), each prod(extents) doubles, column-major, host pointers. */

@@ -71,6 +71,7 @@ struct slb_grid {
     int64_t numel;
     double *front, *back;
     bool owned;
+    double* linesum;  // optional: per-line sums of the next strided sweeps' outputs
 };
 
 struct slb_interp {
@@ -293,6 +294,7 @@ static int grid_init(slb_ctx* c, int nd, const int64_t* ext, slb_grid** out)
     g->numel = numel;
     g->front = g->back = nullptr;
     g->owned = false;
+    g->linesum = nullptr;
     *out = g;
     return SLB_OK;
 }
@@ -350,6 +352,13 @@ extern "C" int slb_grid_download(const slb_grid* g, double* host)
     if (!g || !host) return fail(SLB_E_ARG, "slb_grid_download: NULL argument");
     CUDA_TRY(cudaMemcpyAsync(host, g->front, g->numel * sizeof(double), cudaMemcpyDeviceToHost, g->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(g->ctx->stream));
+    return SLB_OK;
+}
+
+extern "C" int slb_grid_set_linesum(slb_grid* g, double* dev)
+{
+    if (!g) return fail(SLB_E_ARG, "grid is NULL");
+    g->linesum = dev;
     return SLB_OK;
 }
 
@@ -450,14 +459,14 @@ static View make_view(const slb_grid* g, int dim)
 
 template <int P1>
 static void launch_strided(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
-                           const slb_interp* it, const OutMap& om, bool exact)
+                           const slb_interp* it, const OutMap& om, bool exact, double* linesum)
 {
     long long nlines = v.inner * v.outer;
     unsigned blocks = (unsigned)((nlines + 127) / 128);
     if (exact)
-        k_sweep_strided<P1, true><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om);
+        k_sweep_strided<P1, true><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om, linesum);
     else
-        k_sweep_strided<P1, false><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om);
+        k_sweep_strided<P1, false><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om, linesum);
 }
 
 template <int P1, int R>
@@ -507,6 +516,8 @@ static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const doub
         om.bstride = (long long)v.n * v.inner;
     }
     int P1 = it->order + 1;
+    if (g->linesum && (dim == 0 || !it->fast || omp))
+        return fail(SLB_E_UNSUPPORTED, "line sums are produced by fast-path sweeps along dim > 0 in the plain layout only");
     InMap im;
     memset(&im, 0, sizeof(im));
     if (imp) {
@@ -522,7 +533,7 @@ static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const doub
             }
         } else {
             switch (P1) {
-#define X(P) case P: launch_strided<P>(c, in, out, v, am, it, om, exact); break;
+#define X(P) case P: launch_strided<P>(c, in, out, v, am, it, om, exact, g->linesum); break;
                 SLB_FOR_P1(X)
 #undef X
             }
@@ -721,15 +732,30 @@ extern "C" int slb_subtract_mean(slb_ctx* c, double* dev, int64_t n)
     return SLB_OK;
 }
 
+static int charge_from(slb_ctx* c, const double* f, long long ns, long long nv, double dv, double* rho_dev);
+
 extern "C" int slb_charge_density_raw(slb_grid* g, int nsp, double dv, double* rho_dev)
 {
     if (!g || !rho_dev) return fail(SLB_E_ARG, "slb_charge_density: NULL argument");
     if (nsp < 1 || nsp >= g->nd) return fail(SLB_E_ARG, "slb_charge_density: nsp=%d must be in [1,%d)", nsp, g->nd);
-    slb_ctx* c = g->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
     long long ns = 1, nv = 1;
     for (int d = 0; d < nsp; ++d) ns *= g->ext[d];
     for (int d = nsp; d < g->nd; ++d) nv *= g->ext[d];
+    return charge_from(g->ctx, g->front, ns, nv, dv, rho_dev);
+}
+
+extern "C" int slb_charge_density_from(slb_ctx* c, const double* f_dev, int64_t nsp_total, int64_t nv_total, double dv,
+                                       double* rho_dev, int subtract_mean)
+{
+    if (!c || !f_dev || !rho_dev || nsp_total < 1 || nv_total < 1) return fail(SLB_E_ARG, "slb_charge_density_from: bad argument");
+    int rc = charge_from(c, f_dev, nsp_total, nv_total, dv, rho_dev);
+    if (rc || !subtract_mean) return rc;
+    return slb_subtract_mean(c, rho_dev, nsp_total);
+}
+
+static int charge_from(slb_ctx* c, const double* fsrc, long long ns, long long nv, double dv, double* rho_dev)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
     long long xt = (ns + 31) / 32;
     // enough blocks to fill the machine a few times over, at least 64 velocity rows per block
     long long want = (long long)c->sm_count * 16;
@@ -744,7 +770,7 @@ extern "C" int slb_charge_density_raw(slb_grid* g, int nsp, double dv, double* r
     if (rc) return rc;
     double* partial = (double*)c->scratch;
     dim3 grid((unsigned)xt, (unsigned)nchunk), block(32, 8);
-    k_charge_partial<<<grid, block, 0, c->stream>>>(g->front, ns, nv, chunk, partial);
+    k_charge_partial<<<grid, block, 0, c->stream>>>(fsrc, ns, nv, chunk, partial);
     LAUNCH_CHECK(c);
     k_charge_final<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(partial, ns, (int)nchunk, dv, rho_dev);
     LAUNCH_CHECK(c);

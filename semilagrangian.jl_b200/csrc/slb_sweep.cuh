@@ -133,7 +133,7 @@ __device__ __forceinline__ double slb_dot(const double (&x)[P1], const double (&
 template <int P1, bool EXACT>
 __global__ void __launch_bounds__(128)
 k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long long inner, int n, long long nlines,
-                AlphaMap am, CoefTab ct, int nc, OutMap om)
+                AlphaMap am, CoefTab ct, int nc, OutMap om, double* __restrict__ linesum)
 {
     long long gid = (long long)blockIdx.x * 128 + threadIdx.x;
     if (gid >= nlines) return;
@@ -178,6 +178,7 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
     for (int r = 0; r < P1; ++r) SLB_LOAD_NEXT(nxa[r]);
 
     const bool plain = (om.kc >= n);
+    double lsum = 0.0;  // sum of this line's outputs: feeds the charge density without another pass over f
     double* po = pout;
     int ko = 0;  // position inside the current output k-block
 
@@ -199,6 +200,7 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
         if ((tb) + r < n) {                                 \
             win[(r + P1 - 1) % P1] = buf[r];                \
             double acc = slb_dot<P1, EXACT>(win, w, r);     \
+            lsum += acc;                                    \
             SLB_STORE(acc);                                 \
         }                                                   \
     }
@@ -217,6 +219,7 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
             SLB_COMPUTE_GROUP(nxb, t0 + P1);
         }
     }
+    if (linesum) linesum[gid] = lsum;
 #undef SLB_COMPUTE_GROUP
 #undef SLB_STORE
 #undef SLB_LOAD_NEXT

@@ -47,6 +47,8 @@ SIGNATURES = [
     ("slb_presolve", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("slb_charge_density", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     ("slb_charge_density_raw", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    ("slb_grid_set_linesum", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_charge_density_from", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_int]),
     ("slb_subtract_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     ("slb_poisson_create", C.c_int, [C.c_void_p, C.c_int, c_int64_p, C.POINTER(c_double_p), c_void_pp]),
     ("slb_poisson_destroy", None, [C.c_void_p]),
@@ -105,9 +107,15 @@ def dptr(a):
 class Context:
     """One per process and GPU (slb_ctx)."""
 
+    LEGACY_DEFAULT_STREAM = 1  # cudaStreamLegacy: adopt the default stream explicitly
+
     def __init__(self, device=0, stream=None):
+        """stream: None -> the library creates a private non-blocking stream; an integer
+        cudaStream_t handle -> adopt it (0, torch's default stream, is passed as cudaStreamLegacy)."""
         h = C.c_void_p()
-        check(lib().slb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        if stream is not None and int(stream) == 0:
+            stream = self.LEGACY_DEFAULT_STREAM
+        check(lib().slb_ctx_create(int(device), C.c_void_p(int(stream)) if stream is not None else None, C.byref(h)))
         self.h = h
         self.device = device
 

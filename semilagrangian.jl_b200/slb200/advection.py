@@ -115,6 +115,9 @@ class AdvectionData:
         h = C.c_void_p()
         _lib.check(_lib.lib().slb_grid_create(self.ctx.h, adv.N, _lib.i64(adv.sizeall), C.byref(h)))
         self.grid = h
+        self._linesum = None        # device buffer for per-line output sums (see poisson.py)
+        self._linesum_dim = None    # dim whose sweep produced the sums currently held, else None
+        self.use_linesum = True
         self.upload(data)
         # mesh nodes stay on the device: shift tables for space sweeps (src/poisson.jl:191-203)
         self._points_dev = {}
@@ -124,6 +127,7 @@ class AdvectionData:
         host = np.asfortranarray(data, dtype=np.float64)
         _lib.check(_lib.lib().slb_grid_upload(self.grid, host.ctypes.data_as(C.c_void_p)))
         self.ctx.sync()
+        self._linesum_dim = None
 
     def getdata(self, out=None):
         """getdata(advd) (src/advection.jl:317): a host copy of the device-resident array."""
@@ -172,6 +176,9 @@ class AdvectionData:
         for p in self._points_dev.values():
             self.ctx.free(p)
         self._points_dev = {}
+        if self._linesum is not None:
+            self.ctx.free(self._linesum)
+            self._linesum = None
         if hasattr(self.parext, "close"):
             self.parext.close()
 
@@ -186,19 +193,32 @@ def getdata(advd):
     return advd.getdata()
 
 
-def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0):
+def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0, want_linesum=False):
     """One slb_sweep on advd's grid (kernel seam).  table: device pointer (c_void_p) when
-    on_device else a float64 numpy array."""
+    on_device else a float64 numpy array.  want_linesum: also store, per line, the sum of the
+    line's outputs (consumed by the Poisson provider's next charge density)."""
     n = advd.adv.sizeall[dim0]
     h = interp.handle(advd.ctx, n)
+    advd._linesum_dim = None  # any sweep invalidates sums held from an earlier one
+    ls_ok = want_linesum and advd.use_linesum and dim0 > 0 and interp.order + 1 <= 14 and interp.tabfct.shape[1] <= 14
+    if ls_ok:
+        if advd._linesum is None:
+            advd._linesum = advd.ctx.malloc(int(np.prod(advd.adv.sizeall)) // min(advd.adv.sizeall[1:]) * 8)
+        _lib.check(_lib.lib().slb_grid_set_linesum(advd.grid, advd._linesum))
     if on_device:
         ptr, length = table
     else:
         table = np.ascontiguousarray(table, dtype=np.float64)
         ptr, length = table.ctypes.data_as(C.c_void_p), table.size
-    _lib.check(
-        _lib.lib().slb_sweep(advd.grid, int(dim0), h, ptr, int(length), _lib.i64(strides), float(scale), 1 if on_device else 0, int(flags))
-    )
+    try:
+        _lib.check(
+            _lib.lib().slb_sweep(advd.grid, int(dim0), h, ptr, int(length), _lib.i64(strides), float(scale), 1 if on_device else 0, int(flags))
+        )
+    finally:
+        if ls_ok:
+            _lib.check(_lib.lib().slb_grid_set_linesum(advd.grid, None))
+    if ls_ok:
+        advd._linesum_dim = dim0
 
 
 def advection(advd):
@@ -213,5 +233,6 @@ def advection(advd):
     ext = advd.parext
     ext.initcoef(advd)  # src/advection.jl:407-408
     table, strides, scale, on_device = ext.alpha_table(advd)
-    sweep(advd, st.perm[0] - 1, interp, table, strides, scale, on_device, advd.flags)
+    want = bool(getattr(ext, "wants_linesum", lambda a: False)(advd))
+    sweep(advd, st.perm[0] - 1, interp, table, strides, scale, on_device, advd.flags, want_linesum=want)
     return advd.nextstate()

@@ -146,8 +146,10 @@ class ShardedAdvectionData:
         if n2 % self.P or n4 % self.P:
             raise ValueError(f"n2={n2} and n4={n4} must be divisible by the number of ranks {self.P}")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.ctx = _lib.Context(self.device.index, stream=stream)
+        # one dedicated stream carries the sweeps AND the collectives: torch.distributed orders its
+        # NCCL work against the current stream, so every call below runs under this stream
+        self.stream = torch.cuda.Stream(self.device)
+        self.ctx = _lib.Context(self.device.index, stream=self.stream.cuda_stream)
         self.nloc = n1 * n2 * n3 * n4 // self.P
         self.bufs = [torch.empty(self.nloc, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.cur = 0  # index of the buffer holding f
@@ -157,7 +159,9 @@ class ShardedAdvectionData:
         if tuple(data_local_B.shape) != shp:
             raise ValueError(f"local slab shape {tuple(data_local_B.shape)} must be {shp}")
         host = torch.from_numpy(np.ascontiguousarray(np.asfortranarray(data_local_B).reshape(-1, order="F")))
-        self.bufs[0].copy_(host)
+        with torch.cuda.stream(self.stream):
+            self.bufs[0].copy_(host)
+        self.stream.synchronize()
         self._grids = {}
         self.state_gen = 1
         self.time_cur = 0.0
@@ -177,6 +181,7 @@ class ShardedAdvectionData:
         self.points = [torch.from_numpy(np.ascontiguousarray(m.points)).to(self.device) for m in adv.t_mesh]
         self.has_field = False
         self.n_exchanges = 0
+        torch.cuda.synchronize(self.device)  # buffers above were filled on torch's default stream
 
     # ---- grid handles over the two buffers ---------------------------------------------
     def _grid(self, layout):
@@ -192,6 +197,7 @@ class ShardedAdvectionData:
         return g
 
     def _exchange(self):
+        # called under `with torch.cuda.stream(self.stream)`
         self.dist.all_to_all_single(self.bufs[1 - self.cur], self.bufs[self.cur], group=self.group)
         self.cur = 1 - self.cur
         self.n_exchanges += 1
@@ -213,6 +219,10 @@ class ShardedAdvectionData:
 
     # ---- field solve (src/poisson.jl:119-144) ---------------------------------------------
     def compute_field(self):
+        with self.torch.cuda.stream(self.stream):
+            self._compute_field()
+
+    def _compute_field(self):
         if self.layout != LAYOUT_B or self.blocked:
             raise RuntimeError("the charge density is a local reduction in layout B only")
         adv = self.adv
@@ -241,6 +251,10 @@ class ShardedAdvectionData:
 
     # ---- one advection! call ---------------------------------------------------------------
     def advection(self):
+        with self.torch.cuda.stream(self.stream):
+            return self._advection()
+
+    def _advection(self):
         adv, st = self.adv, self.getst()
         d = st.perm[0] - 1
         dt = self.getcur_t()
@@ -260,7 +274,7 @@ class ShardedAdvectionData:
         strides = [0, 0, 0, 0]
         if d >= 2:  # velocity sweep: alpha = (dt/dv_d) * E_{d-2}[x1, x2l + r*c2]   (src/poisson.jl:178-189)
             if d == 2:
-                self.compute_field()
+                self._compute_field()
             if not self.has_field:
                 raise RuntimeError("velocity state before any field solve")
             strides[0], strides[1] = 1, n1
@@ -296,7 +310,7 @@ class ShardedAdvectionData:
     # ---- data access ----------------------------------------------------------------------
     def getdata_local(self):
         """this rank's slab in the current layout (numpy, Fortran order); valid between steps"""
-        self.torch.cuda.synchronize(self.device)
+        self.stream.synchronize()
         flat = self.bufs[self.cur].cpu().numpy()
         return flat.reshape(local_shape(self.gshape, self.layout, self.P), order="F")
 
@@ -307,6 +321,7 @@ class ShardedAdvectionData:
         out = [self.torch.empty_like(t) for _ in range(self.P)]
         if self.P > 1:
             self.dist.all_gather(out, t, group=self.group)
+            self.torch.cuda.synchronize(self.device)
         else:
             out = [t]
         d = SHARD_DIM[self.layout]

@@ -78,7 +78,24 @@ class PoissonVar(AbstractExtDataAdv):
         dv = 1.0
         for m in self.adv.t_mesh[self.Nsp:]:
             dv = dv * m.step
+        d = getattr(advd, "_linesum_dim", None)
+        if d is not None and d >= self.Nsp:
+            # the previous sweep ran along velocity dim d and left sum_d f per line: rho needs only
+            # the remaining velocity dims (1/n_d of the traffic of a pass over f)
+            nv_rest = int(np.prod(self.adv.sizeall[self.Nsp:])) // self.adv.sizeall[d]
+            _lib.check(_lib.lib().slb_charge_density_from(self.ctx.h, advd._linesum, self.nsp_tot, nv_rest, dv, self.rho_dev, 1))
+            return
         _lib.check(_lib.lib().slb_charge_density(advd.grid, self.Nsp, dv, self.rho_dev))
+
+    def wants_linesum(self, advd):
+        """True when the NEXT advection! call starts with compute_charge! (src/poisson.jl:171-174)
+        and the current sweep runs along a velocity dim, so its line sums can feed it."""
+        adv = advd.adv
+        st = advd.getst()
+        if st.perm[0] <= self.Nsp:
+            return False
+        nxt = adv.getst(advd.state_gen + 1 if advd.state_gen < adv.nbstates else 1)
+        return nxt.perm[0] > self.Nsp and (self.Nsp + 1) in nxt.perm[: nxt.ndims]
 
     # src/poisson.jl:139-144
     def compute_elfield(self):
