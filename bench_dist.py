@@ -28,7 +28,15 @@ def run_distributed(args, B):
     a, b, c, d = vecs
     loc = np.empty((n, hi - lo, n, n), order="F")
     B.fill_product(loc, (a, b[lo:hi], c, d))
-    sh = ShardedAdvectionData(adv, loc)
+    exchange = getattr(args, "exchange", "p2p")
+    try:
+        sh = ShardedAdvectionData(adv, loc, exchange=exchange)
+    except Exception as exc:  # CUDA IPC unavailable (container restrictions): NCCL all-to-all instead
+        if exchange != "p2p":
+            raise
+        if rank == 0:
+            print(f"[bench] p2p exchange unavailable ({exc}); falling back to NCCL all-to-all", flush=True)
+        sh = ShardedAdvectionData(adv, loc, exchange="nccl")
     del loc
     cells_per_step = 6 * n**4
 
@@ -77,25 +85,27 @@ def run_distributed(args, B):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms_a2a = timed(lambda: dist.all_to_all_single(sh.bufs[1 - sh.cur], sh.bufs[sh.cur]))
     nbytes_local = n**4 * 8 // world
+    if sh.exchange == "nccl":
+        ms_a2a = timed(lambda: dist.all_to_all_single(sh.bufs[1 - sh.cur], sh.bufs[sh.cur]))
+    else:
+        ms_a2a = None
 
     # e2e: host slab in, host slab out, every step (pinned host memory)
-    host = torch.empty(n**4 // world, dtype=torch.float64).pin_memory()
+    from slb200 import _lib
+
+    host, _hp = _lib.pinned_empty((n**4 // world,))
     torch.cuda.synchronize()
-    host.copy_(sh.bufs[sh.cur])
+    sh.download_local(host)
     e2e_steps = max(1, min(args.steps, 3))
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        with torch.cuda.stream(sh.stream):
-            sh.bufs[sh.cur].copy_(host, non_blocking=True)
+        sh.upload_local(host)       # H2D of this rank's slab (pinned), on the driver's stream
         step()
-        _ = sh.compute_ee()
-        with torch.cuda.stream(sh.stream):
-            host.copy_(sh.bufs[sh.cur], non_blocking=True)
-        torch.cuda.synchronize()
+        _ = sh.compute_ee()         # D2H scalar
+        sh.download_local(host)     # D2H of the slab; synchronises
     dist.barrier()
     wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(wall, op=dist.ReduceOp.MAX)
@@ -111,8 +121,10 @@ def run_distributed(args, B):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": B.UNIT, "h2d_bytes_per_step": nbytes_local * world, "d2h_bytes_per_step": nbytes_local * world + 8 * world,
                     "steps": e2e_steps, "note": "every rank uploads its slab from pinned host memory, full Strang step, reads back ee and its slab"},
-            "gpu_launches": int(launches), "exchanges_per_step": nex / args.steps,
-            "all_to_all_ms": ms_a2a, "all_to_all_GBps_per_gpu": nbytes_local * (world - 1) / world / (ms_a2a * 1e-3) / 1e9,
+            "gpu_launches": int(launches), "exchanges_per_step": nex / args.steps, "exchange": sh.exchange,
+            "all_to_all_ms": ms_a2a,
+            "all_to_all_GBps_per_gpu": (nbytes_local * (world - 1) / world / (ms_a2a * 1e-3) / 1e9) if ms_a2a else None,
+            "exchange_payload_bytes_per_gpu": nbytes_local * (world - 1) // world,
             "roofline": {"bound": "hbm", "kernel": "whole step (6 sweeps + 2 rho passes per rank)", "achieved": value * 1e9 * (112.0 / 6.0) / world / 1e9,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": value * (112.0 / 6.0) / world / peak, "traffic": None},
             "last_ee": ee,

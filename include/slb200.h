@@ -140,6 +140,19 @@ int slb_sweep_ex(slb_grid* g, int dim, const slb_interp* it, const double* alpha
                  const int64_t* alpha_strides, double alpha_scale, int alpha_on_device, int flags,
                  int reshard_mode, int bdim, int nblocks);
 
+/* Fused sweep + all-to-all over NVLink peer memory: like SLB_RESHARD_OUT_BLOCKED along the swept
+ * dim, but k-block q of the output is stored to block_bases[q] -- a pointer into the buffer of the
+ * rank that owns block q after the exchange (this rank's own HBM, or a peer's mapped with
+ * slb_ipc_open_handle) -- instead of this grid's back buffer.  The grid's front/back roles do not
+ * change.  Callers synchronise the ranks (any stream-ordered barrier) before reading the result. */
+int slb_sweep_peer(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+                   const int64_t* alpha_strides, double alpha_scale, int alpha_on_device, int flags,
+                   int nblocks, double* const* block_bases);
+/* CUDA IPC plumbing for the above (handles are 64 bytes; memory must come from slb_malloc) */
+int slb_ipc_get_handle(slb_ctx* ctx, void* dev, void* handle64);
+int slb_ipc_open_handle(slb_ctx* ctx, const void* handle64, void** dev_out);
+int slb_ipc_close_handle(slb_ctx* ctx, void* dev);
+
 /* sol(interp, b) applied to every line along dim (src/interpolation.jl:40,
  * src/bsplinelu.jl:275-284, src/bsplinefft.jl:49-58); in place on the grid (front buffer
  * after the call).  Exposed for tests. */

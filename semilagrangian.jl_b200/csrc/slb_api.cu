@@ -511,13 +511,14 @@ static int launch_stencil(slb_grid* g, int dim, const slb_interp* it, const doub
     if (omp)
         om = *omp;
     else {
+        memset(&om, 0, sizeof(om));
         om.kc = v.n;
         om.kblk = 0;
         om.bstride = (long long)v.n * v.inner;
     }
     int P1 = it->order + 1;
-    if (g->linesum && (dim == 0 || !it->fast || omp))
-        return fail(SLB_E_UNSUPPORTED, "line sums are produced by fast-path sweeps along dim > 0 in the plain layout only");
+    if (g->linesum && (dim == 0 || !it->fast))
+        return fail(SLB_E_UNSUPPORTED, "line sums are produced by fast-path sweeps along dim > 0 only");
     InMap im;
     memset(&im, 0, sizeof(im));
     if (imp) {
@@ -654,6 +655,7 @@ extern "C" int slb_sweep_ex(slb_grid* g, int dim, const slb_interp* it, const do
     if (reshard_mode == SLB_RESHARD_OUT_BLOCKED) {
         if (bdim != dim || dim == 0) return fail(SLB_E_UNSUPPORTED, "SLB_RESHARD_OUT_BLOCKED: the blocked dim must be the swept dim, and not dim 0");
         OutMap om;
+        memset(&om, 0, sizeof(om));
         om.kc = (int)(g->ext[dim] / nblocks);
         om.kblk = g->numel / nblocks;
         om.bstride = (long long)om.kc * v.inner;
@@ -671,6 +673,63 @@ extern "C" int slb_sweep_ex(slb_grid* g, int dim, const slb_interp* it, const do
         return sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, nullptr, &im);
     }
     return fail(SLB_E_ARG, "slb_sweep_ex: unknown reshard mode %d", reshard_mode);
+}
+
+extern "C" int slb_sweep_peer(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
+                              const int64_t* astr, double scale, int on_device, int flags, int nblocks,
+                              double* const* block_bases)
+{
+    if (!g || !block_bases) return fail(SLB_E_ARG, "slb_sweep_peer: NULL argument");
+    if (dim < 1 || dim >= g->nd) return fail(SLB_E_ARG, "slb_sweep_peer: the swept (blocked) dim must be > 0");
+    if (nblocks < 1 || nblocks > SLB_MAX_PEERS) return fail(SLB_E_ARG, "slb_sweep_peer: nblocks=%d not in [1,%d]", nblocks, SLB_MAX_PEERS);
+    if (g->ext[dim] % nblocks != 0) return fail(SLB_E_ARG, "slb_sweep_peer: extent %lld not divisible by %d", (long long)g->ext[dim], nblocks);
+    View v = make_view(g, dim);
+    OutMap om;
+    memset(&om, 0, sizeof(om));
+    om.kc = (int)(g->ext[dim] / nblocks);
+    om.kblk = g->numel / nblocks;
+    om.bstride = (long long)om.kc * v.inner;
+    om.npeer = nblocks;
+    for (int q = 0; q < nblocks; ++q) {
+        if (!block_bases[q]) return fail(SLB_E_ARG, "slb_sweep_peer: block_bases[%d] is NULL", q);
+        om.blk[q] = block_bases[q];
+    }
+    // the output does not land in this grid's back buffer: do not swap (sweep_impl swaps; undo)
+    int rc = sweep_impl(g, dim, it, alpha_tab, alpha_len, astr, scale, on_device, flags, &om);
+    if (rc) return rc;
+    return slb_grid_swap(g);
+}
+
+// ---- CUDA IPC: map another process's device buffer (one process per GPU) --------
+extern "C" int slb_ipc_get_handle(slb_ctx* c, void* dev, void* handle64)
+{
+    if (!c || !dev || !handle64) return fail(SLB_E_ARG, "slb_ipc_get_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, dev));
+    memcpy(handle64, &h, 64);
+    return SLB_OK;
+}
+
+extern "C" int slb_ipc_open_handle(slb_ctx* c, const void* handle64, void** dev_out)
+{
+    if (!c || !handle64 || !dev_out) return fail(SLB_E_ARG, "slb_ipc_open_handle: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SLB_OK;
+}
+
+extern "C" int slb_ipc_close_handle(slb_ctx* c, void* dev)
+{
+    if (!c) return fail(SLB_E_ARG, "ctx is NULL");
+    if (dev) {
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaIpcCloseMemHandle(dev));
+    }
+    return SLB_OK;
 }
 
 extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)

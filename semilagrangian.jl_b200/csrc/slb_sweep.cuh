@@ -49,10 +49,17 @@ struct AlphaMap {
 
 // Generalised addressing of the swept index k on the OUTPUT side (multi-GPU re-shard fused
 // into the sweep epilogue): k -> (k % kc) * inner + (k / kc) * kblk.  kc == n: plain layout.
+#define SLB_MAX_PEERS 16
 struct OutMap {
     int kc;
     long long kblk;
     long long bstride;  // offset between consecutive outer indices b (plain: n * inner)
+    // Fused sweep + all-to-all: when npeer > 0, k-block q of the output is not written to
+    // out + q*kblk but to blk[q], a pointer into the destination rank's buffer (its own HBM or a
+    // peer's, mapped through CUDA IPC): the sweep's coalesced row stores travel over NVLink
+    // directly and no separate collective or pack pass exists.
+    int npeer;
+    double* blk[SLB_MAX_PEERS];
 };
 
 // Generalised addressing of the INPUT lines of a contiguous-dim sweep (multi-GPU re-shard fused
@@ -154,7 +161,8 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
     }
 
     const double* pin = in + (b * n) * inner + a;
-    double* pout = out + b * om.bstride + a;
+    const long long ooff = b * om.bstride + a;
+    double* pout = (om.npeer > 0 ? om.blk[0] : out) + ooff;
     int kk = s0;
     const double* pl = pin + (long long)kk * inner;
 
@@ -181,6 +189,7 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
     double lsum = 0.0;  // sum of this line's outputs: feeds the charge density without another pass over f
     double* po = pout;
     int ko = 0;  // position inside the current output k-block
+    int kb = 0;  // current output k-block
 
 #define SLB_STORE(val)                                  \
     {                                                   \
@@ -189,7 +198,11 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
         if (!plain) {                                   \
             if (++ko == om.kc) {                        \
                 ko = 0;                                 \
-                po += om.kblk - (long long)om.kc * inner; \
+                ++kb;                                   \
+                if (om.npeer > 0)                       \
+                    po = om.blk[kb < om.npeer ? kb : 0] + ooff; \
+                else                                    \
+                    po += om.kblk - (long long)om.kc * inner; \
             }                                           \
         }                                               \
     }

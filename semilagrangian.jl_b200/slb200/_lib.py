@@ -44,6 +44,10 @@ SIGNATURES = [
     ("slb_interp_destroy", None, [C.c_void_p]),
     ("slb_sweep", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int]),
     ("slb_sweep_ex", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("slb_sweep_peer", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int, C.c_int, c_void_pp]),
+    ("slb_ipc_get_handle", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("slb_ipc_open_handle", C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
+    ("slb_ipc_close_handle", C.c_int, [C.c_void_p, C.c_void_p]),
     ("slb_presolve", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("slb_charge_density", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     ("slb_charge_density_raw", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),

@@ -126,9 +126,15 @@ class ShardedAdvectionData:
     (4 states of examples/vlasov-poisson-2d2v.jl: v1, v2, x1, x2 with ndims = 1).
 
     `data_local_B`: this rank's layout-B slab, shape [n1, n2/P, n3, n4] (numpy, Fortran order).
+
+    exchange = "p2p"  : the sweep that precedes a layout change stores its output straight into
+                        the destination ranks' buffers over NVLink (slb_sweep_peer, buffers
+                        mapped with CUDA IPC); the only collective left is a tiny barrier.
+    exchange = "nccl" : the sweep writes a block-major local array and an NCCL all-to-all
+                        (torch.distributed.all_to_all_single) moves the blocks.
     """
 
-    def __init__(self, adv, data_local_B, rank=None, world=None, group=None, device=None):
+    def __init__(self, adv, data_local_B, rank=None, world=None, group=None, device=None, exchange="p2p"):
         import torch
         import torch.distributed as dist
 
@@ -140,6 +146,9 @@ class ShardedAdvectionData:
         for st in adv.states:
             if st.ndims != 1 or not st.isconstdec:
                 raise NotImplementedError("const-shift 1-D states only")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange if self.P > 1 else "nccl"
         self.adv = adv
         self.gshape = adv.sizeall
         n1, n2, n3, n4 = self.gshape
@@ -151,17 +160,47 @@ class ShardedAdvectionData:
         self.stream = torch.cuda.Stream(self.device)
         self.ctx = _lib.Context(self.device.index, stream=self.stream.cuda_stream)
         self.nloc = n1 * n2 * n3 * n4 // self.P
-        self.bufs = [torch.empty(self.nloc, dtype=torch.float64, device=self.device) for _ in range(2)]
+        L = _lib.lib()
+        if self.exchange == "p2p":
+            # three buffers: a peer never stores into a buffer its owner may still be reading
+            self.nbuf = 3
+            self._raw = [self.ctx.malloc(self.nloc * 8) for _ in range(self.nbuf)]
+            self.ptr = [p.value for p in self._raw]
+            self.bufs = None
+            handles = []
+            for p in self._raw:
+                hb = C.create_string_buffer(64)
+                _lib.check(L.slb_ipc_get_handle(self.ctx.h, p, hb))
+                handles.append(hb.raw)
+            allh = [None] * self.P
+            dist.all_gather_object(allh, handles, group=group)
+            self.peer = []  # peer[r][i]: address of rank r's buffer i in this process
+            self._opened = []
+            for r in range(self.P):
+                if r == self.rank:
+                    self.peer.append(list(self.ptr))
+                    continue
+                row = []
+                for hb in allh[r]:
+                    q = C.c_void_p()
+                    _lib.check(L.slb_ipc_open_handle(self.ctx.h, C.create_string_buffer(hb, 64), C.byref(q)))
+                    row.append(q.value)
+                    self._opened.append(q)
+                self.peer.append(row)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        else:
+            self.nbuf = 2
+            self.bufs = [torch.empty(self.nloc, dtype=torch.float64, device=self.device) for _ in range(2)]
+            self.ptr = [b.data_ptr() for b in self.bufs]
         self.cur = 0  # index of the buffer holding f
         self.layout = LAYOUT_B
-        self.blocked = False  # True while cur holds a block-major (just exchanged) layout-A array
+        self.since_barrier = 99  # sweeps since the last cross-rank barrier
         shp = local_shape(self.gshape, LAYOUT_B, self.P)
         if tuple(data_local_B.shape) != shp:
             raise ValueError(f"local slab shape {tuple(data_local_B.shape)} must be {shp}")
-        host = torch.from_numpy(np.ascontiguousarray(np.asfortranarray(data_local_B).reshape(-1, order="F")))
-        with torch.cuda.stream(self.stream):
-            self.bufs[0].copy_(host)
-        self.stream.synchronize()
+        host = np.ascontiguousarray(np.asfortranarray(data_local_B).reshape(-1, order="F"))
+        _lib.check(L.slb_memcpy_h2d(self.ctx.h, C.c_void_p(self.ptr[0]), host.ctypes.data_as(C.c_void_p), host.nbytes))
+        self.ctx.sync()
         self._grids = {}
         self.state_gen = 1
         self.time_cur = 0.0
@@ -173,30 +212,42 @@ class ShardedAdvectionData:
         self.fctv = [np.ascontiguousarray(a.reshape(-1, order="F")) for a in _get_fctv_k_imag(adv)]
         arr = (_lib.c_double_p * 2)(*[_lib.dptr(a) for a in self.fctv])
         h = C.c_void_p()
-        _lib.check(_lib.lib().slb_poisson_create(self.ctx.h, 2, _lib.i64((n1, n2)), arr, C.byref(h)))
+        _lib.check(L.slb_poisson_create(self.ctx.h, 2, _lib.i64((n1, n2)), arr, C.byref(h)))
         self.plan = h
         self.rho_local = torch.empty(n1 * n2 // self.P, dtype=torch.float64, device=self.device)
         self.rho = torch.empty(n1 * n2, dtype=torch.float64, device=self.device)
         self.E = [torch.empty(n1 * n2, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.points = [torch.from_numpy(np.ascontiguousarray(m.points)).to(self.device) for m in adv.t_mesh]
+        self.linesum = torch.empty(self.nloc // min(n3, n4), dtype=torch.float64, device=self.device)
+        self.linesum_dim = None
+        self.use_linesum = True
         self.has_field = False
         self.n_exchanges = 0
+        self.n_barriers = 0
         torch.cuda.synchronize(self.device)  # buffers above were filled on torch's default stream
+        if self.P > 1:
+            dist.barrier(group=group)
 
-    # ---- grid handles over the two buffers ---------------------------------------------
-    def _grid(self, layout):
-        key = (layout, self.cur)
+    # ---- grid handles over the buffers ---------------------------------------------------
+    def _grid(self, layout, out=None):
+        out = (self.cur + 1) % self.nbuf if out is None else out
+        key = (layout, self.cur, out)
         g = self._grids.get(key)
         if g is None:
             shp = local_shape(self.gshape, layout, self.P)
             g = C.c_void_p()
             _lib.check(_lib.lib().slb_grid_create_external(
-                self.ctx.h, 4, _lib.i64(shp), C.c_void_p(self.bufs[self.cur].data_ptr()),
-                C.c_void_p(self.bufs[1 - self.cur].data_ptr()), C.byref(g)))
+                self.ctx.h, 4, _lib.i64(shp), C.c_void_p(self.ptr[self.cur]), C.c_void_p(self.ptr[out]), C.byref(g)))
             self._grids[key] = g
         return g
 
-    def _exchange(self):
+    def _barrier(self):
+        """stream-ordered cross-rank barrier (called under the driver's stream)"""
+        self.dist.all_reduce(self._flag, group=self.group)
+        self.since_barrier = 0
+        self.n_barriers += 1
+
+    def _exchange_nccl(self):
         # called under `with torch.cuda.stream(self.stream)`
         self.dist.all_to_all_single(self.bufs[1 - self.cur], self.bufs[self.cur], group=self.group)
         self.cur = 1 - self.cur
@@ -223,12 +274,19 @@ class ShardedAdvectionData:
             self._compute_field()
 
     def _compute_field(self):
-        if self.layout != LAYOUT_B or self.blocked:
+        if self.layout != LAYOUT_B:
             raise RuntimeError("the charge density is a local reduction in layout B only")
         adv = self.adv
+        n1, n2, n3, n4 = self.gshape
         dv = adv.t_mesh[2].step * adv.t_mesh[3].step
         L = _lib.lib()
-        _lib.check(L.slb_charge_density_raw(self._grid(LAYOUT_B), 2, dv, C.c_void_p(self.rho_local.data_ptr())))
+        rl = C.c_void_p(self.rho_local.data_ptr())
+        if self.linesum_dim is not None:
+            # the last velocity sweep left sum over that dim per line: reduce the remaining one
+            nv_rest = n3 * n4 // self.gshape[self.linesum_dim]
+            _lib.check(L.slb_charge_density_from(self.ctx.h, C.c_void_p(self.linesum.data_ptr()), n1 * n2 // self.P, nv_rest, dv, rl, 0))
+        else:
+            _lib.check(L.slb_charge_density_raw(self._grid(LAYOUT_B), 2, dv, rl))
         if self.P > 1:
             self.dist.all_gather_into_tensor(self.rho, self.rho_local, group=self.group)
         else:
@@ -254,6 +312,10 @@ class ShardedAdvectionData:
         with self.torch.cuda.stream(self.stream):
             return self._advection()
 
+    def _next_dim(self):
+        adv = self.adv
+        return adv.getst(self.state_gen + 1 if self.state_gen < adv.nbstates else 1).perm[0] - 1
+
     def _advection(self):
         adv, st = self.adv, self.getst()
         d = st.perm[0] - 1
@@ -263,13 +325,14 @@ class ShardedAdvectionData:
         need = LAYOUT_A if d < 2 else LAYOUT_B
         interp = adv.t_interp[d]
         L = _lib.lib()
+        multi = self.P > 1
         mode, bdim = _lib.SLB_RESHARD_NONE, 0
         if need != self.layout:
+            # only B -> A is ever pending here: A -> B is completed by the x2 sweep itself
             if not (need == LAYOUT_A and d == 0):
                 raise NotImplementedError("unsupported state order for the fused re-shard (needs x1 first after v-sweeps)")
-            if self.P > 1:
-                self._exchange()            # B -> A: received array is block-major along x2
-                mode, bdim = _lib.SLB_RESHARD_IN_BLOCKED, 1
+            if multi:
+                mode, bdim = _lib.SLB_RESHARD_IN_BLOCKED, 1   # cur holds the blocks received from every rank
             self.layout = LAYOUT_A
         strides = [0, 0, 0, 0]
         if d >= 2:  # velocity sweep: alpha = (dt/dv_d) * E_{d-2}[x1, x2l + r*c2]   (src/poisson.jl:178-189)
@@ -288,30 +351,71 @@ class ShardedAdvectionData:
             tab = self.points[src].data_ptr() + 8 * off
             tlen = c4 if src == 3 else self.gshape[src]
             scale = -dt / adv.t_mesh[d].step
-        # the last space sweep before velocity sweeps writes its output block-major along x2
-        nxt = adv.getst(self.state_gen + 1 if self.state_gen < adv.nbstates else 1).perm[0] - 1
-        reshard_after = (self.layout == LAYOUT_A and nxt >= 2)
-        if reshard_after and self.P > 1:
-            if d != 1 or mode != _lib.SLB_RESHARD_NONE:
-                raise NotImplementedError("unsupported state order for the fused re-shard (needs x2 last before v-sweeps)")
-            mode, bdim = _lib.SLB_RESHARD_OUT_BLOCKED, 1
-        g = self._grid(self.layout)
+        nxt = self._next_dim()
+        # layout change AFTER this sweep: v2 followed by x1 (B -> A), x2 followed by a v-sweep (A -> B)
+        to_A = self.layout == LAYOUT_B and nxt < 2
+        to_B = self.layout == LAYOUT_A and nxt >= 2
+        if (to_A and d != 3) or (to_B and d != 1):
+            raise NotImplementedError("unsupported state order for the fused re-shard (v2 must precede x-sweeps, x2 must precede v-sweeps)")
+        reshard = multi and (to_A or to_B)
+        # line sums of a velocity sweep feed the next charge density (next state = v1)
+        self.linesum_dim = None
+        want_ls = self.use_linesum and d >= 2 and nxt == 2
+        out = (self.cur + 1) % self.nbuf
+        g = self._grid(self.layout, out)
         h = interp.handle(self.ctx, self.gshape[d])
-        _lib.check(L.slb_sweep_ex(g, d, h, C.c_void_p(tab), tlen, _lib.i64(strides), float(scale), 1, int(self.flags),
-                                  mode, bdim, self.P))
-        _lib.check(L.slb_grid_swap(g))  # keep the handle's orientation; the driver tracks `cur`
-        self.cur = 1 - self.cur
-        if reshard_after:
-            if self.P > 1:
-                self._exchange()            # A -> B: blocks concatenate along v2 into the layout-B slab
+        if want_ls:
+            _lib.check(L.slb_grid_set_linesum(g, C.c_void_p(self.linesum.data_ptr())))
+        try:
+            if reshard and self.exchange == "p2p":
+                if mode != _lib.SLB_RESHARD_NONE:
+                    raise NotImplementedError("a sweep cannot both read and write re-sharded data")
+                if self.since_barrier > 1:
+                    self._barrier()  # every rank is done with the buffer we are about to store into
+                blk = self.nloc // self.P
+                bases = (C.c_void_p * self.P)(*[self.peer[q][out] + 8 * self.rank * blk for q in range(self.P)])
+                _lib.check(L.slb_sweep_peer(g, d, h, C.c_void_p(tab), tlen, _lib.i64(strides), float(scale), 1, int(self.flags),
+                                            self.P, bases))
+                self._barrier()      # all blocks have landed everywhere
+                self.n_exchanges += 1
+                self.cur = out
+            else:
+                if reshard and to_B:
+                    if mode != _lib.SLB_RESHARD_NONE:
+                        raise NotImplementedError("a sweep cannot both read and write re-sharded data")
+                    mode, bdim = _lib.SLB_RESHARD_OUT_BLOCKED, 1
+                _lib.check(L.slb_sweep_ex(g, d, h, C.c_void_p(tab), tlen, _lib.i64(strides), float(scale), 1, int(self.flags),
+                                          mode, bdim, self.P))
+                _lib.check(L.slb_grid_swap(g))  # keep the handle's orientation; the driver tracks `cur`
+                self.cur = out
+                self.since_barrier += 1
+                if reshard:
+                    self._exchange_nccl()       # B -> A: contiguous slabs; A -> B: block-major output
+        finally:
+            if want_ls:
+                _lib.check(L.slb_grid_set_linesum(g, None))
+        if want_ls:
+            self.linesum_dim = d
+        if to_A:
+            pass  # layout flips when the x1 sweep consumes the blocks (keeps compute_field honest)
+        if to_B:
             self.layout = LAYOUT_B
         return self.nextstate()
 
     # ---- data access ----------------------------------------------------------------------
+    def upload_local(self, host_flat):
+        """copy this rank's slab (current layout, flat Fortran order, e.g. pinned memory) to the device"""
+        _lib.check(_lib.lib().slb_memcpy_h2d(self.ctx.h, C.c_void_p(self.ptr[self.cur]), host_flat.ctypes.data_as(C.c_void_p), self.nloc * 8))
+        self.linesum_dim = None
+
+    def download_local(self, host_flat):
+        _lib.check(_lib.lib().slb_memcpy_d2h(self.ctx.h, host_flat.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr[self.cur]), self.nloc * 8))
+        self.ctx.sync()
+
     def getdata_local(self):
         """this rank's slab in the current layout (numpy, Fortran order); valid between steps"""
-        self.stream.synchronize()
-        flat = self.bufs[self.cur].cpu().numpy()
+        flat = np.empty(self.nloc, dtype=np.float64)
+        self.download_local(flat)
         return flat.reshape(local_shape(self.gshape, self.layout, self.P), order="F")
 
     def gather_global(self):
@@ -330,9 +434,22 @@ class ShardedAdvectionData:
         return np.asfortranarray(np.concatenate(parts, axis=d))
 
     def close(self):
+        L = _lib.lib()
+        self.ctx.sync()
         for g in self._grids.values():
-            _lib.lib().slb_grid_destroy(g)
+            L.slb_grid_destroy(g)
         self._grids = {}
         if self.plan:
-            _lib.lib().slb_poisson_destroy(self.plan)
+            L.slb_poisson_destroy(self.plan)
             self.plan = None
+        if self.exchange == "p2p" and self._raw:
+            if self.P > 1:
+                self.dist.barrier(group=self.group)
+            for q in self._opened:
+                L.slb_ipc_close_handle(self.ctx.h, q)
+            self._opened = []
+            if self.P > 1:
+                self.dist.barrier(group=self.group)
+            for p in self._raw:
+                self.ctx.free(p)
+            self._raw = []
