@@ -1,0 +1,41 @@
+#!/bin/bash
+# One GPU-box session: parity tests, bench (both arms), ncu launch list and full captures of the
+# sweep kernels.  Run as:  gpurun --timeout 1500 -- 'bash tools/gpu_eval.sh [tag] [what...]'
+# Outputs under gpurun_out/<tag>/ ; summaries are copied into profiles/ by tools/summarize_ncu.py.
+TAG=${1:-eval}
+shift
+WHAT=${*:-tests bench ref launches full}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,memory.total --format=csv > "$OUT/smi.csv" 2>&1
+for w in $WHAT; do
+  case $w in
+    tests)
+      timeout 1200 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
+      echo "pytest rc=$?"; tail -3 "$OUT/pytest_gpu.log" ;;
+    bench)
+      timeout 600 python bench.py --steps 10 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"
+      echo "bench rc=$?"; cat "$OUT/bench.json" ;;
+    ref)
+      timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
+      echo "ref rc=$?"; cat "$OUT/bench_ref.json" ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+        --log-file "$OUT/launches.csv" python tools/prof_step.py --steps 2 > "$OUT/launches.log" 2>&1
+      echo "launches rc=$?" ;;
+    full)
+      # skip the warm-up step's launches; 1 capture each of the strided and contiguous sweep kernels
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 6 \
+        -f -o "$OUT/prof_sweep" python tools/prof_step.py --steps 1 > "$OUT/full.log" 2>&1
+      echo "full rc=$?" ;;
+    bspline)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sweep|k_bspline' -s 12 -c 12 \
+        -f -o "$OUT/prof_bspline" python tools/prof_step.py --steps 1 --interp bspline_fft --order 11 > "$OUT/full_bspline.log" 2>&1
+      echo "bspline rc=$?"
+      timeout 600 python bench.py --steps 5 --warmup 3 --interp bspline_fft --order 11 --no-cpu > "$OUT/bench_bspline.json" 2> "$OUT/bench_bspline.err"
+      cat "$OUT/bench_bspline.json" ;;
+    *)
+      echo "unknown item $w" ;;
+  esac
+done
+ls -la "$OUT"
