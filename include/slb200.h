@@ -125,6 +125,23 @@ void slb_interp_destroy(slb_interp* it);
 int slb_sweep(slb_grid* g, int dim, const slb_interp* it, const double* alpha_tab, int64_t alpha_len,
               const int64_t* alpha_strides, double alpha_scale, int alpha_on_device, int flags);
 
+/* ---- two consecutive sweeps in one pass over HBM ---------------------------------------------- */
+/* Equivalent to slb_sweep(dimA, ...) followed by slb_sweep(dimB, ...) -- two advection! calls of a
+ * split step (src/advection.jl:594-657; e.g. the v1 v2 and x1 x2 pairs of
+ * examples/vlasov-poisson-2d2v.jl:126-131) -- with BIT-IDENTICAL results, but f is read from and
+ * written to HBM once: sweep A is a cross-thread stencil on rows staged in shared memory, sweep B
+ * runs along the march direction in registers (csrc/slb_pair.cuh).  Both alpha tables follow
+ * slb_sweep's convention and are evaluated before either sweep, like bufcur in
+ * src/poisson.jl:178-203.  A line-sum buffer set with slb_grid_set_linesum receives the sums of
+ * sweep B's outputs.
+ * Returns SLB_E_UNSUPPORTED for combinations that are not pair-fused (dimB == 0, alpha_A depending
+ * on dimB, B-spline pre-solves, different orders, more than 4 dims): callers then issue the two
+ * sweeps separately. */
+int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA_tab, int64_t alphaA_len,
+                   const int64_t* alphaA_strides, double alphaA_scale, int dimB, const slb_interp* itB,
+                   const double* alphaB_tab, int64_t alphaB_len, const int64_t* alphaB_strides, double alphaB_scale,
+                   int alpha_on_device, int flags);
+
 /* ---- sweeps fused with the multi-GPU re-shard -------------------------------- */
 /* A 2D2V grid sharded over P ranks alternates between two slab layouts; the all-to-all between
  * them (replacing mpibroadcast, src/mpiinterface.jl:17-38) moves contiguous blocks only when the

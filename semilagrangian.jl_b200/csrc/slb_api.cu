@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -13,6 +14,7 @@
 
 #include "../../include/slb200.h"
 #include "slb_sweep.cuh"
+#include "slb_pair.cuh"
 #include "slb_bspline.cuh"
 #include "slb_field.cuh"
 
@@ -730,6 +732,158 @@ extern "C" int slb_ipc_close_handle(slb_ctx* c, void* dev)
         CUDA_TRY(cudaIpcCloseMemHandle(dev));
     }
     return SLB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// pair-fused sweeps (slb_pair.cuh): two advection! stages in one pass over HBM
+// ------------------------------------------------------------------------------------------
+static int check_alpha_table(const slb_grid* g, int dim, const double* tab, int64_t len, const int64_t* astr)
+{
+    if (!tab || len < 1 || !astr) return fail(SLB_E_ARG, "slb_sweep_pair: alpha table missing");
+    int64_t maxoff = 0;
+    for (int d = 0; d < g->nd; ++d) {
+        if (d == dim) continue;
+        if (astr[d] < 0) return fail(SLB_E_ARG, "slb_sweep_pair: negative alpha stride");
+        maxoff += astr[d] * (g->ext[d] - 1);
+    }
+    if (maxoff >= len) return fail(SLB_E_ARG, "slb_sweep_pair: alpha table too short (%lld needed, %lld given)", (long long)maxoff + 1, (long long)len);
+    return SLB_OK;
+}
+
+static long long env_ll(const char* name, long long dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoll(v);
+}
+
+extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
+                              const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
+                              int64_t alenB, const int64_t* astrB, double scaleB, int on_device, int flags)
+{
+    if (!g || !itA || !itB) return fail(SLB_E_ARG, "slb_sweep_pair: NULL argument");
+    slb_ctx* c = g->ctx;
+    const int nd = g->nd;
+    if (dimA < 0 || dimA >= nd || dimB < 0 || dimB >= nd || dimA == dimB) return fail(SLB_E_ARG, "slb_sweep_pair: need two distinct dims in range");
+    int rc = check_alpha_table(g, dimA, alphaA, alenA, astrA);
+    if (rc) return rc;
+    rc = check_alpha_table(g, dimB, alphaB, alenB, astrB);
+    if (rc) return rc;
+    if (nd > 4) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: grids with more than 4 dims are not pair-fused");
+    if (dimB == 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: the second sweep must not run along dim 0");
+    auto plain = [](const slb_interp* it) { return it->fast && it->kind != SLB_BSPLINE_LU && it->kind != SLB_BSPLINE_FFT; };
+    if (!plain(itA) || !plain(itB) || itA->order != itB->order)
+        return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: both stages need the same order (<= %d) and an identity pre-solve", SLB_P1MAX - 1);
+    if (astrA[dimB] != 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: the first sweep's shift must not depend on the second sweep's dim");
+    const int P1 = itA->order + 1;
+    const int64_t ncross = g->ext[dimA], nmarch = g->ext[dimB];
+    if (ncross < P1 || ncross >= ((int64_t)1 << 30) || nmarch >= ((int64_t)1 << 30))
+        return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: line length out of range for the fused kernel");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int64_t gs[SLB_MAX_DIMS], lsstr[SLB_MAX_DIMS];
+    int64_t run = 1, lsrun = 1;
+    for (int q = 0; q < nd; ++q) {
+        gs[q] = run;
+        run *= g->ext[q];
+        lsstr[q] = lsrun;  // index of the plain kernel's line id over the dims other than dimB
+        if (q != dimB) lsrun *= g->ext[q];
+    }
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.in = g->front;
+    fa.out = g->back;
+    fa.ncross = (int)ncross;
+    fa.nmarch = (int)nmarch;
+    fa.sc = gs[dimA];
+    fa.sm = gs[dimB];
+    fa.elo = fa.ehi = 1;
+    int npass = 0;
+    for (int q = 0; q < nd; ++q) {
+        if (q == dimA || q == dimB) continue;
+        if (npass == 0) {
+            fa.elo = (unsigned)g->ext[q];
+            fa.slo = gs[q];
+            fa.aAlo = astrA[q];
+            fa.aBlo = astrB[q];
+            fa.lslo = lsstr[q];
+        } else {
+            fa.ehi = (unsigned)g->ext[q];
+            fa.shi = gs[q];
+            fa.aAhi = astrA[q];
+            fa.aBhi = astrB[q];
+            fa.lshi = lsstr[q];
+        }
+        ++npass;
+    }
+    fa.aBc = astrB[dimA];
+    fa.lsc = lsstr[dimA];
+    const int64_t np = (int64_t)fa.elo * fa.ehi;
+    if (np >= ((int64_t)1 << 31)) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: grid too large");
+    const bool cc = (dimA == 0);
+    int gg, ta, full;
+    if (cc) {
+        if (ncross <= SLB_FUSED_MAXTHREADS) {
+            full = 1;
+            ta = (int)ncross;
+            int64_t want = env_ll("SLB_FUSED_CC_THREADS", 256) / ncross;
+            gg = (int)(want < 1 ? 1 : want);
+            if (gg > np) gg = (int)np;
+            while ((int64_t)gg * ta > SLB_FUSED_MAXTHREADS) --gg;
+        } else {
+            full = 0;
+            ta = 256;
+            gg = 1;
+        }
+    } else {
+        gg = 16;  // 128 B rows; smaller only when dim 0 is not a multiple
+        while (gg > 1 && (fa.elo % gg != 0 || !slb_fused_supported(P1, false, gg))) gg >>= 1;
+        int64_t want = env_ll("SLB_FUSED_THREADS", 512) / gg;
+        if (want > SLB_FUSED_MAXTHREADS / gg) want = SLB_FUSED_MAXTHREADS / gg;
+        if (want < 32) want = 32;
+        if (want >= ncross) {
+            full = 1;
+            ta = (int)ncross;
+        } else {
+            full = 0;
+            ta = (int)want;
+        }
+        if ((int64_t)gg * ta > SLB_FUSED_MAXTHREADS) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit a thread block");
+    }
+    if (!slb_fused_supported(P1, cc, gg)) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: order %d is not on the fused path", P1 - 1);
+    fa.g = gg;
+    fa.ta = ta;
+    fa.full = full;
+    fa.ntile_c = (int)((ncross + ta - 1) / ta);
+    fa.nrows_max = full ? (int)ncross + P1 - 1 : ta + P1 - 1 + SLB_FUSED_SPREAD_MAX;
+    if ((int64_t)fa.nrows_max * gg > 2 * (int64_t)gg * ta) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: lines too short for the fused kernel");
+    const double *tabA = alphaA, *tabB = alphaB;
+    if (!on_device) {
+        rc = ensure_scratch(c, (size_t)(alenA + alenB) * sizeof(double));
+        if (rc) return rc;
+        double* s = (double*)c->scratch;
+        CUDA_TRY(cudaMemcpyAsync(s, alphaA, (size_t)alenA * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(s + alenA, alphaB, (size_t)alenB * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        tabA = s;
+        tabB = s + alenA;
+    }
+    fa.tabA = tabA;
+    fa.scaleA = scaleA;
+    fa.tabB = tabB;
+    fa.scaleB = scaleB;
+    fa.ncA = itA->nc;
+    fa.ncB = itB->nc;
+    fa.linesum = g->linesum;
+    const int64_t nblk = (int64_t)fa.ntile_c * ((np + gg - 1) / gg);
+    if (nblk >= 0x7fffffffLL) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: too many blocks");
+    const size_t smem = slb_fused_smem_bytes(fa.nrows_max, gg);
+    if (smem > 200 * 1024) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit shared memory");
+    const bool exact = (flags & SLB_SWEEP_EXACT) != 0;
+    int lrc = slb_fused_launch(fa, itA->tab, itB->tab, P1, exact, cc, (unsigned)nblk, (unsigned)(gg * ta), smem, c->stream);
+    if (lrc < 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: no fused kernel for order %d, tile width %d", P1 - 1, gg);
+    if (lrc != 0) return fail(SLB_E_CUDA, "slb_sweep_pair: launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+    c->launches++;
+    return slb_grid_swap(g);
 }
 
 extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)

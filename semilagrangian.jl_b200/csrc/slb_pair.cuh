@@ -1,0 +1,333 @@
+// slb_pair.cuh -- K7: two consecutive 1-D sweeps fused into ONE pass over HBM.
+//
+// A Strang step of a 2D2V grid runs its sweeps in pairs (v1 v2 | x1 x2 | v1 v2,
+// examples/vlasov-poisson-2d2v.jl:126-131); the reference executes each as a separate
+// advection! call (src/advection.jl:594-657), i.e. one full read + write of f per sweep.
+// Here a pair (A along the "cross" dim, then B along the "march" dim) is one kernel that reads f
+// once and writes it once -- 16 B of HBM traffic per cell for TWO cell-updates:
+//
+//   * a CTA owns a tile of `ta` consecutive cross indices x `g` points of the remaining
+//     ("passive") dims and marches over the whole march dim, one input row per step;
+//   * sweep A is a cross-THREAD stencil: the step's input rows (tile + periodic halo) are staged
+//     in shared memory by cp.async (a ring of D stages, filled D-1 steps ahead, so the loads in
+//     flight cost no registers), and thread (p, a) forms T = sum_q w1[q] * raw[a + s0A(p) + q];
+//   * sweep B runs along the march direction in REGISTERS: every thread keeps a rotating window
+//     of its last order+1 values of T and emits one output per step,
+//         out[i] = sum_q w2[q] * T[(i + s0B + q) mod n],   i = (step - order - s0B) mod n.
+//
+// The intermediate T is rounded to Float64 exactly as when a separate sweep stores it, and both
+// stencils use the same operation order as k_sweep_strided / k_sweep_contig, so the result is
+// BIT-IDENTICAL to two slb_sweep calls.  Lane order follows the memory-contiguous index:
+// CC = true  (cross dim is dim 0, e.g. x1 x2): lanes run along the cross index;
+// CC = false (dim 0 is passive, e.g. v1 v2)  : lanes run along the passive index (g = 16: 128 B rows).
+// Shifts may differ between the passive points of a tile: the staged row range is the union over
+// the tile (up to SLB_FUSED_SPREAD_MAX extra rows); beyond that the CTA reads its stencil inputs
+// straight from global memory (correct, slower).  alpha_A must not depend on the march index
+// (it would change w1 every step); alpha_B may depend on everything but the march index.
+//
+// (A first version staged T of whole chunks through a ring buffer kept resident in the L2:
+// ncu showed the ring does stay in the L2 up to ~24 MB -- DRAM traffic halved -- but one thread
+// per line keeps >= 50 MB of intermediate in flight at full occupancy, so it never beat two
+// separate sweeps; see profiles/r1_pair_l2_experiment.txt.)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "slb_sweep.cuh"
+
+#define SLB_FUSED_SPREAD_MAX 16
+#define SLB_FUSED_STAGES 5       // ring of shared-memory stages
+#define SLB_FUSED_ROWS 2         // march rows per stage (= per block barrier)
+#define SLB_FUSED_MAXTHREADS 512
+
+struct FusedArgs {
+    const double* in;
+    double* out;
+    int ncross, nmarch;          // extents of the cross (sweep A) and march (sweep B) dims
+    long long sc, sm;            // their element strides
+    unsigned elo, ehi;           // extents of the (up to two) passive index groups
+    long long slo, shi;          // their element strides
+    int g, ta;                   // passive points / cross outputs per tile (blockDim = g * ta)
+    int ntile_c;                 // tiles along the cross dim
+    int full;                    // 1: a tile is the whole periodic cross line
+    int nrows_max;               // staged rows per march row (shared-memory pitch)
+    const double* tabA;          // alpha_A = scaleA * tabA[plo*aAlo + phi*aAhi]
+    double scaleA;
+    long long aAlo, aAhi;
+    const double* tabB;          // alpha_B = scaleB * tabB[plo*aBlo + phi*aBhi + a*aBc]
+    double scaleB;
+    long long aBlo, aBhi, aBc;
+    int ncA, ncB;                // polynomial coefficients per weight
+    double* linesum;             // optional: per (passive, cross) sum over the march dim of the outputs
+    long long lslo, lshi, lsc;
+};
+
+// host launcher (slb_pair.cu); returns cudaGetLastError() of the launch, or -1 when (P1, G) is not instantiated
+int slb_fused_launch(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, int P1, bool exact, bool cc,
+                     unsigned nblocks, unsigned nthreads, size_t smem_bytes, cudaStream_t stream);
+bool slb_fused_supported(int P1, bool cc, int g);
+size_t slb_fused_smem_bytes(int nrows_max, int g);
+
+#ifdef SLB_PAIR_IMPL
+__device__ __forceinline__ void fused_cp_async8(unsigned smem_dst, const double* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fused_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fused_cp_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// one term of slb_dot: same rounding as its EXACT / FMA branches
+template <bool EXACT>
+__device__ __forceinline__ double slb_mul(double x, double w)
+{
+    return EXACT ? __dmul_rn(x, w) : x * w;
+}
+template <bool EXACT>
+__device__ __forceinline__ double slb_acc(double acc, double x, double w)
+{
+    return EXACT ? __dadd_rn(acc, __dmul_rn(x, w)) : fma(x, w, acc);
+}
+
+template <int P1>
+__device__ __forceinline__ void fused_weights(const CoefTab& ct, int nc, double t, double (&w)[P1])
+{
+#pragma unroll
+    for (int j = 0; j < P1; ++j) w[j] = ct.c[j * SLB_NCMAX + nc - 1];
+    for (int k = nc - 2; k >= 0; --k) {
+#pragma unroll
+        for (int j = 0; j < P1; ++j) w[j] = fma(t, w[j], ct.c[j * SLB_NCMAX + k]);
+    }
+}
+
+// G > 0: passive points per tile fixed at compile time (CC = false); G == 0: run-time fa.g (CC = true)
+template <int P1, bool EXACT, bool CC, int G>
+__global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, 1)
+k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ CoefTab ctA, const __grid_constant__ CoefTab ctB)
+{
+    constexpr int D = SLB_FUSED_STAGES;
+    constexpr int R = SLB_FUSED_ROWS;
+    constexpr int HALF = (P1 - 1) / 2;
+    static_assert(P1 % R == 0, "rows per stage must divide the unroll length");
+    extern __shared__ __align__(16) double fsm[];
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int g = G > 0 ? G : fa.g;
+    const int ta = fa.ta, nc_ = fa.ncross, nm = fa.nmarch;
+    int p, a;
+    if (CC) {
+        a = tid % ta;
+        p = tid / ta;
+    } else {
+        p = tid % g;
+        a = tid / g;
+    }
+    const int tc = (int)(blockIdx.x % (unsigned)fa.ntile_c);
+    const long long tp = blockIdx.x / (unsigned)fa.ntile_c;
+    const int a0 = tc * ta;
+    const long long np = (long long)fa.elo * fa.ehi;
+    const long long P = tp * g + p;
+    const bool act = (P < np) && (a0 + a < nc_);
+    const long long Pc = P < np ? P : np - 1;  // idle threads mimic a valid point (they never store)
+    const int ac = (a0 + a < nc_) ? a0 + a : nc_ - 1;
+    const unsigned plo = (unsigned)(Pc % fa.elo), phi = (unsigned)(Pc / fa.elo);
+    const long long pbase = (long long)plo * fa.slo + (long long)phi * fa.shi;
+
+    // ---- sweep A (cross): shift and weights of this thread's passive point ---------------------
+    double w1[P1], w2[P1];
+    int s0A;
+    long long dA;
+    {
+        const double alpha = fa.scaleA * __ldg(fa.tabA + (long long)plo * fa.aAlo + (long long)phi * fa.aAhi);
+        double t;
+        slb_split(alpha, nc_, HALF, t, s0A);
+        const double fl = floor(alpha);
+        dA = fabs(fl) < 4.0e18 ? (long long)fl : (fl < 0 ? -4000000000000000000LL : 4000000000000000000LL);
+        fused_weights<P1>(ctA, fa.ncA, t, w1);
+    }
+    // ---- sweep B (march) -----------------------------------------------------------------------
+    int s0B;
+    {
+        const double alpha = fa.scaleB * __ldg(fa.tabB + (long long)plo * fa.aBlo + (long long)phi * fa.aBhi + (long long)ac * fa.aBc);
+        double t;
+        slb_split(alpha, nm, HALF, t, s0B);
+        fused_weights<P1>(ctB, fa.ncB, t, w2);
+    }
+
+    // ---- staged row range: union over the tile's passive points --------------------------------
+    const int row_elems = fa.nrows_max * g;       // one march row of the tile in shared memory
+    long long* dsh = reinterpret_cast<long long*>(fsm + (size_t)D * R * row_elems);
+    if (a == 0) dsh[p] = dA;
+    __syncthreads();
+    long long dmin = dsh[0], dmax = dsh[0];
+    for (int q = 1; q < g; ++q) {
+        long long v = dsh[q];
+        dmin = v < dmin ? v : dmin;
+        dmax = v > dmax ? v : dmax;
+    }
+    const bool full = fa.full != 0;
+    const bool direct = !full && (dmax - dmin > SLB_FUSED_SPREAD_MAX);  // uniform over the CTA
+    const int spread = full || direct ? 0 : (int)(dmax - dmin);
+    const int nrows = full ? nc_ + P1 - 1 : ta + P1 - 1 + spread;
+    int rowbase = 0;
+    if (!full) {
+        long long rb = ((long long)a0 + dmin - HALF) % nc_;
+        rowbase = (int)(rb < 0 ? rb + nc_ : rb);
+    }
+    int roff;  // first staged row of this thread's stencil
+    if (full) {
+        roff = ac + s0A;
+        roff -= roff >= nc_ ? nc_ : 0;
+    } else {
+        roff = a + (direct ? 0 : (int)(dA - dmin));
+    }
+    constexpr int QS = CC ? 1 : (G > 0 ? G : 1);  // shared-memory stride between consecutive staged rows
+    const int sread = CC ? p * fa.nrows_max + roff : roff * g + p;
+
+    const int nsteps = nm + P1 - 1;
+    const long long smel = fa.sm;
+    int iout = s0B == 0 ? 0 : nm - s0B;  // output index emitted at step P1-1
+    double* const po0 = fa.out + pbase + (long long)ac * fa.sc;
+    double* po = po0 + (long long)iout * smel;
+    double win[P1];
+#pragma unroll
+    for (int j = 0; j < P1; ++j) win[j] = 0.0;
+    double lsum = 0.0;
+
+    auto emit = [&](double acc) {
+        lsum += acc;
+        if (act) __stcs(po, acc);
+        po += smel;
+        if (++iout == nm) {
+            iout = 0;
+            po = po0;
+        }
+    };
+
+    if (!direct) {
+        // ---- load slots: the (up to two) staged elements this thread fetches for every march row ----
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(fsm);
+        const double* gsrc[2];
+        unsigned sdst[2];
+        bool lval[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int e = tid + s * NT;
+            lval[s] = e < nrows * g;
+            int pe, j;
+            if (CC) {
+                j = e % nrows;
+                pe = e / nrows;
+            } else {
+                pe = e % g;
+                j = e / g;
+            }
+            const long long Pe = tp * g + pe;
+            if (Pe >= np) lval[s] = false;
+            const long long Pq = Pe < np ? Pe : np - 1;
+            const int rc = (rowbase + j) % nc_;
+            gsrc[s] = fa.in + (long long)(Pq % fa.elo) * fa.slo + (long long)(Pq / fa.elo) * fa.shi + (long long)rc * fa.sc;
+            sdst[s] = sbase + 8u * (unsigned)(CC ? pe * fa.nrows_max + j : j * g + pe);
+        }
+        const unsigned row_b = 8u * (unsigned)row_elems, ring_b = row_b * R * D;
+        // block-uniform bookkeeping of the fetch pipeline (kept in the uniform datapath)
+        int b_iss = 0, k_iss = 0;   // march index / step number of the next row to fetch
+        long long boff = 0;         // b_iss * smel
+        unsigned off_iss = 0;       // byte offset of that row's slot in the ring
+        auto issue_stage = [&]() {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                if (k_iss < nsteps) {
+                    if (lval[0]) fused_cp_async8(sdst[0] + off_iss, gsrc[0] + boff);
+                    if (lval[1]) fused_cp_async8(sdst[1] + off_iss, gsrc[1] + boff);
+                    boff += smel;
+                    if (++b_iss == nm) {
+                        b_iss = 0;
+                        boff = 0;
+                    }
+                }
+                ++k_iss;
+                off_iss += row_b;
+                off_iss = off_iss == ring_b ? 0u : off_iss;
+            }
+            fused_cp_commit();
+        };
+#pragma unroll 1
+        for (int st = 0; st < D - 1; ++st) issue_stage();
+
+        const double* sp = fsm + sread;
+        const double* const sp_end = sp + (size_t)R * D * row_elems;
+
+        // One barrier interval = R = 2 march rows at window slots r, r+1.  The terms of the two
+        // march-direction dot products that only involve OLD window entries are summed before the
+        // barrier (same left-to-right order as slb_dot, hence bit-identical), so that after the
+        // barrier only the cross stencil and two or three dependent operations remain.
+#define SLB_FUSED_INTERVAL(r, EMIT0, EMIT1)                                                             \
+    {                                                                                                   \
+        double part0 = slb_mul<EXACT>(win[((r) + 1) % P1], w2[0]);                                      \
+        _Pragma("unroll") for (int j = 1; j < P1 - 1; ++j)                                              \
+            part0 = slb_acc<EXACT>(part0, win[((r) + 1 + j) % P1], w2[j]);                              \
+        double part1 = slb_mul<EXACT>(win[((r) + 2) % P1], w2[0]);                                      \
+        _Pragma("unroll") for (int j = 1; j < P1 - 2; ++j)                                              \
+            part1 = slb_acc<EXACT>(part1, win[((r) + 2 + j) % P1], w2[j]);                              \
+        fused_cp_wait<D - 2>();                                                                         \
+        __syncthreads();                                                                                \
+        issue_stage();                                                                                  \
+        double xa[R][P1];                                                                               \
+        _Pragma("unroll") for (int rr = 0; rr < R; ++rr)                                                \
+            _Pragma("unroll") for (int q = 0; q < P1; ++q) xa[rr][q] = sp[rr * row_elems + q * QS];     \
+        sp += R * row_elems;                                                                            \
+        sp = sp == sp_end ? sp - (size_t)R * D * row_elems : sp;                                        \
+        const double T0 = slb_dot<P1, EXACT>(xa[0], w1, 0);                                             \
+        const double T1 = slb_dot<P1, EXACT>(xa[1], w1, 0);                                             \
+        win[(r)] = T0;                                                                                  \
+        win[(r) + 1] = T1;                                                                              \
+        if (EMIT0) emit(slb_acc<EXACT>(part0, T0, w2[P1 - 1]));                                         \
+        if (EMIT1) emit(slb_acc<EXACT>(slb_acc<EXACT>(part1, T0, w2[P1 - 2]), T1, w2[P1 - 1]));         \
+    }
+        // first block: the window fills up (nsteps >= P1, so no bounds checks)
+#pragma unroll
+        for (int r = 0; r < P1; r += R) SLB_FUSED_INTERVAL(r, (r >= P1 - 1), (r + 1 >= P1 - 1))
+        int k0 = P1;
+        for (; k0 + P1 <= nsteps; k0 += P1) {
+#pragma unroll
+            for (int r = 0; r < P1; r += R) SLB_FUSED_INTERVAL(r, true, true)
+        }
+        // tail block
+#pragma unroll
+        for (int r = 0; r < P1; r += R) {
+            if (k0 + r < nsteps) SLB_FUSED_INTERVAL(r, true, (k0 + r + 1 < nsteps))
+        }
+#undef SLB_FUSED_INTERVAL
+    } else {
+        // shifts inside the tile are too far apart to stage a common row range: every thread reads
+        // its own stencil inputs from global memory (rare; correct, slower)
+        const double* pdir = fa.in + pbase;
+        int b = 0;
+        for (int k0 = 0; k0 < nsteps; k0 += P1) {
+#pragma unroll
+            for (int r = 0; r < P1; ++r) {
+                const int k = k0 + r;
+                if (k < nsteps) {
+                    const double* src = pdir + (long long)b * smel;
+                    b = b + 1 == nm ? 0 : b + 1;
+                    int rc = ac + s0A;
+                    rc -= rc >= nc_ ? nc_ : 0;
+                    double xa[P1];
+#pragma unroll
+                    for (int q = 0; q < P1; ++q) {
+                        xa[q] = __ldg(src + (long long)rc * fa.sc);
+                        rc = rc + 1 == nc_ ? 0 : rc + 1;
+                    }
+                    win[r] = slb_dot<P1, EXACT>(xa, w1, 0);
+                    if (k >= P1 - 1) emit(slb_dot<P1, EXACT>(win, w2, (r + 1) % P1));
+                }
+            }
+        }
+    }
+    if (fa.linesum && act)
+        fa.linesum[(long long)plo * fa.lslo + (long long)phi * fa.lshi + (long long)ac * fa.lsc] = lsum;
+}
+#endif  // SLB_PAIR_IMPL

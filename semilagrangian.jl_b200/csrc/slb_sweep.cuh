@@ -397,7 +397,7 @@ k_sweep_contig(const double* __restrict__ in, double* __restrict__ out, int n, l
 // ------------------------------------------------------------------------------------------
 // generic fallback: thread per line, any order <= 63
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_sweep_generic(const double* __restrict__ in, double* __restrict__ out, long long inner, int n, long long nlines,
                 AlphaMap am, const double* __restrict__ coef, int np, int nc, int exact)
 {

@@ -60,6 +60,17 @@ class DeviceGrid:
         h = interp.handle(self.ctx, self.shape[dim])
         _lib.check(_lib.lib().slb_sweep(self.h, dim, h, tab.ctypes.data_as(C.c_void_p), tab.size, _lib.i64(astride), float(scale), 0, flags))
 
+    def sweep_pair(self, dimA, interpA, tabA, astrA, dimB, interpB, tabB, astrB, flags=0):
+        """slb_sweep_pair with host alpha tables"""
+        _lib, C = self._lib, self.C
+        tabA = np.ascontiguousarray(tabA, dtype=np.float64)
+        tabB = np.ascontiguousarray(tabB, dtype=np.float64)
+        hA = interpA.handle(self.ctx, self.shape[dimA])
+        hB = interpB.handle(self.ctx, self.shape[dimB])
+        _lib.check(_lib.lib().slb_sweep_pair(
+            self.h, dimA, hA, tabA.ctypes.data_as(C.c_void_p), tabA.size, _lib.i64(astrA), 1.0,
+            dimB, hB, tabB.ctypes.data_as(C.c_void_p), tabB.size, _lib.i64(astrB), 1.0, 0, flags))
+
     def get(self):
         out = np.empty(self.shape, dtype=np.float64, order="F")
         self._lib.check(self._lib.lib().slb_grid_download(self.h, out.ctypes.data_as(self.C.c_void_p)))
