@@ -826,7 +826,7 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
         if (ncross <= SLB_FUSED_MAXTHREADS) {
             full = 1;
             ta = (int)ncross;
-            int64_t want = env_ll("SLB_FUSED_CC_THREADS", 256) / ncross;
+            int64_t want = env_ll("SLB_FUSED_CC_THREADS", 128) / ncross;
             gg = (int)(want < 1 ? 1 : want);
             if (gg > np) gg = (int)np;
             while ((int64_t)gg * ta > SLB_FUSED_MAXTHREADS) --gg;
@@ -838,9 +838,9 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     } else {
         gg = 16;  // 128 B rows; smaller only when dim 0 is not a multiple
         while (gg > 1 && (fa.elo % gg != 0 || !slb_fused_supported(P1, false, gg))) gg >>= 1;
-        int64_t want = env_ll("SLB_FUSED_THREADS", 512) / gg;
+        int64_t want = env_ll("SLB_FUSED_THREADS", 256) / gg;
         if (want > SLB_FUSED_MAXTHREADS / gg) want = SLB_FUSED_MAXTHREADS / gg;
-        if (want < 32) want = 32;
+        if (want < 16) want = 16;
         if (want >= ncross) {
             full = 1;
             ta = (int)ncross;
@@ -855,8 +855,22 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     fa.ta = ta;
     fa.full = full;
     fa.ntile_c = (int)((ncross + ta - 1) / ta);
-    fa.nrows_max = full ? (int)ncross + P1 - 1 : ta + P1 - 1 + SLB_FUSED_SPREAD_MAX;
-    if ((int64_t)fa.nrows_max * gg > 2 * (int64_t)gg * ta) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: lines too short for the fused kernel");
+    // every thread fetches at most two staged elements per march row: rows <= 2 * ta
+    fa.spread_max = full ? 0 : 2 * ta - (ta + P1 - 1);
+    if (fa.spread_max > SLB_FUSED_SPREAD_MAX) fa.spread_max = SLB_FUSED_SPREAD_MAX;
+    fa.nrows_max = full ? (int)ncross + P1 - 1 : ta + P1 - 1 + fa.spread_max;
+    if (fa.spread_max < 0 || fa.nrows_max > 2 * ta) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: lines too short for the fused kernel");
+    // 16-byte fetches (pairs of doubles along the contiguous index) when everything is 16-byte aligned
+    const bool aligned = ((uintptr_t)g->front % 16 == 0);
+    auto even = [](long long v) { return (v & 1) == 0; };
+    if (cc) {
+        fa.w16 = aligned && even(ncross) && even(fa.sm) && even(fa.slo) && even(fa.shi) && fa.sc == 1;
+        if (fa.w16) fa.nrows_max = (fa.nrows_max + 3) & ~1;  // even pitch + room for the alignment element
+    } else {
+        fa.w16 = gg > 1;
+        if (fa.w16 && !(aligned && fa.slo == 1 && even(fa.elo) && even(fa.sc) && even(fa.sm) && (fa.ehi == 1 || even(fa.shi))))
+            return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: buffers are not 16-byte aligned");
+    }
     const double *tabA = alphaA, *tabB = alphaB;
     if (!on_device) {
         rc = ensure_scratch(c, (size_t)(alenA + alenB) * sizeof(double));

@@ -22,11 +22,11 @@ size_t slb_fused_smem_bytes(int nrows_max, int g)
     return ((size_t)SLB_FUSED_STAGES * SLB_FUSED_ROWS * nrows_max * g + g) * sizeof(double);
 }
 
-template <int P1, bool EXACT, bool CC, int G>
+template <int P1, bool EXACT, bool CC, int G, bool W16>
 static int launch1(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, unsigned nblocks, unsigned nthreads,
                    size_t smem, cudaStream_t stream)
 {
-    auto kern = k_sweep_fused<P1, EXACT, CC, G>;
+    auto kern = k_sweep_fused<P1, EXACT, CC, G, W16>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -39,11 +39,13 @@ template <int P1, bool EXACT>
 static int launch2(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, bool cc, unsigned nblocks,
                    unsigned nthreads, size_t smem, cudaStream_t stream)
 {
-    if (cc) return launch1<P1, EXACT, true, 0>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
-    switch (fa.g) {
-    case 16: return launch1<P1, EXACT, false, 16>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
-    case 4: return launch1<P1, EXACT, false, 4>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
-    case 1: return launch1<P1, EXACT, false, 1>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
+    if (cc)
+        return fa.w16 ? launch1<P1, EXACT, true, 0, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream)
+                      : launch1<P1, EXACT, true, 0, false>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
+    switch (fa.g) {  // g = 16 and 4 imply even strides: always 16-byte fetches (the host checks the base pointer)
+    case 16: return fa.w16 ? launch1<P1, EXACT, false, 16, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream) : -1;
+    case 4: return fa.w16 ? launch1<P1, EXACT, false, 4, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream) : -1;
+    case 1: return fa.w16 ? -1 : launch1<P1, EXACT, false, 1, false>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
     }
     return -1;
 }

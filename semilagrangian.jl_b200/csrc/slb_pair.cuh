@@ -51,6 +51,8 @@ struct FusedArgs {
     int ntile_c;                 // tiles along the cross dim
     int full;                    // 1: a tile is the whole periodic cross line
     int nrows_max;               // staged rows per march row (shared-memory pitch)
+    int spread_max;              // largest shift spread inside a tile that is still staged
+    int w16;                     // rows fetched with 16-byte cp.async (alignment verified by the host)
     const double* tabA;          // alpha_A = scaleA * tabA[plo*aAlo + phi*aAhi]
     double scaleA;
     long long aAlo, aAhi;
@@ -69,9 +71,13 @@ bool slb_fused_supported(int P1, bool cc, int g);
 size_t slb_fused_smem_bytes(int nrows_max, int g);
 
 #ifdef SLB_PAIR_IMPL
-__device__ __forceinline__ void fused_cp_async8(unsigned smem_dst, const double* gsrc)
+__device__ __forceinline__ void fused_cp_async8(unsigned smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fused_cp_async16(unsigned smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void fused_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -104,7 +110,9 @@ __device__ __forceinline__ void fused_weights(const CoefTab& ct, int nc, double 
 }
 
 // G > 0: passive points per tile fixed at compile time (CC = false); G == 0: run-time fa.g (CC = true)
-template <int P1, bool EXACT, bool CC, int G>
+// W16: rows are fetched with 16-byte cp.async (pairs of doubles; the host checks alignment), one per
+// thread and march row, instead of up to two 8-byte ones
+template <int P1, bool EXACT, bool CC, int G, bool W16>
 __global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, 1)
 k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ CoefTab ctA, const __grid_constant__ CoefTab ctB)
 {
@@ -168,20 +176,25 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         dmax = v > dmax ? v : dmax;
     }
     const bool full = fa.full != 0;
-    const bool direct = !full && (dmax - dmin > SLB_FUSED_SPREAD_MAX);  // uniform over the CTA
+    const bool direct = !full && (dmax - dmin > fa.spread_max);  // uniform over the CTA
     const int spread = full || direct ? 0 : (int)(dmax - dmin);
-    const int nrows = full ? nc_ + P1 - 1 : ta + P1 - 1 + spread;
-    int rowbase = 0;
+    int nrows = full ? nc_ + P1 - 1 : ta + P1 - 1 + spread;
+    if (W16 && CC) nrows = (nrows + 2) & ~1;  // even, with room for the alignment element
+    int rowbase = 0, rowpad = 0;
     if (!full) {
         long long rb = ((long long)a0 + dmin - HALF) % nc_;
         rowbase = (int)(rb < 0 ? rb + nc_ : rb);
+        if (W16 && CC) {  // 16-byte fetches along the cross dim start at an even index
+            rowpad = rowbase & 1;
+            rowbase -= rowpad;
+        }
     }
     int roff;  // first staged row of this thread's stencil
     if (full) {
         roff = ac + s0A;
         roff -= roff >= nc_ ? nc_ : 0;
     } else {
-        roff = a + (direct ? 0 : (int)(dA - dmin));
+        roff = a + rowpad + (direct ? 0 : (int)(dA - dmin));
     }
     constexpr int QS = CC ? 1 : (G > 0 ? G : 1);  // shared-memory stride between consecutive staged rows
     const int sread = CC ? p * fa.nrows_max + roff : roff * g + p;
@@ -207,42 +220,65 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     };
 
     if (!direct) {
-        // ---- load slots: the (up to two) staged elements this thread fetches for every march row ----
+        // ---- load slots: what this thread fetches for every march row (W16: one pair of doubles,
+        // else up to two doubles) ----------------------------------------------------------------
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(fsm);
-        const double* gsrc[2];
-        unsigned sdst[2];
-        bool lval[2];
+        constexpr int NSLOT = W16 ? 1 : 2;
+        const char* gsrc[NSLOT];
+        unsigned sdst[NSLOT];
+        bool lval[NSLOT];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NSLOT; ++s) {
             const int e = tid + s * NT;
-            lval[s] = e < nrows * g;
-            int pe, j;
-            if (CC) {
-                j = e % nrows;
-                pe = e / nrows;
+            int pe, j;  // passive point / staged row of the (first) element
+            if constexpr (W16) {
+                if (CC) {
+                    const int h = nrows >> 1;
+                    j = 2 * (e % h);
+                    pe = e / h;
+                    lval[s] = pe < g;
+                } else {
+                    const int h = g >> 1;
+                    pe = 2 * (e % h);
+                    j = e / h;
+                    lval[s] = j < nrows;
+                }
             } else {
-                pe = e % g;
-                j = e / g;
+                lval[s] = e < nrows * g;
+                if (CC) {
+                    j = e % nrows;
+                    pe = e / nrows;
+                } else {
+                    pe = e % g;
+                    j = e / g;
+                }
             }
             const long long Pe = tp * g + pe;
             if (Pe >= np) lval[s] = false;
             const long long Pq = Pe < np ? Pe : np - 1;
             const int rc = (rowbase + j) % nc_;
-            gsrc[s] = fa.in + (long long)(Pq % fa.elo) * fa.slo + (long long)(Pq / fa.elo) * fa.shi + (long long)rc * fa.sc;
+            gsrc[s] = reinterpret_cast<const char*>(fa.in) +
+                      8 * ((long long)(Pq % fa.elo) * fa.slo + (long long)(Pq / fa.elo) * fa.shi + (long long)rc * fa.sc);
             sdst[s] = sbase + 8u * (unsigned)(CC ? pe * fa.nrows_max + j : j * g + pe);
         }
         const unsigned row_b = 8u * (unsigned)row_elems, ring_b = row_b * R * D;
         // block-uniform bookkeeping of the fetch pipeline (kept in the uniform datapath)
         int b_iss = 0, k_iss = 0;   // march index / step number of the next row to fetch
-        long long boff = 0;         // b_iss * smel
+        long long boff = 0;         // b_iss * smel, in bytes
+        const long long smb = 8 * smel;
         unsigned off_iss = 0;       // byte offset of that row's slot in the ring
         auto issue_stage = [&]() {
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 if (k_iss < nsteps) {
-                    if (lval[0]) fused_cp_async8(sdst[0] + off_iss, gsrc[0] + boff);
-                    if (lval[1]) fused_cp_async8(sdst[1] + off_iss, gsrc[1] + boff);
-                    boff += smel;
+                    if constexpr (W16) {
+                        if (lval[0]) fused_cp_async16(sdst[0] + off_iss, gsrc[0] + boff);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NSLOT; ++s)
+                            if (lval[s]) fused_cp_async8(sdst[s] + off_iss, gsrc[s] + boff);
+                    }
+                    boff += smb;
                     if (++b_iss == nm) {
                         b_iss = 0;
                         boff = 0;

@@ -15,10 +15,12 @@ meaning  alpha(line) = scale * table[sum_d idx_d * strides[d]]  over the line's 
 indices -- which is exactly how the reference's own providers index their `bufcur` arrays.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _lib
+from .interp import HERMITE, LAGRANGE
 from .splitting import strangsplit
 
 
@@ -53,6 +55,12 @@ class AbstractExtDataAdv:
 
     def alpha_table(self, advd):
         raise NotImplementedError
+
+    def initcoef_reads_data(self, advd):
+        """True when initcoef of the CURRENT state reads advd's data (e.g. a charge density).
+        A provider that returns False for a state lets advection() fuse that stage with the one
+        before it into a single pass over HBM (slb_sweep_pair).  Default: assume it does."""
+        return True
 
 
 class Advection:
@@ -118,12 +126,25 @@ class AdvectionData:
         self._linesum = None        # device buffer for per-line output sums (see poisson.py)
         self._linesum_dim = None    # dim whose sweep produced the sums currently held, else None
         self.use_linesum = True
+        # pair fusion: a stage may be held back one advection() call and then run together with the
+        # next one in a single pass over HBM (slb_sweep_pair, bit-identical to two sweeps); anything
+        # that looks at the data flushes it first
+        self.fuse_pairs = os.environ.get("SLB_FUSE", "1") != "0"
+        self._pending = None
+        self.n_fused = 0
         self.upload(data)
         # mesh nodes stay on the device: shift tables for space sweeps (src/poisson.jl:191-203)
         self._points_dev = {}
 
     # -- data movement ---------------------------------------------------------------
+    def flush(self):
+        """run a stage that advection() held back for pair fusion (no-op otherwise)"""
+        pend, self._pending = self._pending, None
+        if pend is not None:
+            _sweep_now(self, *pend)
+
     def upload(self, data):
+        self._pending = None  # the data it would have swept is being replaced
         host = np.asfortranarray(data, dtype=np.float64)
         _lib.check(_lib.lib().slb_grid_upload(self.grid, host.ctypes.data_as(C.c_void_p)))
         self.ctx.sync()
@@ -131,6 +152,7 @@ class AdvectionData:
 
     def getdata(self, out=None):
         """getdata(advd) (src/advection.jl:317): a host copy of the device-resident array."""
+        self.flush()
         if out is None:
             out = np.empty(self.adv.sizeall, dtype=np.float64, order="F")
         assert out.flags.f_contiguous and out.dtype == np.float64
@@ -170,6 +192,7 @@ class AdvectionData:
         return False
 
     def close(self):
+        self._pending = None
         if self.grid:
             _lib.lib().slb_grid_destroy(self.grid)
             self.grid = None
@@ -193,23 +216,29 @@ def getdata(advd):
     return advd.getdata()
 
 
-def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0, want_linesum=False):
-    """One slb_sweep on advd's grid (kernel seam).  table: device pointer (c_void_p) when
-    on_device else a float64 numpy array.  want_linesum: also store, per line, the sum of the
-    line's outputs (consumed by the Poisson provider's next charge density)."""
-    n = advd.adv.sizeall[dim0]
-    h = interp.handle(advd.ctx, n)
+def _table_args(table, on_device):
+    if on_device:
+        ptr, length = table
+        return ptr, int(length), None
+    arr = np.ascontiguousarray(table, dtype=np.float64)
+    return arr.ctypes.data_as(C.c_void_p), arr.size, arr
+
+
+def _linesum_begin(advd, dim0, interp, want_linesum):
     advd._linesum_dim = None  # any sweep invalidates sums held from an earlier one
     ls_ok = want_linesum and advd.use_linesum and dim0 > 0 and interp.order + 1 <= 14 and interp.tabfct.shape[1] <= 14
     if ls_ok:
         if advd._linesum is None:
             advd._linesum = advd.ctx.malloc(int(np.prod(advd.adv.sizeall)) // min(advd.adv.sizeall[1:]) * 8)
         _lib.check(_lib.lib().slb_grid_set_linesum(advd.grid, advd._linesum))
-    if on_device:
-        ptr, length = table
-    else:
-        table = np.ascontiguousarray(table, dtype=np.float64)
-        ptr, length = table.ctypes.data_as(C.c_void_p), table.size
+    return ls_ok
+
+
+def _sweep_now(advd, dim0, interp, table, strides, scale, on_device, flags=0, want_linesum=False):
+    n = advd.adv.sizeall[dim0]
+    h = interp.handle(advd.ctx, n)
+    ls_ok = _linesum_begin(advd, dim0, interp, want_linesum)
+    ptr, length, _keep = _table_args(table, on_device)
     try:
         _lib.check(
             _lib.lib().slb_sweep(advd.grid, int(dim0), h, ptr, int(length), _lib.i64(strides), float(scale), 1 if on_device else 0, int(flags))
@@ -221,9 +250,71 @@ def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0, want_li
         advd._linesum_dim = dim0
 
 
+def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0, want_linesum=False):
+    """One slb_sweep on advd's grid (kernel seam).  table: (device pointer, length) when
+    on_device else a float64 numpy array.  want_linesum: also store, per line, the sum of the
+    line's outputs (consumed by the Poisson provider's next charge density)."""
+    advd.flush()
+    _sweep_now(advd, dim0, interp, table, strides, scale, on_device, flags, want_linesum)
+
+
+FUSED_ORDERS = (3, 5, 7, 9, 11)  # order + 1 in {4, 6, 8, 10, 12}: instantiated in csrc/slb_pair.cu
+
+
+def _pair_candidate(advd, stA, interpA, stridesA, on_device, stB):
+    """Can stage A (about to run) be held back and fused with the next stage B?  Static part of
+    the decision (slb_sweep_pair re-checks and may still answer SLB_E_UNSUPPORTED)."""
+    adv = advd.adv
+    if not advd.fuse_pairs or adv.N > 4:
+        return False
+    if stB.ndims != 1 or not stB.isconstdec:
+        return False
+    dA, dB = stA.perm[0] - 1, stB.perm[0] - 1
+    if dB == 0 or dA == dB or stridesA[dB] != 0:
+        return False
+    interpB = adv.t_interp[dB]
+    plain = lambda it: getattr(it, "kind", None) in (LAGRANGE, HERMITE) and it.tabfct.shape[1] <= 14
+    if not (plain(interpA) and plain(interpB)) or interpA.order != interpB.order or interpA.order not in FUSED_ORDERS:
+        return False
+    return adv.sizeall[dA] >= interpA.order + 1
+
+
+def sweep_pair(advd, stageA, stageB):
+    """Two stages in one pass over HBM.  stage = (dim0, interp, table, strides, scale, on_device,
+    flags, want_linesum).  Returns False when the library does not fuse this combination."""
+    dA, itA, tabA, strA, scA, devA = stageA[:6]
+    dB, itB, tabB, strB, scB, devB = stageB[:6]
+    flags, want_ls = stageB[6], stageB[7]
+    if devA != devB:
+        return False
+    hA = itA.handle(advd.ctx, advd.adv.sizeall[dA])
+    hB = itB.handle(advd.ctx, advd.adv.sizeall[dB])
+    pA, lA, _ka = _table_args(tabA, devA)
+    pB, lB, _kb = _table_args(tabB, devB)
+    ls_ok = _linesum_begin(advd, dB, itB, want_ls)
+    try:
+        rc = _lib.lib().slb_sweep_pair(advd.grid, int(dA), hA, pA, lA, _lib.i64(strA), float(scA), int(dB), hB, pB, lB, _lib.i64(strB),
+                                       float(scB), 1 if devA else 0, int(flags))
+    finally:
+        if ls_ok:
+            _lib.check(_lib.lib().slb_grid_set_linesum(advd.grid, None))
+    if rc == _lib.SLB_E_UNSUPPORTED:
+        return False
+    _lib.check(rc)
+    if ls_ok:
+        advd._linesum_dim = dB
+    advd.n_fused += 1
+    return True
+
+
 def advection(advd):
     """advection!(advd) -- src/advection.jl:594-704.  One split stage; returns True while
-    more stages remain in the current time step."""
+    more stages remain in the current time step.
+
+    Pair fusion: when the NEXT stage can run in the same pass over HBM (slb_sweep_pair) and its
+    initcoef does not look at the data, the current stage is only recorded; the next call runs
+    both.  getdata / compute_ke / any charge density flush a recorded stage first, so every
+    observable value is the one the reference's stage-by-stage execution produces."""
     st = advd.getst()
     if st.ndims != 1 or not st.isconstdec:
         raise NotImplementedError(
@@ -231,8 +322,27 @@ def advection(advd):
         )
     interp = advd.getinterp()[0]
     ext = advd.parext
+    if advd._pending is not None and ext.initcoef_reads_data(advd):
+        advd.flush()
     ext.initcoef(advd)  # src/advection.jl:407-408
     table, strides, scale, on_device = ext.alpha_table(advd)
     want = bool(getattr(ext, "wants_linesum", lambda a: False)(advd))
-    sweep(advd, st.perm[0] - 1, interp, table, strides, scale, on_device, advd.flags, want_linesum=want)
+    cur = (st.perm[0] - 1, interp, table, list(strides), scale, on_device, advd.flags, want)
+    if advd._pending is not None:
+        pend, advd._pending = advd._pending, None
+        if not sweep_pair(advd, pend, cur):
+            _sweep_now(advd, *pend)
+            _sweep_now(advd, *cur)
+        return advd.nextstate()
+    adv = advd.adv
+    if advd.state_gen < adv.nbstates:  # never hold a stage back across the end of a time step
+        nxt = adv.getst(advd.state_gen + 1)
+        if _pair_candidate(advd, st, interp, strides, on_device, nxt):
+            advd.state_gen += 1
+            ok = not ext.initcoef_reads_data(advd)
+            advd.state_gen -= 1
+            if ok:
+                advd._pending = cur
+                return advd.nextstate()
+    _sweep_now(advd, *cur)
     return advd.nextstate()

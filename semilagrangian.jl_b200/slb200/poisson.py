@@ -75,6 +75,7 @@ class PoissonVar(AbstractExtDataAdv):
 
     # src/poisson.jl:119-125 -> src/util_poisson.jl:68-79
     def compute_charge(self, advd):
+        advd.flush()  # a stage held back for pair fusion must have run before f is reduced
         dv = 1.0
         for m in self.adv.t_mesh[self.Nsp:]:
             dv = dv * m.step
@@ -115,6 +116,12 @@ class PoissonVar(AbstractExtDataAdv):
 
     def isvelocity(self, advd):  # src/poisson.jl:155-158
         return advd.getst().perm[0] > self.Nsp
+
+    def initcoef_reads_data(self, advd):
+        """initcoef! computes the charge density only at a velocity state that contains dim Nsp+1
+        (src/poisson.jl:171-176): every other state can be pair-fused with its predecessor."""
+        st = advd.getst()
+        return self.isvelocity(advd) and (self.Nsp + 1) in st.perm[: st.ndims]
 
     def initcoef(self, advd):
         """initcoef!(pv, advd) -- src/poisson.jl:164-205"""
@@ -198,6 +205,7 @@ def compute_ke(advd):
     dv = 1.0
     for m in adv.t_mesh[pv.Nsp:]:
         dv *= m.step
+    advd.flush()
     v = C.c_double()
     _lib.check(_lib.lib().slb_kinetic_energy(advd.grid, pv.Nsp, pv.vsq_dev, dsp * dv, C.byref(v)))
     return v.value

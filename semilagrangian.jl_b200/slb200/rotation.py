@@ -18,6 +18,9 @@ class RotationVar(AbstractExtDataAdv):
         self._other = st_other
         self.decfl = self._scale * advd.adv.t_mesh[st_other - 1].points
 
+    def initcoef_reads_data(self, advd):
+        return False  # shifts come from the meshes / constants only
+
     def alpha_table(self, advd):  # getalpha(pv, advd, ind) = (decfl[ind],)  (src/rotation.jl:71)
         strides = [0, 0]
         strides[self._other - 1] = 1

@@ -13,6 +13,9 @@ class TranslationVar(AbstractExtDataAdv):
         st = advd.getst()
         self.valok = tuple(self.values[st.perm[i] - 1] * advd.getcur_t() for i in range(st.ndims))
 
+    def initcoef_reads_data(self, advd):
+        return False  # shifts come from the meshes / constants only
+
     def alpha_table(self, advd):  # getalpha: constant shift (src/translation.jl:33-35)
         return np.array([self.valok[0]]), [0] * advd.adv.N, 1.0, False
 

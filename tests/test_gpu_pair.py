@@ -123,3 +123,101 @@ def test_pair_repeated_launches_and_linesums():
     ctx.free(ls)
     g1.close()
     g2.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# driver level: advection() holds a stage back and fuses it with the next one
+# ---------------------------------------------------------------------------------------------
+def _vp_2d2v(M, sz, order, dt=0.1, eps=0.5):
+    import math
+
+    ms = (M.UniformMesh(0.0, 4 * math.pi, sz[0]), M.UniformMesh(0.0, 4 * math.pi, sz[1]),
+          M.UniformMesh(-6.0, 6.0, sz[2]), M.UniformMesh(-6.0, 6.0, sz[3]))
+    tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+    adv = M.Advection(ms, [M.Lagrange(order)] * 4, dt, tabst)
+    fsp = lambda x: eps * np.cos(x / 2) + 1
+    fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+    f = M.dotprod((fsp(ms[0].points), fsp(ms[1].points), fv(ms[2].points), fv(ms[3].points)))
+    return adv, M.AdvectionData(adv, f, M.getpoissonvar(adv))
+
+
+@pytest.mark.parametrize("use_linesum", [False, True])
+@pytest.mark.parametrize("sz,order", [((32, 32, 32, 32), 7), ((48, 20, 24, 12), 9), ((16, 16, 40, 36), 5)])
+def test_driver_fuses_pairs_and_matches_unfused_and_oracle(sz, order, use_linesum):
+    """A Strang step of examples/vlasov-poisson-2d2v.jl runs as three fused passes (v1v2, x1x2,
+    v1v2); the result equals the stage-by-stage execution bit for bit and the oracle to 1e-12/sweep.
+    (With the line-sum shortcut for rho the two drivers add the same numbers in a different
+    order -- the fused kernel emits a line's outputs starting at the wrap point -- so they agree
+    to rounding only.)"""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    _, fused = _vp_2d2v(S, sz, order)
+    _, plain = _vp_2d2v(S, sz, order)
+    _, orc = _vp_2d2v(R, sz, order)
+    plain.fuse_pairs = False
+    fused.use_linesum = plain.use_linesum = use_linesum
+    assert fused.fuse_pairs
+    nsteps = 3
+    for step in range(nsteps):
+        while S.advection(fused):
+            pass
+        while S.advection(plain):
+            pass
+        while R.advection(orc):
+            pass
+        assert fused.n_fused == 3 * (step + 1) and plain.n_fused == 0
+        ee_f, ee_p, ee_o = S.compute_ee(fused), S.compute_ee(plain), R.compute_ee(orc)
+        assert ee_f == ee_p if not use_linesum else abs(ee_f - ee_p) <= 1e-13 * abs(ee_p)
+        assert abs(ee_f - ee_o) <= 1e-11 * abs(ee_o)
+    a, b = fused.getdata(), plain.getdata()
+    assert np.array_equal(a, b) if not use_linesum else relerr(a, b) <= 1e-13
+    assert relerr(a, orc.data) <= 1e-12 * 6 * nsteps
+    assert abs(S.compute_ke(fused) - R.compute_ke(orc)) <= 1e-12 * abs(R.compute_ke(orc))
+
+
+def test_driver_flushes_a_held_back_stage_on_access():
+    """getdata() between the two stages of a pair must see the first stage applied (the reference
+    mutates advd.data in every advection! call, src/advection.jl:594-657)."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    sz = (16, 16, 16, 16)
+    _, g = _vp_2d2v(S, sz, 7)
+    _, o = _vp_2d2v(R, sz, 7)
+    more = True
+    while more:
+        more = S.advection(g)
+        R.advection(o)
+        assert relerr(g.getdata(), o.data) <= 1e-12 * 8
+    assert g.n_fused == 0  # every stage was flushed by the read that followed it
+    while S.advection(g):
+        pass
+    while R.advection(o):
+        pass
+    assert g.n_fused == 3
+    assert relerr(g.getdata(), o.data) <= 1e-12 * 14
+
+
+def test_driver_fuses_translation_with_host_tables():
+    """2-D translation (src/translation.jl): both stages have constant host-side shifts; the x/y pair
+    of a Strang step [x y x] fuses as (x, y) and the trailing x runs alone."""
+    import slb200 as S
+
+    def build(fuse):
+        m1, m2 = S.UniformMesh(0.0, 1.0, 96), S.UniformMesh(0.0, 1.0, 80)
+        adv = S.Advection((m1, m2), [S.Lagrange(5), S.Lagrange(5)], 0.01, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)])
+        X, Y = np.meshgrid(m1.points, m2.points, indexing="ij")
+        f = np.asfortranarray(np.exp(-(np.sin(2 * np.pi * X) + np.sin(2 * np.pi * Y))))
+        d = S.AdvectionData(adv, f, S.gettranslationvar((30.0, -20.0)))
+        d.fuse_pairs = fuse
+        return d
+
+    a, b = build(True), build(False)
+    for _ in range(4):
+        while S.advection(a):
+            pass
+        while S.advection(b):
+            pass
+    assert a.n_fused == 4 and b.n_fused == 0
+    assert np.array_equal(a.getdata(), b.getdata())
