@@ -135,8 +135,8 @@ int slb_sweep(slb_grid* g, int dim, const slb_interp* it, const double* alpha_ta
  * src/poisson.jl:178-203.  A line-sum buffer set with slb_grid_set_linesum receives the sums of
  * sweep B's outputs.
  * Returns SLB_E_UNSUPPORTED for combinations that are not pair-fused (dimB == 0, alpha_A depending
- * on dimB, B-spline pre-solves, different orders, more than 4 dims): callers then issue the two
- * sweeps separately. */
+ * on dimB or alpha_B on dimA, B-spline pre-solves, different or even orders, more than 4 dims):
+ * callers then issue the two sweeps separately. */
 int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA_tab, int64_t alphaA_len,
                    const int64_t* alphaA_strides, double alphaA_scale, int dimB, const slb_interp* itB,
                    const double* alphaB_tab, int64_t alphaB_len, const int64_t* alphaB_strides, double alphaB_scale,

@@ -816,60 +816,71 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
         }
         ++npass;
     }
-    fa.aBc = astrB[dimA];
+    if (astrB[dimA] != 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: the second sweep's shift must not depend on the first sweep's dim");
     fa.lsc = lsstr[dimA];
     const int64_t np = (int64_t)fa.elo * fa.ehi;
     if (np >= ((int64_t)1 << 31)) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: grid too large");
+    // tiles: `ta` (even) cross outputs x `gg` passive points, two cross outputs per thread
     const bool cc = (dimA == 0);
     int gg, ta, full;
+    const int64_t nc_even = (ncross + 1) & ~(int64_t)1;
     if (cc) {
-        if (ncross <= SLB_FUSED_MAXTHREADS) {
+        if (nc_even / 2 <= SLB_FUSED_MAXTHREADS) {
             full = 1;
-            ta = (int)ncross;
-            int64_t want = env_ll("SLB_FUSED_CC_THREADS", 128) / ncross;
+            ta = (int)nc_even;
+            int64_t want = 2 * env_ll("SLB_FUSED_CC_THREADS", 64) / ta;  // lines per block
             gg = (int)(want < 1 ? 1 : want);
             if (gg > np) gg = (int)np;
-            while ((int64_t)gg * ta > SLB_FUSED_MAXTHREADS) --gg;
+            while ((int64_t)gg * ta / 2 > SLB_FUSED_MAXTHREADS) --gg;
         } else {
             full = 0;
-            ta = 256;
+            ta = 512;
             gg = 1;
         }
     } else {
         gg = 16;  // 128 B rows; smaller only when dim 0 is not a multiple
         while (gg > 1 && (fa.elo % gg != 0 || !slb_fused_supported(P1, false, gg))) gg >>= 1;
-        int64_t want = env_ll("SLB_FUSED_THREADS", 256) / gg;
-        if (want > SLB_FUSED_MAXTHREADS / gg) want = SLB_FUSED_MAXTHREADS / gg;
+        int64_t want = 2 * env_ll("SLB_FUSED_THREADS", 256) / gg;  // cross outputs per tile
+        if (want > 2 * SLB_FUSED_MAXTHREADS / gg) want = 2 * SLB_FUSED_MAXTHREADS / gg;
         if (want < 16) want = 16;
-        if (want >= ncross) {
+        want &= ~(int64_t)1;
+        if (want >= nc_even) {
             full = 1;
-            ta = (int)ncross;
+            ta = (int)nc_even;
         } else {
             full = 0;
             ta = (int)want;
         }
-        if ((int64_t)gg * ta > SLB_FUSED_MAXTHREADS) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit a thread block");
+        if ((int64_t)gg * ta / 2 > SLB_FUSED_MAXTHREADS) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit a thread block");
     }
     if (!slb_fused_supported(P1, cc, gg)) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: order %d is not on the fused path", P1 - 1);
     fa.g = gg;
     fa.ta = ta;
     fa.full = full;
     fa.ntile_c = (int)((ncross + ta - 1) / ta);
-    // every thread fetches at most two staged elements per march row: rows <= 2 * ta
-    fa.spread_max = full ? 0 : 2 * ta - (ta + P1 - 1);
-    if (fa.spread_max > SLB_FUSED_SPREAD_MAX) fa.spread_max = SLB_FUSED_SPREAD_MAX;
-    fa.nrows_max = full ? (int)ncross + P1 - 1 : ta + P1 - 1 + fa.spread_max;
-    if (fa.spread_max < 0 || fa.nrows_max > 2 * ta) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: lines too short for the fused kernel");
     // 16-byte fetches (pairs of doubles along the contiguous index) when everything is 16-byte aligned
-    const bool aligned = ((uintptr_t)g->front % 16 == 0);
+    const bool aligned = ((uintptr_t)g->front % 16 == 0) && ((uintptr_t)g->back % 16 == 0);
     auto even = [](long long v) { return (v & 1) == 0; };
     if (cc) {
         fa.w16 = aligned && even(ncross) && even(fa.sm) && even(fa.slo) && even(fa.shi) && fa.sc == 1;
-        if (fa.w16) fa.nrows_max = (fa.nrows_max + 3) & ~1;  // even pitch + room for the alignment element
     } else {
         fa.w16 = gg > 1;
         if (fa.w16 && !(aligned && fa.slo == 1 && even(fa.elo) && even(fa.sc) && even(fa.sm) && (fa.ehi == 1 || even(fa.shi))))
             return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: buffers are not 16-byte aligned");
+    }
+    // every thread fetches at most two pairs (four doubles) per march row: staged rows <= 2 * ta
+    for (;;) {
+        const int extra = (cc && fa.w16) ? 2 : 0;  // even pitch + room for the alignment element
+        fa.spread_max = full ? 0 : 2 * ta - (ta + P1 - 1) - extra;
+        if (fa.spread_max > SLB_FUSED_SPREAD_MAX) fa.spread_max = SLB_FUSED_SPREAD_MAX;
+        fa.nrows_max = (full ? (int)ncross + P1 : ta + P1 - 1 + fa.spread_max) + extra;
+        if (extra) fa.nrows_max &= ~1;
+        if (fa.spread_max >= 0 && fa.nrows_max <= 2 * ta) break;
+        if (cc && fa.w16) {
+            fa.w16 = 0;  // short lines: 8-byte fetches need no alignment slack
+            continue;
+        }
+        return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: lines too short for the fused kernel");
     }
     const double *tabA = alphaA, *tabB = alphaB;
     if (!on_device) {
@@ -893,7 +904,7 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     const size_t smem = slb_fused_smem_bytes(fa.nrows_max, gg);
     if (smem > 200 * 1024) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit shared memory");
     const bool exact = (flags & SLB_SWEEP_EXACT) != 0;
-    int lrc = slb_fused_launch(fa, itA->tab, itB->tab, P1, exact, cc, (unsigned)nblk, (unsigned)(gg * ta), smem, c->stream);
+    int lrc = slb_fused_launch(fa, itA->tab, itB->tab, P1, exact, cc, (unsigned)nblk, (unsigned)(gg * ta / 2), smem, c->stream);
     if (lrc < 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: no fused kernel for order %d, tile width %d", P1 - 1, gg);
     if (lrc != 0) return fail(SLB_E_CUDA, "slb_sweep_pair: launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
     c->launches++;

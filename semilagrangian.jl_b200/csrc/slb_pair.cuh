@@ -7,7 +7,9 @@
 // once and writes it once -- 16 B of HBM traffic per cell for TWO cell-updates:
 //
 //   * a CTA owns a tile of `ta` consecutive cross indices x `g` points of the remaining
-//     ("passive") dims and marches over the whole march dim, one input row per step;
+//     ("passive") dims and marches over the whole march dim, two input rows per block barrier;
+//     every thread produces TWO neighbouring cross outputs (their stencils share order of the
+//     order+2 staged inputs, and all per-row bookkeeping is paid once for both);
 //   * sweep A is a cross-THREAD stencil: the step's input rows (tile + periodic halo) are staged
 //     in shared memory by cp.async (a ring of D stages, filled D-1 steps ahead, so the loads in
 //     flight cost no registers), and thread (p, a) forms T = sum_q w1[q] * raw[a + s0A(p) + q];
@@ -36,9 +38,9 @@
 #include "slb_sweep.cuh"
 
 #define SLB_FUSED_SPREAD_MAX 16
-#define SLB_FUSED_STAGES 5       // ring of shared-memory stages
-#define SLB_FUSED_ROWS 2         // march rows per stage (= per block barrier)
-#define SLB_FUSED_MAXTHREADS 512
+#define SLB_FUSED_STAGES 5       // shared-memory ring: D stages ...
+#define SLB_FUSED_ROWS 2         // ... of R march rows each; one block barrier per stage
+#define SLB_FUSED_MAXTHREADS 256
 
 struct FusedArgs {
     const double* in;
@@ -47,7 +49,7 @@ struct FusedArgs {
     long long sc, sm;            // their element strides
     unsigned elo, ehi;           // extents of the (up to two) passive index groups
     long long slo, shi;          // their element strides
-    int g, ta;                   // passive points / cross outputs per tile (blockDim = g * ta)
+    int g, ta;                   // passive points / cross outputs (even) per tile; blockDim = g * ta / 2
     int ntile_c;                 // tiles along the cross dim
     int full;                    // 1: a tile is the whole periodic cross line
     int nrows_max;               // staged rows per march row (shared-memory pitch)
@@ -56,9 +58,9 @@ struct FusedArgs {
     const double* tabA;          // alpha_A = scaleA * tabA[plo*aAlo + phi*aAhi]
     double scaleA;
     long long aAlo, aAhi;
-    const double* tabB;          // alpha_B = scaleB * tabB[plo*aBlo + phi*aBhi + a*aBc]
+    const double* tabB;          // alpha_B = scaleB * tabB[plo*aBlo + phi*aBhi]
     double scaleB;
-    long long aBlo, aBhi, aBc;
+    long long aBlo, aBhi;
     int ncA, ncB;                // polynomial coefficients per weight
     double* linesum;             // optional: per (passive, cross) sum over the march dim of the outputs
     long long lslo, lshi, lsc;
@@ -85,6 +87,10 @@ __device__ __forceinline__ void fused_cp_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void fused_st_v2(double* p, double a, double b)
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
 
 // one term of slb_dot: same rounding as its EXACT / FMA branches
 template <bool EXACT>
@@ -96,6 +102,24 @@ template <bool EXACT>
 __device__ __forceinline__ double slb_acc(double acc, double x, double w)
 {
     return EXACT ? __dadd_rn(acc, __dmul_rn(x, w)) : fma(x, w, acc);
+}
+// sum_{j < P1} x[OFF + j] * w[j], left to right (== slb_dot on the shifted window)
+template <int P1, bool EXACT, int OFF, int NX>
+__device__ __forceinline__ double fused_dot(const double (&x)[NX], const double (&w)[P1])
+{
+    double acc = slb_mul<EXACT>(x[OFF], w[0]);
+#pragma unroll
+    for (int j = 1; j < P1; ++j) acc = slb_acc<EXACT>(acc, x[OFF + j], w[j]);
+    return acc;
+}
+// the first NOLD terms of the march-direction dot product whose window starts at slot `rot`
+template <int P1, bool EXACT, int NOLD>
+__device__ __forceinline__ double fused_partial(const double (&win)[P1], const double (&w)[P1], int rot)
+{
+    double acc = slb_mul<EXACT>(win[rot % P1], w[0]);
+#pragma unroll
+    for (int j = 1; j < NOLD; ++j) acc = slb_acc<EXACT>(acc, win[(rot + j) % P1], w[j]);
+    return acc;
 }
 
 template <int P1>
@@ -110,42 +134,42 @@ __device__ __forceinline__ void fused_weights(const CoefTab& ct, int nc, double 
 }
 
 // G > 0: passive points per tile fixed at compile time (CC = false); G == 0: run-time fa.g (CC = true)
-// W16: rows are fetched with 16-byte cp.async (pairs of doubles; the host checks alignment), one per
-// thread and march row, instead of up to two 8-byte ones
+// W16: rows are fetched with 16-byte cp.async (pairs of doubles; the host checks alignment)
 template <int P1, bool EXACT, bool CC, int G, bool W16>
-__global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, 1)
+__global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, (P1 <= 8 ? 2 : 1))  // orders <= 7: 128 registers, two blocks per SM
 k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ CoefTab ctA, const __grid_constant__ CoefTab ctB)
 {
     constexpr int D = SLB_FUSED_STAGES;
     constexpr int R = SLB_FUSED_ROWS;
     constexpr int HALF = (P1 - 1) / 2;
-    static_assert(P1 % R == 0, "rows per stage must divide the unroll length");
+    static_assert(P1 % 2 == 0 && R == 2, "two march rows per barrier; order + 1 must be even");
     extern __shared__ __align__(16) double fsm[];
     const int NT = blockDim.x, tid = threadIdx.x;
     const int g = G > 0 ? G : fa.g;
-    const int ta = fa.ta, nc_ = fa.ncross, nm = fa.nmarch;
-    int p, a;
+    const int ta = fa.ta, ta2 = ta >> 1, nc_ = fa.ncross, nm = fa.nmarch;
+    int p, a;  // passive point and FIRST cross output (local index, even) of this thread
     if (CC) {
-        a = tid % ta;
-        p = tid / ta;
+        a = 2 * (tid % ta2);
+        p = tid / ta2;
     } else {
         p = tid % g;
-        a = tid / g;
+        a = 2 * (tid / g);
     }
     const int tc = (int)(blockIdx.x % (unsigned)fa.ntile_c);
     const long long tp = blockIdx.x / (unsigned)fa.ntile_c;
     const int a0 = tc * ta;
     const long long np = (long long)fa.elo * fa.ehi;
     const long long P = tp * g + p;
-    const bool act = (P < np) && (a0 + a < nc_);
+    const bool act0 = (P < np) && (a0 + a < nc_);
+    const bool act1 = (P < np) && (a0 + a + 1 < nc_);
     const long long Pc = P < np ? P : np - 1;  // idle threads mimic a valid point (they never store)
     const int ac = (a0 + a < nc_) ? a0 + a : nc_ - 1;
     const unsigned plo = (unsigned)(Pc % fa.elo), phi = (unsigned)(Pc / fa.elo);
     const long long pbase = (long long)plo * fa.slo + (long long)phi * fa.shi;
 
-    // ---- sweep A (cross): shift and weights of this thread's passive point ---------------------
+    // ---- shifts and weights of this thread's passive point: sweep A (cross), sweep B (march) ----
     double w1[P1], w2[P1];
-    int s0A;
+    int s0A, s0B;
     long long dA;
     {
         const double alpha = fa.scaleA * __ldg(fa.tabA + (long long)plo * fa.aAlo + (long long)phi * fa.aAhi);
@@ -155,10 +179,8 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         dA = fabs(fl) < 4.0e18 ? (long long)fl : (fl < 0 ? -4000000000000000000LL : 4000000000000000000LL);
         fused_weights<P1>(ctA, fa.ncA, t, w1);
     }
-    // ---- sweep B (march) -----------------------------------------------------------------------
-    int s0B;
     {
-        const double alpha = fa.scaleB * __ldg(fa.tabB + (long long)plo * fa.aBlo + (long long)phi * fa.aBhi + (long long)ac * fa.aBc);
+        const double alpha = fa.scaleB * __ldg(fa.tabB + (long long)plo * fa.aBlo + (long long)phi * fa.aBhi);
         double t;
         slb_split(alpha, nm, HALF, t, s0B);
         fused_weights<P1>(ctB, fa.ncB, t, w2);
@@ -178,7 +200,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     const bool full = fa.full != 0;
     const bool direct = !full && (dmax - dmin > fa.spread_max);  // uniform over the CTA
     const int spread = full || direct ? 0 : (int)(dmax - dmin);
-    int nrows = full ? nc_ + P1 - 1 : ta + P1 - 1 + spread;
+    int nrows = full ? nc_ + P1 : ta + P1 - 1 + spread;
     if (W16 && CC) nrows = (nrows + 2) & ~1;  // even, with room for the alignment element
     int rowbase = 0, rowpad = 0;
     if (!full) {
@@ -189,7 +211,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
             rowbase -= rowpad;
         }
     }
-    int roff;  // first staged row of this thread's stencil
+    int roff;  // first staged row of this thread's stencils (inputs roff .. roff + P1)
     if (full) {
         roff = ac + s0A;
         roff -= roff >= nc_ ? nc_ : 0;
@@ -200,30 +222,34 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     const int sread = CC ? p * fa.nrows_max + roff : roff * g + p;
 
     const int nsteps = nm + P1 - 1;
-    const long long smel = fa.sm;
-    int iout = s0B == 0 ? 0 : nm - s0B;  // output index emitted at step P1-1
-    double* const po0 = fa.out + pbase + (long long)ac * fa.sc;
-    double* po = po0 + (long long)iout * smel;
-    double win[P1];
+    const long long smel = fa.sm, scel = fa.sc;
+    int iout = s0B == 0 ? 0 : nm - s0B;  // march index of the outputs emitted at step P1-1
+    double* const po0 = fa.out + pbase + (long long)ac * scel;
+    double winA[P1], winB[P1];           // last order+1 values of T for the two cross outputs
 #pragma unroll
-    for (int j = 0; j < P1; ++j) win[j] = 0.0;
-    double lsum = 0.0;
+    for (int j = 0; j < P1; ++j) winA[j] = winB[j] = 0.0;
+    double lsumA = 0.0, lsumB = 0.0;
 
-    auto emit = [&](double acc) {
-        lsum += acc;
-        if (act) __stcs(po, acc);
-        po += smel;
-        if (++iout == nm) {
-            iout = 0;
-            po = po0;
+    auto emit = [&](double accA, double accB) {
+        lsumA += accA;
+        lsumB += accB;
+        double* po = po0 + (long long)iout * smel;
+        if (CC && W16) {  // neighbouring outputs are neighbours in memory, 16-byte aligned
+            if (act1)
+                fused_st_v2(po, accA, accB);
+            else if (act0)
+                __stcs(po, accA);
+        } else {
+            if (act0) __stcs(po, accA);
+            if (act1) __stcs(po + scel, accB);
         }
+        iout = iout + 1 == nm ? 0 : iout + 1;
     };
 
     if (!direct) {
-        // ---- load slots: what this thread fetches for every march row (W16: one pair of doubles,
-        // else up to two doubles) ----------------------------------------------------------------
+        // ---- load slots: what this thread fetches for every march row ---------------------------
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(fsm);
-        constexpr int NSLOT = W16 ? 1 : 2;
+        constexpr int NSLOT = W16 ? 2 : 4;
         const char* gsrc[NSLOT];
         unsigned sdst[NSLOT];
         bool lval[NSLOT];
@@ -258,7 +284,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
             const long long Pq = Pe < np ? Pe : np - 1;
             const int rc = (rowbase + j) % nc_;
             gsrc[s] = reinterpret_cast<const char*>(fa.in) +
-                      8 * ((long long)(Pq % fa.elo) * fa.slo + (long long)(Pq / fa.elo) * fa.shi + (long long)rc * fa.sc);
+                      8 * ((long long)(Pq % fa.elo) * fa.slo + (long long)(Pq / fa.elo) * fa.shi + (long long)rc * scel);
             sdst[s] = sbase + 8u * (unsigned)(CC ? pe * fa.nrows_max + j : j * g + pe);
         }
         const unsigned row_b = 8u * (unsigned)row_elems, ring_b = row_b * R * D;
@@ -271,12 +297,14 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 if (k_iss < nsteps) {
-                    if constexpr (W16) {
-                        if (lval[0]) fused_cp_async16(sdst[0] + off_iss, gsrc[0] + boff);
-                    } else {
 #pragma unroll
-                        for (int s = 0; s < NSLOT; ++s)
-                            if (lval[s]) fused_cp_async8(sdst[s] + off_iss, gsrc[s] + boff);
+                    for (int s = 0; s < NSLOT; ++s) {
+                        if (lval[s]) {
+                            if constexpr (W16)
+                                fused_cp_async16(sdst[s] + off_iss, gsrc[s] + boff);
+                            else
+                                fused_cp_async8(sdst[s] + off_iss, gsrc[s] + boff);
+                        }
                     }
                     boff += smb;
                     if (++b_iss == nm) {
@@ -296,34 +324,38 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         const double* sp = fsm + sread;
         const double* const sp_end = sp + (size_t)R * D * row_elems;
 
-        // One barrier interval = R = 2 march rows at window slots r, r+1.  The terms of the two
+        // One block barrier per two march rows (window slots r, r+1).  The terms of the four
         // march-direction dot products that only involve OLD window entries are summed before the
-        // barrier (same left-to-right order as slb_dot, hence bit-identical), so that after the
-        // barrier only the cross stencil and two or three dependent operations remain.
+        // barrier (same left-to-right order as slb_dot, hence bit-identical), so that after it only
+        // the cross stencils and two or three dependent operations per output remain.
 #define SLB_FUSED_INTERVAL(r, EMIT0, EMIT1)                                                             \
     {                                                                                                   \
-        double part0 = slb_mul<EXACT>(win[((r) + 1) % P1], w2[0]);                                      \
-        _Pragma("unroll") for (int j = 1; j < P1 - 1; ++j)                                              \
-            part0 = slb_acc<EXACT>(part0, win[((r) + 1 + j) % P1], w2[j]);                              \
-        double part1 = slb_mul<EXACT>(win[((r) + 2) % P1], w2[0]);                                      \
-        _Pragma("unroll") for (int j = 1; j < P1 - 2; ++j)                                              \
-            part1 = slb_acc<EXACT>(part1, win[((r) + 2 + j) % P1], w2[j]);                              \
+        const double pA0 = fused_partial<P1, EXACT, P1 - 1>(winA, w2, (r) + 1);                         \
+        const double pB0 = fused_partial<P1, EXACT, P1 - 1>(winB, w2, (r) + 1);                         \
+        const double pA1 = fused_partial<P1, EXACT, P1 - 2>(winA, w2, (r) + 2);                         \
+        const double pB1 = fused_partial<P1, EXACT, P1 - 2>(winB, w2, (r) + 2);                         \
         fused_cp_wait<D - 2>();                                                                         \
         __syncthreads();                                                                                \
         issue_stage();                                                                                  \
-        double xa[R][P1];                                                                               \
+        double xa[R][P1 + 1];                                                                           \
         _Pragma("unroll") for (int rr = 0; rr < R; ++rr)                                                \
-            _Pragma("unroll") for (int q = 0; q < P1; ++q) xa[rr][q] = sp[rr * row_elems + q * QS];     \
+            _Pragma("unroll") for (int q = 0; q <= P1; ++q) xa[rr][q] = sp[rr * row_elems + q * QS];    \
         sp += R * row_elems;                                                                            \
         sp = sp == sp_end ? sp - (size_t)R * D * row_elems : sp;                                        \
-        const double T0 = slb_dot<P1, EXACT>(xa[0], w1, 0);                                             \
-        const double T1 = slb_dot<P1, EXACT>(xa[1], w1, 0);                                             \
-        win[(r)] = T0;                                                                                  \
-        win[(r) + 1] = T1;                                                                              \
-        if (EMIT0) emit(slb_acc<EXACT>(part0, T0, w2[P1 - 1]));                                         \
-        if (EMIT1) emit(slb_acc<EXACT>(slb_acc<EXACT>(part1, T0, w2[P1 - 2]), T1, w2[P1 - 1]));         \
+        const double TA0 = fused_dot<P1, EXACT, 0>(xa[0], w1);                                          \
+        const double TB0 = fused_dot<P1, EXACT, 1>(xa[0], w1);                                          \
+        const double TA1 = fused_dot<P1, EXACT, 0>(xa[1], w1);                                          \
+        const double TB1 = fused_dot<P1, EXACT, 1>(xa[1], w1);                                          \
+        winA[(r)] = TA0;                                                                                \
+        winB[(r)] = TB0;                                                                                \
+        winA[(r) + 1] = TA1;                                                                            \
+        winB[(r) + 1] = TB1;                                                                            \
+        if (EMIT0) emit(slb_acc<EXACT>(pA0, TA0, w2[P1 - 1]), slb_acc<EXACT>(pB0, TB0, w2[P1 - 1]));    \
+        if (EMIT1)                                                                                      \
+            emit(slb_acc<EXACT>(slb_acc<EXACT>(pA1, TA0, w2[P1 - 2]), TA1, w2[P1 - 1]),                 \
+                 slb_acc<EXACT>(slb_acc<EXACT>(pB1, TB0, w2[P1 - 2]), TB1, w2[P1 - 1]));                \
     }
-        // first block: the window fills up (nsteps >= P1, so no bounds checks)
+        // first block: the windows fill up (nsteps >= P1, so no bounds checks)
 #pragma unroll
         for (int r = 0; r < P1; r += R) SLB_FUSED_INTERVAL(r, (r >= P1 - 1), (r + 1 >= P1 - 1))
         int k0 = P1;
@@ -351,19 +383,23 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
                     b = b + 1 == nm ? 0 : b + 1;
                     int rc = ac + s0A;
                     rc -= rc >= nc_ ? nc_ : 0;
-                    double xa[P1];
+                    double xa[P1 + 1];
 #pragma unroll
-                    for (int q = 0; q < P1; ++q) {
-                        xa[q] = __ldg(src + (long long)rc * fa.sc);
+                    for (int q = 0; q <= P1; ++q) {
+                        xa[q] = __ldg(src + (long long)rc * scel);
                         rc = rc + 1 == nc_ ? 0 : rc + 1;
                     }
-                    win[r] = slb_dot<P1, EXACT>(xa, w1, 0);
-                    if (k >= P1 - 1) emit(slb_dot<P1, EXACT>(win, w2, (r + 1) % P1));
+                    winA[r] = fused_dot<P1, EXACT, 0>(xa, w1);
+                    winB[r] = fused_dot<P1, EXACT, 1>(xa, w1);
+                    if (k >= P1 - 1) emit(slb_dot<P1, EXACT>(winA, w2, (r + 1) % P1), slb_dot<P1, EXACT>(winB, w2, (r + 1) % P1));
                 }
             }
         }
     }
-    if (fa.linesum && act)
-        fa.linesum[(long long)plo * fa.lslo + (long long)phi * fa.lshi + (long long)ac * fa.lsc] = lsum;
+    if (fa.linesum) {
+        double* ls = fa.linesum + (long long)plo * fa.lslo + (long long)phi * fa.lshi + (long long)ac * fa.lsc;
+        if (act0) ls[0] = lsumA;
+        if (act1) ls[fa.lsc] = lsumB;
+    }
 }
 #endif  // SLB_PAIR_IMPL

@@ -261,7 +261,7 @@ def sweep(advd, dim0, interp, table, strides, scale, on_device, flags=0, want_li
 FUSED_ORDERS = (3, 5, 7, 9, 11)  # order + 1 in {4, 6, 8, 10, 12}: instantiated in csrc/slb_pair.cu
 
 
-def _pair_candidate(advd, stA, interpA, stridesA, on_device, stB):
+def _pair_candidate(advd, stA, interpA, stridesA, on_device, stB):  # noqa: ARG001
     """Can stage A (about to run) be held back and fused with the next stage B?  Static part of
     the decision (slb_sweep_pair re-checks and may still answer SLB_E_UNSUPPORTED)."""
     adv = advd.adv

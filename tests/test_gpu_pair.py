@@ -50,7 +50,7 @@ def test_pair_equals_two_sweeps_bitwise(shape, dimA, dimB, kind, order, mode):
     iA, oA = make_pair(kind, order, shape[dimA])
     iB, oB = make_pair(kind, order, shape[dimB])
     tA, sA = _alpha(rng, shape, dimA, mode, skip=dimB)
-    tB, sB = _alpha(rng, shape, dimB, mode)
+    tB, sB = _alpha(rng, shape, dimB, mode, skip=dimA)
     for flags in (0, 1):
         g1 = DeviceGrid(f)
         g1.sweep(dimA, iA, tA, sA, flags=flags)
@@ -83,6 +83,11 @@ def test_pair_rejects_unsupported_combinations():
         g.sweep_pair(1, L7, one, z, 0, L7, one, z)
     with pytest.raises(S.SlbError):   # alpha_A must not depend on the second sweep's dim
         g.sweep_pair(2, L7, np.full(8, 0.3), [0, 0, 0, 1], 3, L7, one, z)
+    with pytest.raises(S.SlbError):   # nor alpha_B on the first sweep's dim
+        g.sweep_pair(2, L7, one, z, 3, L7, np.full(8, 0.3), [0, 0, 1, 0])
+    with pytest.raises(S.SlbError):   # even orders are not instantiated
+        L4 = S.Lagrange(4)
+        g.sweep_pair(2, L4, one, z, 3, L4, one, z)
     with pytest.raises(S.SlbError):   # different orders
         g.sweep_pair(2, L7, one, z, 3, L5, one, z)
     with pytest.raises(ValueError):   # same dim twice
