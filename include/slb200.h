@@ -142,6 +142,26 @@ int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, const double* a
                    const double* alphaB_tab, int64_t alphaB_len, const int64_t* alphaB_strides, double alphaB_scale,
                    int alpha_on_device, int flags);
 
+/* slb_sweep_pair with the multi-GPU re-shard fused in (replaces mpibroadcast,
+ * src/mpiinterface.jl:17-38).  Both sides may be BLOCK-MAJOR along dimB: nblocks consecutive
+ * sub-arrays, each with extent[dimB] / nblocks along dimB.
+ *   in_nblocks  > 1: the front buffer holds the blocks an all-to-all delivered (block r from rank r);
+ *   out_nblocks > 1: block q of the result is stored at out_block_bases[q] -- a pointer into the
+ *                    buffer of the rank that owns block q after the exchange (this GPU's HBM or a
+ *                    peer's, mapped with slb_ipc_open_handle): the stores travel over NVLink inside
+ *                    the sweep and no separate collective or pack pass exists.  With
+ *                    out_block_bases == NULL the blocks go to this grid's back buffer (for an NCCL
+ *                    all-to-all) and front/back swap; otherwise the grid's roles do not change and
+ *                    callers synchronise the ranks before reading the result.
+ *   first_block    : the march along dimB is periodic and may start at any output block; rank r of P
+ *                    passes (r + 1) % P so that at any time the P ranks store into P different
+ *                    destinations (no incast on one GPU's NVLink ingress). */
+int slb_sweep_pair_ex(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA_tab, int64_t alphaA_len,
+                      const int64_t* alphaA_strides, double alphaA_scale, int dimB, const slb_interp* itB,
+                      const double* alphaB_tab, int64_t alphaB_len, const int64_t* alphaB_strides, double alphaB_scale,
+                      int alpha_on_device, int flags, int in_nblocks, int out_nblocks, double* const* out_block_bases,
+                      int first_block);
+
 /* ---- sweeps fused with the multi-GPU re-shard -------------------------------- */
 /* A 2D2V grid sharded over P ranks alternates between two slab layouts; the all-to-all between
  * them (replacing mpibroadcast, src/mpiinterface.jl:17-38) moves contiguous blocks only when the

@@ -758,9 +758,10 @@ static long long env_ll(const char* name, long long dflt)
     return atoll(v);
 }
 
-extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
-                              const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
-                              int64_t alenB, const int64_t* astrB, double scaleB, int on_device, int flags)
+static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
+                           const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
+                           int64_t alenB, const int64_t* astrB, double scaleB, int on_device, int flags, int in_nblocks,
+                           int out_nblocks, double* const* out_bases, int first_block)
 {
     if (!g || !itA || !itB) return fail(SLB_E_ARG, "slb_sweep_pair: NULL argument");
     slb_ctx* c = g->ctx;
@@ -781,11 +782,22 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     if (ncross < P1 || ncross >= ((int64_t)1 << 30) || nmarch >= ((int64_t)1 << 30))
         return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: line length out of range for the fused kernel");
     CUDA_TRY(cudaSetDevice(c->device));
-    int64_t gs[SLB_MAX_DIMS], lsstr[SLB_MAX_DIMS];
-    int64_t run = 1, lsrun = 1;
+    if (in_nblocks < 1) in_nblocks = 1;
+    if (out_nblocks < 1) out_nblocks = 1;
+    if (in_nblocks > SLB_MAX_PEERS || out_nblocks > SLB_MAX_PEERS || nmarch % in_nblocks != 0 || nmarch % out_nblocks != 0)
+        return fail(SLB_E_ARG, "slb_sweep_pair: the block counts (%d in, %d out) must divide extent %lld and not exceed %d", in_nblocks,
+                    out_nblocks, (long long)nmarch, SLB_MAX_PEERS);
+    // strides of the plain layout (gs), of an input block (is) and of an output block (os): a block is
+    // the sub-array with extent[dimB] / nblocks along dimB, stored contiguously
+    int64_t gs[SLB_MAX_DIMS], is[SLB_MAX_DIMS], os[SLB_MAX_DIMS], lsstr[SLB_MAX_DIMS];
+    int64_t run = 1, irun = 1, orun = 1, lsrun = 1;
     for (int q = 0; q < nd; ++q) {
         gs[q] = run;
+        is[q] = irun;
+        os[q] = orun;
         run *= g->ext[q];
+        irun *= (q == dimB ? g->ext[q] / in_nblocks : g->ext[q]);
+        orun *= (q == dimB ? g->ext[q] / out_nblocks : g->ext[q]);
         lsstr[q] = lsrun;  // index of the plain kernel's line id over the dims other than dimB
         if (q != dimB) lsrun *= g->ext[q];
     }
@@ -795,21 +807,34 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     fa.out = g->back;
     fa.ncross = (int)ncross;
     fa.nmarch = (int)nmarch;
-    fa.sc = gs[dimA];
-    fa.sm = gs[dimB];
+    fa.isc = is[dimA];
+    fa.ism = is[dimB];
+    fa.osc = os[dimA];
+    fa.osm = os[dimB];
+    fa.ikc = (int)(nmarch / in_nblocks);
+    fa.okc = (int)(nmarch / out_nblocks);
+    fa.iblk = g->numel / in_nblocks;
+    if (first_block < 0 || first_block >= out_nblocks) return fail(SLB_E_ARG, "slb_sweep_pair: first_block out of range");
+    fa.march0 = first_block * fa.okc;
+    for (int q = 0; q < out_nblocks; ++q) {
+        fa.oblk[q] = out_bases ? out_bases[q] : g->back + (int64_t)q * (g->numel / out_nblocks);
+        if (!fa.oblk[q]) return fail(SLB_E_ARG, "slb_sweep_pair: out_block_bases[%d] is NULL", q);
+    }
     fa.elo = fa.ehi = 1;
     int npass = 0;
     for (int q = 0; q < nd; ++q) {
         if (q == dimA || q == dimB) continue;
         if (npass == 0) {
             fa.elo = (unsigned)g->ext[q];
-            fa.slo = gs[q];
+            fa.islo = is[q];
+            fa.oslo = os[q];
             fa.aAlo = astrA[q];
             fa.aBlo = astrB[q];
             fa.lslo = lsstr[q];
         } else {
             fa.ehi = (unsigned)g->ext[q];
-            fa.shi = gs[q];
+            fa.ishi = is[q];
+            fa.oshi = os[q];
             fa.aAhi = astrA[q];
             fa.aBhi = astrB[q];
             fa.lshi = lsstr[q];
@@ -859,13 +884,15 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     fa.full = full;
     fa.ntile_c = (int)((ncross + ta - 1) / ta);
     // 16-byte fetches (pairs of doubles along the contiguous index) when everything is 16-byte aligned
-    const bool aligned = ((uintptr_t)g->front % 16 == 0) && ((uintptr_t)g->back % 16 == 0);
+    bool aligned = ((uintptr_t)g->front % 16 == 0);
+    for (int q = 0; q < out_nblocks; ++q) aligned = aligned && ((uintptr_t)fa.oblk[q] % 16 == 0);
     auto even = [](long long v) { return (v & 1) == 0; };
+    const bool even_strides = even(fa.ism) && even(fa.osm) && even(fa.iblk) && (fa.ehi == 1 || (even(fa.ishi) && even(fa.oshi)));
     if (cc) {
-        fa.w16 = aligned && even(ncross) && even(fa.sm) && even(fa.slo) && even(fa.shi) && fa.sc == 1;
+        fa.w16 = aligned && even(ncross) && even_strides && even(fa.islo) && even(fa.oslo) && fa.isc == 1 && fa.osc == 1;
     } else {
         fa.w16 = gg > 1;
-        if (fa.w16 && !(aligned && fa.slo == 1 && even(fa.elo) && even(fa.sc) && even(fa.sm) && (fa.ehi == 1 || even(fa.shi))))
+        if (fa.w16 && !(aligned && fa.islo == 1 && even(fa.elo) && even(fa.isc) && even_strides))
             return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: buffers are not 16-byte aligned");
     }
     // every thread fetches at most two pairs (four doubles) per march row: staged rows <= 2 * ta
@@ -908,7 +935,25 @@ extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, cons
     if (lrc < 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: no fused kernel for order %d, tile width %d", P1 - 1, gg);
     if (lrc != 0) return fail(SLB_E_CUDA, "slb_sweep_pair: launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
     c->launches++;
+    if (out_bases) return SLB_OK;  // the result left this grid (slb_sweep_peer's convention): roles unchanged
     return slb_grid_swap(g);
+}
+
+extern "C" int slb_sweep_pair(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
+                              const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
+                              int64_t alenB, const int64_t* astrB, double scaleB, int on_device, int flags)
+{
+    return sweep_pair_impl(g, dimA, itA, alphaA, alenA, astrA, scaleA, dimB, itB, alphaB, alenB, astrB, scaleB, on_device, flags, 1, 1,
+                           nullptr, 0);
+}
+
+extern "C" int slb_sweep_pair_ex(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
+                                 const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
+                                 int64_t alenB, const int64_t* astrB, double scaleB, int on_device, int flags, int in_nblocks,
+                                 int out_nblocks, double* const* out_block_bases, int first_block)
+{
+    return sweep_pair_impl(g, dimA, itA, alphaA, alenA, astrA, scaleA, dimB, itB, alphaB, alenB, astrB, scaleB, on_device, flags,
+                           in_nblocks, out_nblocks, out_block_bases, first_block);
 }
 
 extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)

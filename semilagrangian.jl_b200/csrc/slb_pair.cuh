@@ -46,9 +46,20 @@ struct FusedArgs {
     const double* in;
     double* out;
     int ncross, nmarch;          // extents of the cross (sweep A) and march (sweep B) dims
-    long long sc, sm;            // their element strides
     unsigned elo, ehi;           // extents of the (up to two) passive index groups
-    long long slo, shi;          // their element strides
+    // element strides of (cross, march, passive lo, passive hi) on the input and on the output side.
+    // Either side may be BLOCK-MAJOR along the march dim (multi-GPU re-shard fused into the pass,
+    // SURVEY.md 8e): march index b lives in block b / kc at position b % kc; input blocks are
+    // iblk elements apart, output block q starts at oblk[q] (this GPU's HBM or a peer's, mapped
+    // through CUDA IPC).  kc == nmarch: plain layout.
+    long long isc, ism, islo, ishi;
+    long long osc, osm, oslo, oshi;
+    int ikc, okc;
+    long long iblk;
+    int march0;                  // march index of the first input row (a multiple of okc): the line is
+                                 // periodic, so the march may start anywhere -- ranks start at different
+                                 // blocks so that their peer stores hit different destinations at any time
+    double* oblk[SLB_MAX_PEERS];
     int g, ta;                   // passive points / cross outputs (even) per tile; blockDim = g * ta / 2
     int ntile_c;                 // tiles along the cross dim
     int full;                    // 1: a tile is the whole periodic cross line
@@ -165,7 +176,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     const long long Pc = P < np ? P : np - 1;  // idle threads mimic a valid point (they never store)
     const int ac = (a0 + a < nc_) ? a0 + a : nc_ - 1;
     const unsigned plo = (unsigned)(Pc % fa.elo), phi = (unsigned)(Pc / fa.elo);
-    const long long pbase = (long long)plo * fa.slo + (long long)phi * fa.shi;
+    const long long obase = (long long)plo * fa.oslo + (long long)phi * fa.oshi;
 
     // ---- shifts and weights of this thread's passive point: sweep A (cross), sweep B (march) ----
     double w1[P1], w2[P1];
@@ -222,9 +233,18 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     const int sread = CC ? p * fa.nrows_max + roff : roff * g + p;
 
     const int nsteps = nm + P1 - 1;
-    const long long smel = fa.sm, scel = fa.sc;
-    int iout = s0B == 0 ? 0 : nm - s0B;  // march index of the outputs emitted at step P1-1
-    double* const po0 = fa.out + pbase + (long long)ac * scel;
+    const long long smel = fa.ism, scel = fa.isc, osmel = fa.osm, oscel = fa.osc;
+    // march index of the outputs emitted at step P1-1, as (block, position in block)
+    const int okc = fa.okc;
+    int oq, ol;
+    {
+        int iout = fa.march0 + nm - s0B;
+        iout -= iout >= nm ? nm : 0;
+        oq = iout / okc;
+        ol = iout - oq * okc;
+    }
+    const long long othr = obase + (long long)ac * oscel;
+    double* pob = fa.oblk[oq] + othr;
     double winA[P1], winB[P1];           // last order+1 values of T for the two cross outputs
 #pragma unroll
     for (int j = 0; j < P1; ++j) winA[j] = winB[j] = 0.0;
@@ -233,7 +253,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     auto emit = [&](double accA, double accB) {
         lsumA += accA;
         lsumB += accB;
-        double* po = po0 + (long long)iout * smel;
+        double* po = pob + (long long)ol * osmel;
         if (CC && W16) {  // neighbouring outputs are neighbours in memory, 16-byte aligned
             if (act1)
                 fused_st_v2(po, accA, accB);
@@ -241,9 +261,13 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
                 __stcs(po, accA);
         } else {
             if (act0) __stcs(po, accA);
-            if (act1) __stcs(po + scel, accB);
+            if (act1) __stcs(po + oscel, accB);
         }
-        iout = iout + 1 == nm ? 0 : iout + 1;
+        if (++ol == okc) {  // next output block (plain layout: wrap around the periodic line)
+            ol = 0;
+            oq = (oq + 1) * okc >= nm ? 0 : oq + 1;
+            pob = fa.oblk[oq] + othr;
+        }
     };
 
     if (!direct) {
@@ -284,14 +308,16 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
             const long long Pq = Pe < np ? Pe : np - 1;
             const int rc = (rowbase + j) % nc_;
             gsrc[s] = reinterpret_cast<const char*>(fa.in) +
-                      8 * ((long long)(Pq % fa.elo) * fa.slo + (long long)(Pq / fa.elo) * fa.shi + (long long)rc * scel);
+                      8 * ((long long)(Pq % fa.elo) * fa.islo + (long long)(Pq / fa.elo) * fa.ishi + (long long)rc * scel);
             sdst[s] = sbase + 8u * (unsigned)(CC ? pe * fa.nrows_max + j : j * g + pe);
         }
         const unsigned row_b = 8u * (unsigned)row_elems, ring_b = row_b * R * D;
         // block-uniform bookkeeping of the fetch pipeline (kept in the uniform datapath)
-        int b_iss = 0, k_iss = 0;   // march index / step number of the next row to fetch
-        long long boff = 0;         // b_iss * smel, in bytes
-        const long long smb = 8 * smel;
+        int b_iss = fa.march0, k_iss = 0;   // march index / step number of the next row to fetch
+        const int ikc = fa.ikc;
+        int il = fa.march0 % ikc;           // its position inside its input block
+        const long long smb = 8 * smel, blkjump = 8 * (fa.iblk - (long long)ikc * smel);
+        long long boff = 8 * ((long long)(fa.march0 / ikc) * fa.iblk + (long long)il * smel);  // its byte offset
         unsigned off_iss = 0;       // byte offset of that row's slot in the ring
         auto issue_stage = [&]() {
 #pragma unroll
@@ -307,6 +333,10 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
                         }
                     }
                     boff += smb;
+                    if (++il == ikc) {  // next input block
+                        il = 0;
+                        boff += blkjump;
+                    }
                     if (++b_iss == nm) {
                         b_iss = 0;
                         boff = 0;
@@ -372,14 +402,14 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     } else {
         // shifts inside the tile are too far apart to stage a common row range: every thread reads
         // its own stencil inputs from global memory (rare; correct, slower)
-        const double* pdir = fa.in + pbase;
-        int b = 0;
+        const double* pdir = fa.in + (long long)plo * fa.islo + (long long)phi * fa.ishi;
+        int b = fa.march0;
         for (int k0 = 0; k0 < nsteps; k0 += P1) {
 #pragma unroll
             for (int r = 0; r < P1; ++r) {
                 const int k = k0 + r;
                 if (k < nsteps) {
-                    const double* src = pdir + (long long)b * smel;
+                    const double* src = pdir + (long long)(b / fa.ikc) * fa.iblk + (long long)(b % fa.ikc) * smel;
                     b = b + 1 == nm ? 0 : b + 1;
                     int rc = ac + s0A;
                     rc -= rc >= nc_ ? nc_ : 0;

@@ -47,6 +47,9 @@ SIGNATURES = [
     ("slb_sweep_peer", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int, C.c_int, c_void_pp]),
     ("slb_sweep_pair", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double,
                                  C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int]),
+    ("slb_sweep_pair_ex", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, c_void_pp, C.c_int]),
     ("slb_ipc_get_handle", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("slb_ipc_open_handle", C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     ("slb_ipc_close_handle", C.c_int, [C.c_void_p, C.c_void_p]),

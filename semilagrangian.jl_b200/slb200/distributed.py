@@ -221,6 +221,12 @@ class ShardedAdvectionData:
         self.linesum = torch.empty(self.nloc // min(n3, n4), dtype=torch.float64, device=self.device)
         self.linesum_dim = None
         self.use_linesum = True
+        import os as _os
+
+        self.fuse_pairs = _os.environ.get("SLB_FUSE", "1") != "0"   # v1v2 / x1x2 in one pass each (slb_sweep_pair_ex)
+        self._pending = None
+        self.n_fused = 0
+        self.rotate_march = _os.environ.get("SLB_ROTATE", "1") != "0"  # ranks start their marches at different blocks
         self.has_field = False
         self.n_exchanges = 0
         self.n_barriers = 0
@@ -274,6 +280,7 @@ class ShardedAdvectionData:
             self._compute_field()
 
     def _compute_field(self):
+        self.flush()
         if self.layout != LAYOUT_B:
             raise RuntimeError("the charge density is a local reduction in layout B only")
         adv = self.adv
@@ -316,42 +323,132 @@ class ShardedAdvectionData:
         adv = self.adv
         return adv.getst(self.state_gen + 1 if self.state_gen < adv.nbstates else 1).perm[0] - 1
 
-    def _advection(self):
-        adv, st = self.adv, self.getst()
-        d = st.perm[0] - 1
-        dt = self.getcur_t()
+    def _stage_table(self, d, dt):
+        """alpha table of a stage along dim d for this rank's slab: (device pointer, length, strides, scale)"""
+        adv = self.adv
         n1, n2, n3, n4 = self.gshape
         c2, c4 = n2 // self.P, n4 // self.P
-        need = LAYOUT_A if d < 2 else LAYOUT_B
-        interp = adv.t_interp[d]
-        L = _lib.lib()
-        multi = self.P > 1
-        mode, bdim = _lib.SLB_RESHARD_NONE, 0
-        if need != self.layout:
-            # only B -> A is ever pending here: A -> B is completed by the x2 sweep itself
-            if not (need == LAYOUT_A and d == 0):
-                raise NotImplementedError("unsupported state order for the fused re-shard (needs x1 first after v-sweeps)")
-            if multi:
-                mode, bdim = _lib.SLB_RESHARD_IN_BLOCKED, 1   # cur holds the blocks received from every rank
-            self.layout = LAYOUT_A
         strides = [0, 0, 0, 0]
         if d >= 2:  # velocity sweep: alpha = (dt/dv_d) * E_{d-2}[x1, x2l + r*c2]   (src/poisson.jl:178-189)
-            if d == 2:
-                self._compute_field()
             if not self.has_field:
                 raise RuntimeError("velocity state before any field solve")
             strides[0], strides[1] = 1, n1
             tab = self.E[d - 2].data_ptr() + 8 * self.rank * c2 * n1
-            tlen = c2 * n1
-            scale = dt / adv.t_mesh[d].step
-        else:       # space sweep: alpha = (-dt/dx_d) * v_{d+2}   (src/poisson.jl:191-203)
-            src = d + 2
-            strides[src] = 1
-            off = self.rank * c4 if src == 3 else 0
-            tab = self.points[src].data_ptr() + 8 * off
-            tlen = c4 if src == 3 else self.gshape[src]
-            scale = -dt / adv.t_mesh[d].step
+            return tab, c2 * n1, strides, dt / adv.t_mesh[d].step
+        src = d + 2  # space sweep: alpha = (-dt/dx_d) * v_{d+2}   (src/poisson.jl:191-203)
+        strides[src] = 1
+        off = self.rank * c4 if src == 3 else 0
+        tab = self.points[src].data_ptr() + 8 * off
+        return tab, (c4 if src == 3 else self.gshape[src]), strides, -dt / adv.t_mesh[d].step
+
+    def _pairable(self, dA, dB):
+        from .advection import FUSED_ORDERS
+        from .interp import HERMITE, LAGRANGE
+
+        if not self.fuse_pairs or dB != dA + 1 or dA not in (0, 2):
+            return False
+        itA, itB = self.adv.t_interp[dA], self.adv.t_interp[dB]
+        ok = lambda it: it.kind in (LAGRANGE, HERMITE) and it.tabfct.shape[1] <= 14
+        return ok(itA) and ok(itB) and itA.order == itB.order and itA.order in FUSED_ORDERS
+
+    def flush(self):
+        """run a stage that was held back for pair fusion (no-op otherwise)"""
+        pend, self._pending = self._pending, None
+        if pend is not None:
+            self._single(*pend)
+
+    def _advection(self):
+        st = self.getst()
+        d = st.perm[0] - 1
+        dt = self.getcur_t()
         nxt = self._next_dim()
+        if self._pending is not None:
+            dA, dtA, _ = self._pending
+            if dA + 1 == d:
+                self._pending = None
+                self._pair(dA, dtA, d, dt, nxt)
+                return self.nextstate()
+            self.flush()
+        if d == 2:
+            self._compute_field()
+        if self.state_gen < self.adv.nbstates and self._pairable(d, nxt):
+            self._pending = (d, dt, nxt)  # held back: the next call runs both stages in one pass
+            return self.nextstate()
+        self._single(d, dt, nxt)
+        return self.nextstate()
+
+    def _enter_layout(self, d):
+        """layout bookkeeping before a pass whose first sweep runs along dim d; returns True when the
+        current buffer holds the blocks of a B -> A exchange (block-major along x2)"""
+        need = LAYOUT_A if d < 2 else LAYOUT_B
+        blocked_in = False
+        if need != self.layout:
+            # only B -> A is ever pending here: A -> B is completed by the x2 sweep itself
+            if not (need == LAYOUT_A and d == 0):
+                raise NotImplementedError("unsupported state order for the fused re-shard (needs x1 first after v-sweeps)")
+            blocked_in = self.P > 1
+            self.layout = LAYOUT_A
+        return blocked_in
+
+    def _pair(self, dA, dtA, dB, dtB, nxt):
+        """stages dA, dB = dA + 1 in ONE pass over HBM (slb_sweep_pair_ex), with the re-shard that
+        follows dB fused into its stores"""
+        adv = self.adv
+        L = _lib.lib()
+        multi = self.P > 1
+        blocked_in = self._enter_layout(dA)
+        tA, lA, sA, scA = self._stage_table(dA, dtA)
+        tB, lB, sB, scB = self._stage_table(dB, dtB)
+        to_A = self.layout == LAYOUT_B and nxt < 2
+        to_B = self.layout == LAYOUT_A and nxt >= 2
+        if (to_A and dB != 3) or (to_B and dB != 1):
+            raise NotImplementedError("unsupported state order for the fused re-shard")
+        reshard = multi and (to_A or to_B)
+        self.linesum_dim = None
+        want_ls = self.use_linesum and dB == 3 and nxt == 2
+        out = (self.cur + 1) % self.nbuf
+        g = self._grid(self.layout, out)
+        hA = adv.t_interp[dA].handle(self.ctx, self.gshape[dA])
+        hB = adv.t_interp[dB].handle(self.ctx, self.gshape[dB])
+        if want_ls:
+            _lib.check(L.slb_grid_set_linesum(g, C.c_void_p(self.linesum.data_ptr())))
+        try:
+            args = (g, dA, hA, C.c_void_p(tA), lA, _lib.i64(sA), float(scA), dB, hB, C.c_void_p(tB), lB, _lib.i64(sB), float(scB), 1,
+                    int(self.flags), self.P if blocked_in else 1)
+            if reshard and self.exchange == "p2p":
+                if self.since_barrier > 1:
+                    self._barrier()  # every rank is done with the buffer we are about to store into
+                blk = self.nloc // self.P
+                bases = (C.c_void_p * self.P)(*[self.peer[q][out] + 8 * self.rank * blk for q in range(self.P)])
+                _lib.check(L.slb_sweep_pair_ex(*args, self.P, bases, (self.rank + 1) % self.P if self.rotate_march else 0))
+                self._barrier()      # all blocks have landed everywhere
+                self.n_exchanges += 1
+                self.cur = out
+            else:
+                _lib.check(L.slb_sweep_pair_ex(*args, self.P if reshard else 1, None, 0))
+                _lib.check(L.slb_grid_swap(g))  # keep the handle's orientation; the driver tracks `cur`
+                self.cur = out
+                self.since_barrier += 1
+                if reshard:
+                    self._exchange_nccl()
+        finally:
+            if want_ls:
+                _lib.check(L.slb_grid_set_linesum(g, None))
+        if want_ls:
+            self.linesum_dim = dB
+        if to_B:
+            self.layout = LAYOUT_B
+        self.n_fused += 1
+
+    def _single(self, d, dt, nxt):
+        adv = self.adv
+        interp = adv.t_interp[d]
+        L = _lib.lib()
+        multi = self.P > 1
+        mode, bdim = _lib.SLB_RESHARD_NONE, 0
+        if self._enter_layout(d):
+            mode, bdim = _lib.SLB_RESHARD_IN_BLOCKED, 1   # cur holds the blocks received from every rank
+        tab, tlen, strides, scale = self._stage_table(d, dt)
         # layout change AFTER this sweep: v2 followed by x1 (B -> A), x2 followed by a v-sweep (A -> B)
         to_A = self.layout == LAYOUT_B and nxt < 2
         to_B = self.layout == LAYOUT_A and nxt >= 2
@@ -396,19 +493,20 @@ class ShardedAdvectionData:
                 _lib.check(L.slb_grid_set_linesum(g, None))
         if want_ls:
             self.linesum_dim = d
-        if to_A:
-            pass  # layout flips when the x1 sweep consumes the blocks (keeps compute_field honest)
         if to_B:
             self.layout = LAYOUT_B
-        return self.nextstate()
 
     # ---- data access ----------------------------------------------------------------------
     def upload_local(self, host_flat):
         """copy this rank's slab (current layout, flat Fortran order, e.g. pinned memory) to the device"""
+        self._pending = None
         _lib.check(_lib.lib().slb_memcpy_h2d(self.ctx.h, C.c_void_p(self.ptr[self.cur]), host_flat.ctypes.data_as(C.c_void_p), self.nloc * 8))
         self.linesum_dim = None
 
     def download_local(self, host_flat):
+        if self._pending is not None:
+            with self.torch.cuda.stream(self.stream):
+                self.flush()
         _lib.check(_lib.lib().slb_memcpy_d2h(self.ctx.h, host_flat.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr[self.cur]), self.nloc * 8))
         self.ctx.sync()
 

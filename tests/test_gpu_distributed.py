@@ -62,6 +62,54 @@ def test_in_blocked_reads_block_major_input(nblocks):
     assert relerr(out2, ref) <= 1e-12
 
 
+def _pair_ex(flat_in, shape, dimA, dimB, interp, tabA, strA, tabB, strB, in_nblocks, out_nblocks, flags=0, first_block=0):
+    from slb200 import _lib
+
+    ctx = _lib.default_context()
+    g = DeviceGrid(np.zeros(shape, order="F"))
+    flat = np.ascontiguousarray(flat_in.reshape(-1, order="F"))
+    _lib.check(_lib.lib().slb_grid_upload(g.h, flat.ctypes.data_as(C.c_void_p)))
+    tabA, tabB = np.ascontiguousarray(tabA, dtype=np.float64), np.ascontiguousarray(tabB, dtype=np.float64)
+    hA, hB = interp.handle(ctx, shape[dimA]), interp.handle(ctx, shape[dimB])
+    _lib.check(_lib.lib().slb_sweep_pair_ex(
+        g.h, dimA, hA, tabA.ctypes.data_as(C.c_void_p), tabA.size, _lib.i64(strA), 1.0,
+        dimB, hB, tabB.ctypes.data_as(C.c_void_p), tabB.size, _lib.i64(strB), 1.0, 0, flags, in_nblocks, out_nblocks, None, first_block))
+    out = g.get()
+    g.close()
+    return out
+
+
+@pytest.mark.parametrize("in_nb,out_nb", [(1, 2), (1, 8), (4, 1), (2, 2), (8, 4)])
+@pytest.mark.parametrize("case", ["v1v2", "x1x2"])
+def test_pair_ex_block_major_input_and_output(case, in_nb, out_nb):
+    """The fused pair with the re-shard maps: block-major input / output along the march dim equal
+    the numpy layout algebra applied to the plain fused result (bit for bit)."""
+    from slb200 import distributed as D
+
+    rng = np.random.default_rng(3)
+    if case == "v1v2":   # layout B slab: sweeps along dims 2, 3; blocks along v2 (B -> A exchange)
+        shape, dA, dB = (32, 6, 20, 16), 2, 3
+        tA, sA = rng.uniform(-2, 2, 32 * 6), [1, 32, 0, 0]
+        tB, sB = rng.uniform(-2, 2, 32 * 6), [1, 32, 0, 0]
+    else:                # layout A slab: sweeps along dims 0, 1; blocks along x2 (A -> B exchange)
+        shape, dA, dB = (48, 16, 5, 3), 0, 1
+        tA, sA = rng.uniform(-6, 6, 5), [0, 0, 1, 0]
+        tB, sB = rng.uniform(-6, 6, 3), [0, 0, 0, 1]
+    f = np.asfortranarray(rng.random(shape))
+    interp, _ = make_pair("lagrange", 7, shape[dA])
+    for flags in (0, 1):
+        plain = _pair_ex(f, shape, dA, dB, interp, tA, sA, tB, sB, 1, 1, flags)
+        fin = D.to_block_major(f, dB, in_nb) if in_nb > 1 else f
+        out = _pair_ex(fin, shape, dA, dB, interp, tA, sA, tB, sB, in_nb, out_nb, flags)
+        got = D.from_block_major(out.reshape(-1, order="F"), shape, dB, out_nb) if out_nb > 1 else out
+        assert np.array_equal(got, plain), (case, in_nb, out_nb, flags)
+        if out_nb > 1:
+            # rotated march start (what rank r of P uses): same result
+            out = _pair_ex(fin, shape, dA, dB, interp, tA, sA, tB, sB, in_nb, out_nb, flags, first_block=out_nb - 1)
+            got = D.from_block_major(out.reshape(-1, order="F"), shape, dB, out_nb)
+            assert np.array_equal(got, plain), (case, in_nb, out_nb, flags, "rotated")
+
+
 def test_sharded_driver_single_rank_matches_plain_driver():
     """P = 1: the sharded driver must reproduce the plain AdvectionData history."""
     import os

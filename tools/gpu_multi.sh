@@ -1,0 +1,20 @@
+#!/bin/bash
+# Multi-GPU session: sharded parity (vs the single-GPU driver) and the scaling bench.
+# gpurun --gpus N --timeout 900 -- 'bash tools/gpu_multi.sh <tag> <N> [check] [bench] [nccl]'
+TAG=$1; N=$2; shift 2
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+for w in "$@"; do
+  case $w in
+    tests) timeout 600 python -m pytest tests/test_gpu_distributed.py tests/test_gpu_pair.py -x -q 2>&1 | tail -3 ;;
+    check)
+      timeout 300 $TR tools/check_sharded.py 32 p2p 2>&1 | grep -E "rank|Error|error" | tee $OUT/check_p2p.log
+      timeout 300 $TR tools/check_sharded.py 32 nccl 2>&1 | grep -E "rank|Error|error" | tee $OUT/check_nccl.log ;;
+    bench)
+      timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 2>&1 | grep -E "^\{|Error|error" | tee $OUT/bench_${N}gpu_p2p.json ;;
+    nccl)
+      timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 --exchange nccl 2>&1 | grep -E "^\{|Error|error" | tee $OUT/bench_${N}gpu_nccl.json ;;
+    unfused)
+      SLB_FUSE=0 timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 2>&1 | grep -E "^\{|Error|error" | tee $OUT/bench_${N}gpu_p2p_unfused.json ;;
+  esac
+done
