@@ -32,6 +32,8 @@ import numpy as np
 METRIC = "Gcell-updates/s per FP64 advection sweep (2D2V 128^4)"
 UNIT = "Gcell/s"
 BYTES_PER_CELL = 16.0  # read f once (8 B) + write once (8 B)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep_fused launch (ncu --set full), by grid size
+NCU_TRAFFIC = {128: 4.349e9}
 
 
 def read_peaks():
@@ -170,7 +172,8 @@ def run_reference(args):
 
 def workload_config(args):
     return {
-        "workload": f"2D2V {args.size}^4 Vlasov-Poisson Strang step, {args.interp} order {args.order}: 6 sweeps + 2 charge/Poisson solves",
+        "workload": f"2D2V {args.size}^4 Vlasov-Poisson Strang step, {args.interp} order {args.order}: 6 sweeps + 2 charge/Poisson solves "
+                    "(value = 6 * n^4 cell-updates per step / device time per step)",
         "grid": [args.size] * 4, "interp": args.interp, "order": args.order, "dt": 0.1,
         "cache": "inputs larger than L2 (f = %.2f GB, ping-pong buffer of the same size)" % (args.size**4 * 8 / 1e9),
     }
@@ -237,6 +240,7 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.3)
     launches0 = ctx.launch_count()
+    nfused0 = advd.n_fused
     ctx.sync()
     ctx.timer_start()
     i = 0
@@ -251,6 +255,7 @@ def run_ours(args):
             ctx.record(evs[i])
     ms_total = ctx.timer_stop()
     launches = ctx.launch_count() - launches0
+    advd_nfused = advd.n_fused - nfused0
     clocks = sampler.stop()
     value = cells_per_step * args.steps / (ms_total * 1e-3) / 1e9
     # per-stage durations (include the field solve for the v1 stages)
@@ -259,55 +264,108 @@ def run_ours(args):
     for d, ms in zip(stage_dims, stage_ms):
         per_dim.setdefault(d, []).append(ms)
 
-    # ---- roofline of the dominant kernel: the strided sweep (5 of the 6 stages) ---------
-    # timed alone with events, same stream, inside this run (no profiler): v2 sweep = pure kernel
+    # ---- roofline of the dominant kernel: the pair-fused pass (all 6 sweeps of a step run as 3 such
+    # launches).  Timed alone with events, same stream, inside this run (no profiler). -------------
     peak, peak_src = read_peaks()
     reps = 5
     e0, e1 = ctx.event(), ctx.event()
     kern = {}
     table = np.linspace(-0.4, 0.4, n * n)  # |alpha| < 0.5 like (dt/dv) E
     vtab = adv.t_mesh[2].points
-    for name, dim, tab, strides, scale in (
-        ("k_sweep_strided/v2", 3, table, [1, n, 0, 0], 1.0),
-        ("k_sweep_strided/v1", 2, table, [1, n, 0, 0], 1.0),
-        ("k_sweep_strided/x2", 1, vtab, [0, 0, 0, 1], -0.1 / adv.t_mesh[1].step),
-        ("k_sweep_contig/x1", 0, vtab, [0, 0, 1, 0], -0.1 / adv.t_mesh[0].step),
-    ):
-        tdev = ctx.to_device(tab)
-        S.sweep(advd, dim, adv.t_interp[dim], (tdev, len(tab)), strides, scale, True)
+    tdev_E = ctx.to_device(table)
+    tdev_v = ctx.to_device(vtab)
+    it = adv.t_interp[0]
+    sx = -0.1 / adv.t_mesh[0].step
+
+    def timed(fn):
+        fn()
         ctx.sync()
         ctx.record(e0)
         for _ in range(reps):
-            S.sweep(advd, dim, adv.t_interp[dim], (tdev, len(tab)), strides, scale, True)
+            fn()
         ctx.record(e1)
-        ms = _lib.Context.elapsed_ms(e0, e1) / reps
-        kern[name] = {"ms": ms, "GBps": n**4 * BYTES_PER_CELL / (ms * 1e-3) / 1e9, "Gcell_s": n**4 / (ms * 1e-3) / 1e9}
-        ctx.free(tdev)
-    dom = "k_sweep_strided/v2"
+        return _lib.Context.elapsed_ms(e0, e1) / reps
+
+    def stage(dim, tab, ln, strides, scale):
+        return (dim, it, (tab, ln), strides, scale, True, 0, False)
+
+    vE = lambda d: stage(d, tdev_E, n * n, [1, n, 0, 0], 1.0)
+    pairs = (("k_sweep_fused/v1v2", vE(2), vE(3)),
+             ("k_sweep_fused/x1x2", stage(0, tdev_v, n, [0, 0, 1, 0], sx), stage(1, tdev_v, n, [0, 0, 0, 1], sx)))
+    for name, sa, sb in pairs:
+        ms = timed(lambda: S.sweep_pair(advd, sa, sb))
+        kern[name] = {"ms": ms, "GBps": n**4 * BYTES_PER_CELL / (ms * 1e-3) / 1e9, "Gcell_s": 2 * n**4 / (ms * 1e-3) / 1e9,
+                      "cell_updates_per_cell": 2}
+    for name, sg in (("k_sweep_strided/v2", vE(3)), ("k_sweep_strided/v1", vE(2)),
+                     ("k_sweep_strided/x2", stage(1, tdev_v, n, [0, 0, 0, 1], sx)), ("k_sweep_contig/x1", stage(0, tdev_v, n, [0, 0, 1, 0], sx))):
+        ms = timed(lambda: S.sweep(advd, *sg[:6]))
+        kern[name] = {"ms": ms, "GBps": n**4 * BYTES_PER_CELL / (ms * 1e-3) / 1e9, "Gcell_s": n**4 / (ms * 1e-3) / 1e9,
+                      "cell_updates_per_cell": 1}
+    ctx.free(tdev_E)
+    ctx.free(tdev_v)
+    dom = "k_sweep_fused/v1v2"
     ach = kern[dom]["GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "bytes_per_launch": n**4 * BYTES_PER_CELL,
+                "frac": ach / peak, "traffic": NCU_TRAFFIC.get(n), "traffic_source": "profiles/r1_ncu_full_fused_L7_128.txt (ncu --set full, per launch)",
+                "bytes_per_launch": n**4 * BYTES_PER_CELL,
+                "note": "one launch reads f once and writes it once (16 B per cell) and performs TWO sweeps (2 cell-updates per cell); "
+                        "in SURVEY.md 8(d)'s per-sweep unit (16 B per cell-update) that is twice the single-sweep roofline rate",
                 "ms_per_launch": kern[dom]["ms"], "all_kernels": kern}
 
-    # ---- e2e: host buffers in, host buffers out, every step ------------------------------
-    # restore a physical state first (the roofline sweeps above used synthetic shifts)
+    # ---- e2e: host buffers in, host buffers out, every step --------------------------------------
+    # Two independent grids in flight on two contexts (streams): the upload of one overlaps the
+    # read-back of the other (PCIe is full duplex); every step still uploads its own input from
+    # pinned host memory and reads back its result (f and the electric energy).
     fill_product(host, vecs)
-    e2e_steps = max(1, min(args.steps, 5))
-    advd.upload(host)
+    e2e_steps = max(4, min(args.steps, 8)) // 2 * 2
+    nbytes = n**4 * 8
+    ctx2 = _lib.Context(ctx.device)
+    host2, hptr2 = _lib.pinned_empty((n,) * 4)
+    np.copyto(host2, host)
+    adv2, _ = vp2d2v_setup(S, n, args.order, args.interp, ctx=ctx2)
+    advd2 = S.AdvectionData(adv2, host2, S.getpoissonvar(adv2, ctx=ctx2), ctx=ctx2)
+    lanes = ((advd, host, ctx), (advd2, host2, ctx2))
+    for a_, _h, _c in lanes:
+        a_.state_gen = 1
+
+    def lane_issue(a_, h_, c_):
+        _lib.check(L.slb_grid_upload(a_.grid, h_.ctypes.data_as(_lib.C.c_void_p)))        # H2D of this step's input f (async)
+        a_._linesum_dim = None
+        while S.advection(a_):
+            pass
+        _lib.check(L.slb_memcpy_d2h(c_.h, h_.ctypes.data_as(_lib.C.c_void_p), L.slb_grid_front(a_.grid), nbytes))  # D2H of f (async)
+
+    for a_, h_, c_ in lanes:   # warm-up of the second lane
+        lane_issue(a_, h_, c_)
+    ctx.sync()
+    ctx2.sync()
+    t0 = time.perf_counter()
+    ee = 0.0
+    done = 0
+    for a_, h_, c_ in lanes:   # fill the pipeline: one step in flight per lane
+        lane_issue(a_, h_, c_)
+    while done < e2e_steps:
+        for a_, h_, c_ in lanes:
+            ee = S.compute_ee(a_)          # D2H scalar; waits for this lane's step (and its read-back of f)
+            done += 1
+            if done + 1 < e2e_steps:       # the other lane still has a step in flight: issue this lane's next one
+                lane_issue(a_, h_, c_)
+    ctx.sync()
+    ctx2.sync()
+    wall_e2e = time.perf_counter() - t0
+    e2e_val = cells_per_step * e2e_steps / wall_e2e / 1e9
+    # serial variant: one grid, upload -> step -> read back, nothing overlapped
+    ser_steps = max(1, min(args.steps, 3))
     advd.state_gen = 1
     ctx.sync()
     t0 = time.perf_counter()
-    ctx.timer_start()
-    ee = 0.0
-    for _ in range(e2e_steps):
-        _lib.check(L.slb_grid_upload(advd.grid, host.ctypes.data_as(_lib.C.c_void_p)))   # H2D of this step's input f
+    for _ in range(ser_steps):
+        _lib.check(L.slb_grid_upload(advd.grid, host.ctypes.data_as(_lib.C.c_void_p)))
+        advd._linesum_dim = None
         step()
-        ee = S.compute_ee(advd)                                                          # D2H scalar (the step's metric)
-        advd.getdata(out=host)                                                           # D2H of the step's result f
-    ms_e2e = ctx.timer_stop()
-    wall_e2e = time.perf_counter() - t0
-    e2e_val = cells_per_step * e2e_steps / max(ms_e2e * 1e-3, wall_e2e) / 1e9
-    nbytes = n**4 * 8
+        ee = S.compute_ee(advd)
+        advd.getdata(out=host)
+    wall_ser = time.perf_counter() - t0
     # resident variant (how the reference API is normally driven: f stays inside AdvectionData,
     # only the electric energy comes back each step)
     ctx.sync()
@@ -317,18 +375,25 @@ def run_ours(args):
         ee = S.compute_ee(advd)
     ctx.sync()
     wall_res = time.perf_counter() - t0
+    advd2.close()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
-                "steps": e2e_steps, "note": "upload f from pinned host memory, full Strang step, read back ee and f, every step"},
+                "steps": e2e_steps, "note": "every step: upload f from pinned host memory, full Strang step, read back f and ee; two independent "
+                                            "grids in flight on two streams so that one grid's upload overlaps the other's read-back (wall clock)"},
+        "e2e_serial": {"value": cells_per_step * ser_steps / wall_ser / 1e9, "unit": UNIT, "steps": ser_steps,
+                       "note": "one grid: upload, step, read back, nothing overlapped"},
         "e2e_resident": {"value": cells_per_step * e2e_steps / wall_res / 1e9, "unit": UNIT,
                          "note": "f resident in HBM across steps (AdvectionData semantics), ee read back per step; wall clock"},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "stage_ms": {f"dim{d}": float(np.mean(v)) for d, v in sorted(per_dim.items())},
+        "gpu_fused_passes_per_step": advd_nfused / args.steps,
+        "advection_call_ms": {f"dim{d}": float(np.mean(v)) for d, v in sorted(per_dim.items())},
+        "advection_call_note": "device time between successive advection() calls: the first stage of a fused pair is only recorded "
+                               "(dim2 = charge density + Poisson solve), the second runs both sweeps",
         "last_ee": ee,
     }
     if not args.no_cpu:

@@ -68,6 +68,7 @@ def run_distributed(args, B):
     ms_total = float(ms.item())
     launches = sh.ctx.launch_count() - launches0
     nex = sh.n_exchanges - ex0
+    nfused = sh.n_fused - nf0
     clocks = sampler.stop() if rank == 0 else None
     ee = sh.compute_ee()
 
@@ -115,7 +116,7 @@ def run_distributed(args, B):
     if rank == 0:
         peak, peak_src = B.read_peaks()
         value = cells_per_step * args.steps / (ms_total * 1e-3) / 1e9
-        fused = (sh.n_fused - nf0) > 0
+        fused = nfused > 0
         payload = nbytes_local * (world - 1) // world
         hbm_bytes = (3 * 16 + 8 if fused else 6 * 16 + 8) * n**4 / world
         line = {
@@ -129,7 +130,7 @@ def run_distributed(args, B):
             "all_to_all_ms": ms_a2a,
             "all_to_all_GBps_per_gpu": (nbytes_local * (world - 1) / world / (ms_a2a * 1e-3) / 1e9) if ms_a2a else None,
             "exchange_payload_bytes_per_gpu": nbytes_local * (world - 1) // world,
-            "gpu_fused_passes_per_step": (sh.n_fused - nf0) / args.steps,
+            "gpu_fused_passes_per_step": nfused / args.steps,
             "roofline": {"bound": "hbm", "kernel": "whole step per rank: %s" % ("3 fused passes (16 B/cell each) + 1 rho pass (8 B/cell)" if fused else "6 sweeps (16 B/cell) + 1 rho pass (8 B/cell)"),
                          "achieved": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak, "traffic": None,

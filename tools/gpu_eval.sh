@@ -25,7 +25,7 @@ for w in $WHAT; do
       echo "launches rc=$?" ;;
     full)
       # skip the warm-up step's launches; 1 capture each of the strided and contiguous sweep kernels
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 6 -c 6 \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep_fused\|k_charge_partial -s 4 -c 5 \
         -f -o "$OUT/prof_sweep" python tools/prof_step.py --steps 1 > "$OUT/full.log" 2>&1
       echo "full rc=$?" ;;
     bspline)
