@@ -16,6 +16,7 @@
 #include "slb_sweep.cuh"
 #include "slb_pair.cuh"
 #include "slb_bspline.cuh"
+#include "slb_bspfused.cuh"
 #include "slb_field.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -85,6 +86,7 @@ struct slb_interp {
     CoefTab tab;
     double* coef_dev;
     BsplineDev bsp;            // LU factors / circulant symbol on the device (B-spline kinds)
+    BspParamTab* bsptab;       // the same factors laid out as kernel parameters (fused sweep), or NULL
 };
 
 struct slb_poisson {
@@ -96,6 +98,13 @@ struct slb_poisson {
     double* mult[SLB_MAX_DIMS];
     double2 *wa, *wb, *wc;
 };
+
+static long long env_ll(const char* name, long long dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoll(v);
+}
 
 static int ensure_scratch(slb_ctx* c, size_t bytes)
 {
@@ -418,13 +427,23 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
         cudaGetLastError();
         return fail(SLB_E_CUDA, "slb_interp_create: %s", cudaGetErrorString(e));
     }
+    it->bsptab = nullptr;
     if (bs) {
         std::string msg;
-        int rc = bspline_build(kind, order, n, node_vals, &it->bsp, msg);
+        BsplineHost hb;
+        int rc = bspline_build(kind, order, n, node_vals, &it->bsp, msg, &hb);
         if (rc) {
             cudaFree(it->coef_dev);
             delete it;
             return fail(rc, "slb_interp_create: %s", msg.c_str());
+        }
+        if (it->fast && slb_bspfused_supported(hb.h, hb.n)) {
+            it->bsptab = new BspParamTab();
+            if (!slb_bspfused_fill(it->bsptab, hb.h, hb.n, hb.N, hb.L.data(), hb.U.data(), hb.invd.data(), hb.Ri.data(), hb.G.data(),
+                                   hb.Sinv.data())) {
+                delete it->bsptab;
+                it->bsptab = nullptr;
+            }
         }
     }
     *out = it;
@@ -437,6 +456,7 @@ extern "C" void slb_interp_destroy(slb_interp* it)
     cudaStreamSynchronize(it->ctx->stream);
     cudaFree(it->coef_dev);
     bspline_free(&it->bsp);
+    delete it->bsptab;
     delete it;
 }
 
@@ -625,6 +645,31 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
     int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, on_device, &am);
     if (rc) return rc;
     const double* src = g->front;
+    if (bs && it->bsptab && !(flags & SLB_SWEEP_EXACT) && !(g->linesum && dim == 0) && !(omp && dim == 0) && !(imp && dim != 0) &&
+        env_ll("SLB_BSPLINE_FUSED", 1) != 0) {
+        // pre-solve + stencil in one pass over HBM (slb_bspfused.cuh): front -> back, then swap
+        BspFusedArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = g->front;
+        a.out = g->back;
+        a.inner = v.inner;
+        a.nlines = v.inner * v.outer;
+        a.n = v.n;
+        a.nc = it->nc;
+        a.am = am;
+        if (omp)
+            a.om = *omp;
+        else {
+            a.om.kc = v.n;
+            a.om.bstride = (long long)v.n * v.inner;
+        }
+        if (imp) a.im = *imp;
+        a.linesum = g->linesum;
+        int lrc = slb_bspfused_launch(a, *it->bsptab, it->tab, c->sm_count, c->stream);
+        if (lrc != 0) return fail(lrc < 0 ? SLB_E_UNSUPPORTED : SLB_E_CUDA, "slb_sweep: fused B-spline launch failed (%d)", lrc);
+        c->launches++;
+        return slb_grid_swap(g);
+    }
     if (bs) {
         // c = sol(interp, line) for every line: front -> back -> (stencil) -> front
         rc = bspline_presolve(c->stream, &it->bsp, g->front, g->back, v.inner, v.n, v.outer, &c->launches);
@@ -751,12 +796,6 @@ static int check_alpha_table(const slb_grid* g, int dim, const double* tab, int6
     return SLB_OK;
 }
 
-static long long env_ll(const char* name, long long dflt)
-{
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    return atoll(v);
-}
 
 static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
                            const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,

@@ -1,0 +1,387 @@
+// slb_bspfused.cuh -- K2+K1 fused: one periodic B-spline sweep (pre-solve c = A^{-1} u AND the
+// order+1 point stencil) in ONE pass over HBM: 16 B of traffic per cell-update, as SURVEY.md 8(d)
+// assumes for every interpolation kind.
+//
+// Reference: advection! for a B-spline state = sol(interp, line) (src/bsplinelu.jl:179-220,
+// :275-284 | src/bsplinefft.jl:49-58) followed by the periodic stencil
+// (src/interpolation.jl:175-193), per line, after a permutedims! (src/advection.jl:372-386).
+//
+// One WARP owns a tile of 32 lines and keeps it in shared memory for the whole sweep:
+//   1. load   : cp.async, 8 bytes per lane and row, every row of the tile in flight at once
+//               (strided dims: lanes = 32 neighbouring lines, each row one coalesced 256 B segment,
+//                tile pitch 32; dim 0: lines are contiguous, lanes run along the line and the tile
+//                is stored transposed with pitch 33 -- conflict-free both ways);
+//   2. solve  : thread-per-line bordered banded LU substitution, in place in shared memory
+//               (the formulation of slb_bspline.cuh; 4h+1 FMAs per cell).  All factor tables live
+//               in the KERNEL PARAMETERS (constant bank; every table read is warp-uniform and
+//               costs no load/store-unit slot), which is what makes the thread-per-line
+//               recurrence run at the FP64 pipe's pace instead of L1 latency;
+//   3. stencil: thread-per-line march with a rotating register window fed from shared memory;
+//               strided dims store each output row straight to HBM (coalesced); dim 0 writes the
+//               outputs back into the tile in place (output i overwrites the oldest window entry,
+//               the first order values are kept in registers for the periodic wrap) and
+//   4. (dim 0) the warp copies the tile out transposed, coalesced along the lines.
+// FP64 work: (4h + 1) + (2h + 2) FMAs per cell -- 33 for order 11, i.e. ~0.5 ms of pure DFMA issue
+// for a 128^4 sweep, next to 0.66 ms of HBM time: order 11 is balanced between the FP64 pipe and
+// HBM, lower orders are HBM-bound.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "slb_sweep.cuh"
+
+// factor tables as kernel parameters, one record of 4h+1 doubles per row i < N:
+//   { invd_i, L[i][0..h), invd_i * U[i][0..h), Ri[i][0..h), G[i][0..h) }   followed by Sinv[h][h]
+// (U is pre-scaled by 1/diag so that the backward recurrence is one FMA deep per row)
+#define SLB_BSPF_TAB 3560
+struct BspParamTab {
+    int h, n, N;
+    int o_S;
+    double v[SLB_BSPF_TAB];
+};
+
+struct BspFusedArgs {
+    const double* in;
+    double* out;
+    long long inner;   // element stride of the swept index (1: contiguous variant)
+    long long nlines;
+    int n;
+    int nc;            // polynomial coefficients per stencil weight
+    AlphaMap am;
+    OutMap om;         // strided variant: re-shard fused into the stores (plain: kc >= n)
+    InMap im;          // contiguous variant: block-major input lines (plain: c == 0)
+    double* linesum;   // strided variant, optional: per-line sums of the outputs
+};
+
+int slb_bspfused_launch(const BspFusedArgs& a, const BspParamTab& tab, const CoefTab& ct, int sm_count, cudaStream_t stream);
+bool slb_bspfused_supported(int h, int n);
+// fills `tab` from the host factor tables; false when they do not fit the parameter space
+bool slb_bspfused_fill(BspParamTab* tab, int h, int n, int N, const double* L, const double* U, const double* invd,
+                       const double* Ri, const double* G, const double* Sinv);
+
+#ifdef SLB_BSPF_IMPL
+__device__ __forceinline__ void bspf_cp_async8(unsigned smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+template <int H, bool CONTIG>
+__global__ void __launch_bounds__(32)
+k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__ BspParamTab tab, const __grid_constant__ CoefTab ct)
+{
+    constexpr int P1 = 2 * H + 2;           // order + 1 stencil points, order = 2h + 1
+    constexpr int PITCH = CONTIG ? 33 : 32;
+    extern __shared__ __align__(16) double tile[];
+    __shared__ int s0s[32];
+    const int lane = threadIdx.x;
+    const int n = fa.n, N = tab.N;
+    const long long line0 = (long long)blockIdx.x * 32;
+    const long long line = line0 + lane;
+    const bool active = line < fa.nlines;
+    const long long lc = active ? line : fa.nlines - 1;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
+
+    // ---- 1. load the tile --------------------------------------------------------------------
+    long long a = 0, b = 0;
+    if (CONTIG) {
+        for (int j = 0; j < 32; ++j) {
+            const long long lj = line0 + j;
+            if (lj < fa.nlines) {
+                const double* src = fa.in + slb_in_line(fa.im, lj) * n;
+                for (int k = lane; k < n; k += 32) bspf_cp_async8(sbase + 8u * (unsigned)(k * PITCH + j), src + k);
+            }
+        }
+    } else {
+        b = lc / fa.inner;
+        a = lc - b * fa.inner;
+        const double* src = fa.in + (b * n) * fa.inner + a;
+        if (active) {
+#pragma unroll 8
+            for (int k = 0; k < n; ++k) bspf_cp_async8(sbase + 8u * (unsigned)(k * PITCH + lane), src + (long long)k * fa.inner);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // stencil shift and weights of this lane's line (overlaps the loads)
+    double w[P1];
+    int s0;
+    {
+        const double alpha = fa.am.scale * __ldg(fa.am.tab + (CONTIG ? slb_alpha_off(fa.am, 0u, (unsigned)lc)
+                                                                      : slb_alpha_off(fa.am, (unsigned)a, (unsigned)b)));
+        double t;
+        slb_split(alpha, n, (P1 - 1) / 2, t, s0);
+        const int nc = fa.nc;
+#pragma unroll
+        for (int j = 0; j < P1; ++j) w[j] = ct.c[j * SLB_NCMAX + nc - 1];
+        for (int k = nc - 2; k >= 0; --k) {
+#pragma unroll
+            for (int j = 0; j < P1; ++j) w[j] = fma(t, w[j], ct.c[j * SLB_NCMAX + k]);
+        }
+    }
+    if (CONTIG) s0s[lane] = s0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    // ---- 2. bordered banded LU solve, in place, thread per line ---------------------------------
+    // Both recurrences are arranged so that the newest dependency enters LAST: the terms that use
+    // older results are summed first (they are ready), the right-hand side is added, and only one
+    // FMA per row waits for the previous row.  Right-hand sides are fetched one group of h rows ahead.
+    constexpr int TS = 4 * H + 1;
+    double* col = tile + lane;
+    const double* tS = tab.v + tab.o_S;
+    double x2[H];
+    {
+        double yw[H], acc[H], un[H];
+#pragma unroll
+        for (int s = 0; s < H; ++s) {
+            yw[s] = 0.0;
+            acc[s] = 0.0;
+            un[s] = s < N ? col[s * PITCH] : 0.0;
+        }
+#define BSPF_FWD_ROW(r, GUARD)                                                                        \
+    {                                                                                                 \
+        const int i = i0 + (r);                                                                       \
+        if (!(GUARD) || i < N) {                                                                      \
+            const double* T = tab.v + i * TS;                                                         \
+            double y;                                                                                 \
+            if (H >= 2) {                                                                             \
+                double sacc = -T[1 + H - 1] * yw[((r) - H + 2 * H) % H];                              \
+                _Pragma("unroll") for (int j = H - 1; j >= 2; --j)                                    \
+                    sacc = fma(-T[1 + j - 1], yw[((r) - j + 2 * H) % H], sacc);                       \
+                y = fma(-T[1], yw[((r) - 1 + 2 * H) % H], u[(r)] + sacc);                             \
+            } else {                                                                                  \
+                y = fma(-T[1], yw[0], u[(r)]);                                                        \
+            }                                                                                         \
+            yw[(r)] = y;                                                                              \
+            _Pragma("unroll") for (int q = 0; q < H; ++q) acc[q] = fma(T[1 + 2 * H + q], y, acc[q]);  \
+            col[i * PITCH] = y;                                                                       \
+        }                                                                                             \
+    }
+        int i0 = 0;
+        for (; i0 + 2 * H <= N; i0 += H) {  // whole groups, the next group's right-hand sides exist: no guards,
+            double u[H];                    // so that the rows of a group can overlap
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                u[r] = un[r];
+                un[r] = col[(i0 + H + r) * PITCH];
+            }
+#pragma unroll
+            for (int r = 0; r < H; ++r) BSPF_FWD_ROW(r, false)
+        }
+        for (; i0 < N; i0 += H) {
+            double u[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                u[r] = un[r];
+                const int inext = i0 + H + r;
+                un[r] = inext < N ? col[inext * PITCH] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < H; ++r) BSPF_FWD_ROW(r, true)
+        }
+#undef BSPF_FWD_ROW
+        double rhs[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) rhs[r] = col[(N + r) * PITCH] - acc[r];
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+            double sq = 0.0;
+#pragma unroll
+            for (int r = 0; r < H; ++r) sq = fma(tS[q * H + r], rhs[r], sq);
+            x2[q] = sq;
+        }
+#pragma unroll
+        for (int q = 0; q < H; ++q) col[(N + q) * PITCH] = x2[q];
+    }
+    {
+        double ww[H], un[H];
+        const int ilast = ((N - 1) / H) * H;
+#pragma unroll
+        for (int s = 0; s < H; ++s) {
+            ww[s] = 0.0;
+            un[s] = ilast + s < N ? col[(ilast + s) * PITCH] : 0.0;
+        }
+#define BSPF_BWD_ROW(r, GUARD)                                                                        \
+    {                                                                                                 \
+        const int i = i0 + (r);                                                                       \
+        if (!(GUARD) || i < N) {                                                                      \
+            const double* T = tab.v + i * TS;                                                         \
+            double v; /* w_i = invd_i * (y_i - sum_j U[i][j-1] w_{i+j}), U pre-scaled by invd_i */    \
+            if (H >= 2) {                                                                             \
+                double sacc = -T[1 + H + H - 1] * ww[((r) + H) % H];                                  \
+                _Pragma("unroll") for (int j = H - 1; j >= 2; --j)                                    \
+                    sacc = fma(-T[1 + H + j - 1], ww[((r) + j) % H], sacc);                           \
+                v = fma(-T[1 + H], ww[((r) + 1) % H], fma(T[0], u[(r)], sacc));                       \
+            } else {                                                                                  \
+                v = fma(-T[1 + H], ww[0], T[0] * u[(r)]);                                             \
+            }                                                                                         \
+            ww[(r)] = v;                                                                              \
+            double x = v;                                                                             \
+            _Pragma("unroll") for (int q = 0; q < H; ++q) x = fma(-T[1 + 3 * H + q], x2[q], x);       \
+            col[i * PITCH] = x;                                                                       \
+        }                                                                                             \
+    }
+        const int ngroups = ilast / H + 1;
+        {   // the last (possibly ragged) group
+            const int i0 = ilast;
+            double u[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                u[r] = un[r];
+                const int inext = i0 - H + r;
+                un[r] = inext >= 0 ? col[inext * PITCH] : 0.0;
+            }
+#pragma unroll
+            for (int r = H - 1; r >= 0; --r) BSPF_BWD_ROW(r, true)
+        }
+        // whole groups, counted upwards so that the table index stays in the uniform datapath
+        for (int gq = 1; gq < ngroups; ++gq) {
+            const int i0 = (ngroups - 1 - gq) * H;
+            double u[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                u[r] = un[r];
+                un[r] = i0 >= H ? col[(i0 - H + r) * PITCH] : 0.0;
+            }
+#pragma unroll
+            for (int r = H - 1; r >= 0; --r) BSPF_BWD_ROW(r, false)
+        }
+#undef BSPF_BWD_ROW
+    }
+
+    // ---- 3. stencil, thread per line ---------------------------------------------------------------
+    // window slot convention of slb_dot: logical element j of output i lives in win[(i + j) % P1]
+    double win[P1];
+    int kk = s0;
+#define BSPF_NEXT(dst)                   \
+    {                                    \
+        dst = col[kk * PITCH];           \
+        kk = kk + 1 == n ? 0 : kk + 1;   \
+    }
+#pragma unroll
+    for (int j = 0; j < P1 - 1; ++j) BSPF_NEXT(win[j]);
+    if (!CONTIG) {
+        const long long ooff = b * fa.om.bstride + a;
+        double* po = (fa.om.npeer > 0 ? fa.om.blk[0] : fa.out) + ooff;
+        double lsum = 0.0;
+        if (fa.om.kc >= n) {  // plain layout
+            int i0 = 0;
+            for (; i0 + P1 <= n; i0 += P1) {  // whole groups: no guards, the order+1 dot products overlap
+                double nx[P1];
+#pragma unroll
+                for (int r = 0; r < P1; ++r) BSPF_NEXT(nx[r]);
+#pragma unroll
+                for (int r = 0; r < P1; ++r) {
+                    win[(r + P1 - 1) % P1] = nx[r];
+                    const double acc = slb_dot<P1, false>(win, w, r);
+                    lsum += acc;
+                    if (active) po[(long long)r * fa.inner] = acc;
+                }
+                po += (long long)P1 * fa.inner;
+            }
+            for (; i0 < n; i0 += P1) {
+#pragma unroll
+                for (int r = 0; r < P1; ++r) {
+                    if (i0 + r < n) {
+                        BSPF_NEXT(win[(r + P1 - 1) % P1]);
+                        const double acc = slb_dot<P1, false>(win, w, r);
+                        lsum += acc;
+                        if (active) *po = acc;
+                        po += fa.inner;
+                    }
+                }
+            }
+        } else {              // output blocked along the swept index (multi-GPU re-shard)
+            int ko = 0, kb = 0;
+            for (int i0 = 0; i0 < n; i0 += P1) {
+#pragma unroll
+                for (int r = 0; r < P1; ++r) {
+                    if (i0 + r < n) {
+                        BSPF_NEXT(win[(r + P1 - 1) % P1]);
+                        const double acc = slb_dot<P1, false>(win, w, r);
+                        lsum += acc;
+                        if (active) *po = acc;
+                        po += fa.inner;
+                        if (++ko == fa.om.kc) {
+                            ko = 0;
+                            ++kb;
+                            if (fa.om.npeer > 0)
+                                po = fa.om.blk[kb < fa.om.npeer ? kb : 0] + ooff;
+                            else
+                                po += fa.om.kblk - (long long)fa.om.kc * fa.inner;
+                        }
+                    }
+                }
+            }
+        }
+        if (fa.linesum && active) fa.linesum[line] = lsum;
+    } else {
+        // in place: output i replaces the oldest window entry c[(i + s0) mod n]; the first order
+        // entries are needed again by the last outputs (periodic wrap) and stay in registers
+        double head[P1 - 1];
+#pragma unroll
+        for (int j = 0; j < P1 - 1; ++j) head[j] = win[j];
+        int kw = s0;  // where output i goes
+        const int nmain = n - (P1 - 1);
+        int i0 = 0;
+        for (; i0 + P1 <= nmain; i0 += P1) {  // whole groups: no guards, the dot products overlap
+            double nx[P1];
+#pragma unroll
+            for (int r = 0; r < P1; ++r) BSPF_NEXT(nx[r]);
+#pragma unroll
+            for (int r = 0; r < P1; ++r) {
+                win[(r + P1 - 1) % P1] = nx[r];
+                col[kw * PITCH] = slb_dot<P1, false>(win, w, r);
+                kw = kw + 1 == n ? 0 : kw + 1;
+            }
+        }
+        for (; i0 < nmain; i0 += P1) {
+#pragma unroll
+            for (int r = 0; r < P1; ++r) {
+                if (i0 + r < nmain) {
+                    BSPF_NEXT(win[(r + P1 - 1) % P1]);
+                    col[kw * PITCH] = slb_dot<P1, false>(win, w, r);
+                    kw = kw + 1 == n ? 0 : kw + 1;
+                }
+            }
+        }
+        // the last order outputs read their inputs afresh: entries not yet overwritten come from the
+        // tile, the wrapped ones (the first order entries of the line's window) from `head`
+        {
+            int kr = kw;  // position of c[(s0 + nmain) mod n], the oldest input of output nmain
+#pragma unroll
+            for (int q = 0; q < P1 - 1; ++q) {
+                double xs[P1];
+                int kq = kr;
+#pragma unroll
+                for (int j = 0; j < P1; ++j) {
+                    if (q + j < P1 - 1) {
+                        xs[j] = col[kq * PITCH];
+                        kq = kq + 1 == n ? 0 : kq + 1;
+                    } else {
+                        xs[j] = head[q + j - (P1 - 1)];
+                    }
+                }
+                col[kr * PITCH] = slb_dot<P1, false>(xs, w, 0);
+                kr = kr + 1 == n ? 0 : kr + 1;
+            }
+        }
+        __syncwarp();
+        // ---- 4. transposed, coalesced write-out ------------------------------------------------------
+        for (int j = 0; j < 32; ++j) {
+            const long long lj = line0 + j;
+            if (lj < fa.nlines) {
+                double* dst = fa.out + lj * n;
+                int pos = s0s[j] + lane;
+                pos %= n;
+                for (int k = lane; k < n; k += 32) {
+                    dst[k] = tile[pos * PITCH + j];
+                    pos += 32;
+                    pos = pos >= n ? pos % n : pos;
+                }
+            }
+        }
+    }
+#undef BSPF_NEXT
+}
+#endif  // SLB_BSPF_IMPL

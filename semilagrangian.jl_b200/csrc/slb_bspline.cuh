@@ -170,10 +170,12 @@ static int bspline_factor(int order, int64_t n64, const double* node_vals, Bspli
     return SLB_OK;
 }
 
-static int bspline_build(int kind, int order, int64_t n64, const double* node_vals, BsplineDev* out, std::string& msg)
+static int bspline_build(int kind, int order, int64_t n64, const double* node_vals, BsplineDev* out, std::string& msg,
+                         BsplineHost* host_out = nullptr)
 {
     (void)kind;
-    BsplineHost hb;
+    BsplineHost hb_local;
+    BsplineHost& hb = host_out ? *host_out : hb_local;
     int rc = bspline_factor(order, n64, node_vals, &hb, msg);
     if (rc) return rc;
     const std::vector<double>&dL = hb.L, &dU = hb.U, &dinv = hb.invd, &dRi = hb.Ri, &dG = hb.G, &dS = hb.Sinv;
