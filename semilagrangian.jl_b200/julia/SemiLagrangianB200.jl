@@ -104,6 +104,7 @@ getst(self::B200AdvectionData) = getst(self.adv, self.state_gen)
 getcur_t(self::B200AdvectionData) = getcur_t(self.adv, self.state_gen)
 
 function getdata(self::B200AdvectionData{T,N}) where {T,N}        # src/advection.jl:317
+    flush!(self)
     out = Array{T,N}(undef, sizeall(self.adv))
     check(ccall((:slb_grid_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), self.grid, out))
     return out
@@ -122,15 +123,56 @@ end
 # A displacement provider returns (table::Ptr{Cvoid} | Vector{Float64}, len, strides::Vector{Int64}, scale):
 #   alpha(line) = scale * table[1 + sum_d (idx_d - 1) * strides[d]]
 # -- the device-side replacement of getalpha(parext, advd, indext) (src/advection.jl:221-224).
+const PENDING = IdDict{Any,Any}()   # stage held back for pair fusion, per B200AdvectionData
+
+sweep_now(self, s) = check(ccall((:slb_sweep, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Cdouble, Cint, Cint),
+    self.grid, s.dim, self.interps[s.dim+1], s.tab, s.len, s.strides, s.scale, s.ondev, 0))
+
+# run a held-back stage (getdata, compute_ke and every charge density call this first)
+function flush!(self::B200AdvectionData)
+    s = pop!(PENDING, self, nothing)
+    s === nothing || sweep_now(self, s)
+end
+
+# Does initcoef! of the CURRENT state read the data?  Default yes; providers overload it
+# (Poisson: only the velocity state that recomputes rho, src/poisson.jl:171-176).
+initcoef_reads_data(parext, self) = true
+
 function advection!(self::B200AdvectionData{T,N}) where {T,N}     # src/advection.jl:594-704
     st = getst(self)
     (st.ndims == 1 && st.isconstdec) || throw(ArgumentError("B200 path: const-shift 1-D states only"))
+    haskey(PENDING, self) && initcoef_reads_data(self.parext, self) && flush!(self)
     initcoef!(self.parext, self)
     tab, len, strides, scale, ondev = alphatable(self.parext, self)
-    dim = st.perm[1] - 1
-    check(ccall((:slb_sweep, LIB), Cint,
-        (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Cdouble, Cint, Cint),
-        self.grid, dim, self.interps[dim+1], tab, len, strides, scale, ondev, 0))
+    cur = (dim = st.perm[1] - 1, tab = tab, len = len, strides = strides, scale = scale, ondev = ondev)
+    prev = pop!(PENDING, self, nothing)
+    if prev !== nothing
+        # two stages in one pass over HBM; bit-identical to two slb_sweep calls
+        rc = ccall((:slb_sweep_pair, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Cdouble,
+             Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Cdouble, Cint, Cint),
+            self.grid, prev.dim, self.interps[prev.dim+1], prev.tab, prev.len, prev.strides, prev.scale,
+            cur.dim, self.interps[cur.dim+1], cur.tab, cur.len, cur.strides, cur.scale, cur.ondev, 0)
+        if rc == -4                       # SLB_E_UNSUPPORTED: not a fusable combination
+            sweep_now(self, prev); sweep_now(self, cur)
+        else
+            check(rc)
+        end
+        return nextstate!(self)
+    end
+    if self.state_gen < self.adv.nbstates   # never hold a stage back across the end of a time step
+        nxt = getst(self.adv, self.state_gen + 1)
+        self.state_gen += 1
+        ok = nxt.ndims == 1 && nxt.isconstdec && nxt.perm[1] != 1 && strides[nxt.perm[1]] == 0 &&
+             !initcoef_reads_data(self.parext, self)
+        self.state_gen -= 1
+        if ok
+            PENDING[self] = cur
+            return nextstate!(self)
+        end
+    end
+    sweep_now(self, cur)
     return nextstate!(self)
 end
 
@@ -156,12 +198,16 @@ mutable struct B200PoissonVar
     end
 end
 
+initcoef_reads_data(pv::B200PoissonVar, self::B200AdvectionData) =
+    (st = getst(self); st.perm[1] > pv.Nsp && (pv.Nsp + 1) in st.perm[1:st.ndims])
+
 function initcoef!(pv::B200PoissonVar, self::B200AdvectionData{T,N}) where {T,N}   # src/poisson.jl:164-205
     st = getst(self); adv = self.adv; dt = getcur_t(self); Nsp = pv.Nsp
     strides = zeros(Int64, N)
     if st.perm[1] > Nsp
         if (Nsp + 1) in st.perm[1:st.ndims]
             dv = prod(step, adv.t_mesh[(Nsp+1):N])
+            flush!(self)
             check(ccall((:slb_charge_density, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}), self.grid, Nsp, dv, pv.rho))
             check(ccall((:slb_poisson_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), pv.plan, pv.rho, pv.E))
         end
