@@ -366,6 +366,13 @@ def run_ours(args):
         ee = S.compute_ee(advd)
         advd.getdata(out=host)
     wall_ser = time.perf_counter() - t0
+    # host-side cost of issuing one step (ctypes + Python driver logic; the launches are asynchronous)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step()
+    host_issue_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    ctx.sync()
     # resident variant (how the reference API is normally driven: f stays inside AdvectionData,
     # only the electric energy comes back each step)
     ctx.sync()
@@ -389,6 +396,7 @@ def run_ours(args):
         "e2e_resident": {"value": cells_per_step * e2e_steps / wall_res / 1e9, "unit": UNIT,
                          "note": "f resident in HBM across steps (AdvectionData semantics), ee read back per step; wall clock"},
         "gpu_launches": int(launches),
+        "host_issue_ms_per_step": host_issue_ms,
         "roofline": roofline,
         "gpu_fused_passes_per_step": advd_nfused / args.steps,
         "advection_call_ms": {f"dim{d}": float(np.mean(v)) for d, v in sorted(per_dim.items())},

@@ -221,6 +221,17 @@ void slb_poisson_destroy(slb_poisson* p);
  * E_dev: nsp device pointers, each prod(extents) doubles. */
 int slb_poisson_solve(slb_poisson* p, const double* rho_dev, double* const* E_dev);
 
+/* The field solve of one initcoef! (src/poisson.jl:171-176) with two launches instead of thirteen:
+ * the charge-density pass over f_dev ([prod(extents), nv_total] doubles: the grid's front buffer, or
+ * the line sums of the last velocity sweep) and ONE cooperative kernel that finishes rho (mean
+ * removed, src/util_poisson.jl:77) and runs every DFT pass of compute_elfield!.  rho_dev and E_dev
+ * as above.  Falls back to the separate kernels where cooperative launch is unavailable. */
+int slb_vp_field_solve(slb_poisson* p, const double* f_dev, int64_t nv_total, double dv, double* rho_dev,
+                       double* const* E_dev);
+/* same, starting from a charge density that is already reduced (e.g. all-gathered slabs of the
+ * sharded driver); subtract_mean != 0 removes its mean first.  rho_dev is updated in place. */
+int slb_poisson_solve_raw(slb_poisson* p, double* rho_dev, int subtract_mean, double* const* E_dev);
+
 /* sum(x .^ 2) for compute_ee (src/util_poisson.jl:156-162); deterministic; synchronises */
 int slb_reduce_sumsq(slb_ctx* ctx, const double* dev, int64_t n, double* host_out);
 /* sum(x) (deterministic; synchronises) */

@@ -97,6 +97,9 @@ struct slb_poisson {
     double2* tw[SLB_MAX_DIMS];
     double* mult[SLB_MAX_DIMS];
     double2 *wa, *wb, *wc;
+    double2* wx[2 * SLB_FIELD_MAXDIM];  // per-component work buffers of the one-kernel field solve
+    double* red;                        // its block sums
+    int coop_blocks;                    // cooperative grid size (0: cooperative launch unavailable)
 };
 
 static long long env_ll(const char* name, long long dflt)
@@ -1145,6 +1148,9 @@ extern "C" void slb_poisson_destroy(slb_poisson* p)
     if (p->wa) cudaFree(p->wa);
     if (p->wb) cudaFree(p->wb);
     if (p->wc) cudaFree(p->wc);
+    for (int d = 0; d < 2 * SLB_FIELD_MAXDIM; ++d)
+        if (p->wx[d]) cudaFree(p->wx[d]);
+    if (p->red) cudaFree(p->red);
     delete p;
 }
 
@@ -1184,6 +1190,22 @@ extern "C" int slb_poisson_create(slb_ctx* c, int nsp, const int64_t* ext, const
     if (e == cudaSuccess) e = cudaMalloc(&p->wa, p->ntot * sizeof(double2));
     if (e == cudaSuccess) e = cudaMalloc(&p->wb, p->ntot * sizeof(double2));
     if (e == cudaSuccess) e = cudaMalloc(&p->wc, p->ntot * sizeof(double2));
+    for (int d = 0; d < 2 * nsp && e == cudaSuccess; ++d) e = cudaMalloc(&p->wx[d], p->ntot * sizeof(double2));
+    if (e == cudaSuccess) {
+        // one-kernel field solve: a cooperative grid, at most one block per line and per resident slot
+        int coop = 0, maxb = 0, nmax = 1;
+        for (int d = 0; d < nsp; ++d) nmax = ext[d] > nmax ? (int)ext[d] : nmax;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        size_t smem = 2 * (size_t)nmax * sizeof(double2);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxb, k_field_solve, 128, smem) == cudaSuccess && maxb > 0) {
+            long long lines = p->ntot / nmax * nsp;
+            long long cap = (long long)maxb * c->sm_count;
+            p->coop_blocks = (int)(lines < cap ? lines : cap);
+            if (p->coop_blocks < 1) p->coop_blocks = 1;
+            e = cudaMalloc(&p->red, (size_t)p->coop_blocks * sizeof(double));
+        }
+        cudaGetLastError();
+    }
     if (e != cudaSuccess) {
         slb_poisson_destroy(p);
         cudaGetLastError();
@@ -1247,4 +1269,89 @@ extern "C" int slb_poisson_solve(slb_poisson* p, const double* rho_dev, double* 
         LAUNCH_CHECK(c);
     }
     return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one-kernel field solve
+// ------------------------------------------------------------------------------------------
+static int field_from_partial(slb_poisson* p, const double* partial, int nchunk, double scale, int subtract_mean, double* rho_dev,
+                              double* const* E_dev)
+{
+    slb_ctx* c = p->ctx;
+    if (!p->coop_blocks) return SLB_E_UNSUPPORTED;
+    FieldArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.partial = partial;
+    fa.nchunk = nchunk;
+    fa.scale = scale;
+    fa.subtract_mean = subtract_mean;
+    fa.nsp = p->nsp;
+    fa.ntot = p->ntot;
+    int nmax = 1;
+    for (int d = 0; d < p->nsp; ++d) {
+        fa.ext[d] = (int)p->ext[d];
+        nmax = fa.ext[d] > nmax ? fa.ext[d] : nmax;
+        fa.tw[d] = p->tw[d];
+        fa.mult[d] = p->mult[d];
+        fa.E[d] = E_dev[d];
+        fa.wc[d] = p->wx[2 * d];
+        fa.wd[d] = p->wx[2 * d + 1];
+    }
+    fa.rho = rho_dev;
+    fa.wa = p->wa;
+    fa.wb = p->wb;
+    fa.red = p->red;
+    void* args[] = {&fa};
+    size_t smem = 2 * (size_t)nmax * sizeof(double2);
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_field_solve, dim3((unsigned)p->coop_blocks), dim3(128), args, smem, c->stream));
+    c->launches++;
+    return SLB_OK;
+}
+
+extern "C" int slb_poisson_solve_raw(slb_poisson* p, double* rho_dev, int subtract_mean, double* const* E_dev)
+{
+    if (!p || !rho_dev || !E_dev) return fail(SLB_E_ARG, "slb_poisson_solve_raw: NULL argument");
+    for (int x = 0; x < p->nsp; ++x)
+        if (!E_dev[x]) return fail(SLB_E_ARG, "slb_poisson_solve_raw: E_dev[%d] is NULL", x);
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    int rc = field_from_partial(p, rho_dev, 1, 1.0, subtract_mean, rho_dev, E_dev);
+    if (rc != SLB_E_UNSUPPORTED) return rc;
+    if (subtract_mean) {
+        rc = slb_subtract_mean(p->ctx, rho_dev, p->ntot);
+        if (rc) return rc;
+    }
+    return slb_poisson_solve(p, rho_dev, E_dev);
+}
+
+extern "C" int slb_vp_field_solve(slb_poisson* p, const double* f_dev, int64_t nv_total, double dv, double* rho_dev,
+                                  double* const* E_dev)
+{
+    if (!p || !f_dev || !rho_dev || !E_dev || nv_total < 1) return fail(SLB_E_ARG, "slb_vp_field_solve: bad argument");
+    for (int x = 0; x < p->nsp; ++x)
+        if (!E_dev[x]) return fail(SLB_E_ARG, "slb_vp_field_solve: E_dev[%d] is NULL", x);
+    slb_ctx* c = p->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const long long ns = p->ntot, nv = nv_total;
+    if (!p->coop_blocks) {
+        int rc = slb_charge_density_from(c, f_dev, ns, nv, dv, rho_dev, 1);
+        if (rc) return rc;
+        return slb_poisson_solve(p, rho_dev, E_dev);
+    }
+    // K4 partial sums (the pass over f or over the line sums), then everything else in one kernel
+    long long xt = (ns + 31) / 32;
+    long long want = (long long)c->sm_count * 16;
+    long long nchunk = (want + xt - 1) / xt;
+    long long maxchunk = (nv + 63) / 64;
+    if (nchunk > maxchunk) nchunk = maxchunk;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 65535) nchunk = 65535;
+    long long chunk = (nv + nchunk - 1) / nchunk;
+    nchunk = (nv + chunk - 1) / chunk;
+    int rc = ensure_scratch(c, (size_t)(nchunk * ns) * sizeof(double));
+    if (rc) return rc;
+    double* partial = (double*)c->scratch;
+    dim3 grid((unsigned)xt, (unsigned)nchunk), block(32, 8);
+    k_charge_partial<<<grid, block, 0, c->stream>>>(f_dev, ns, nv, chunk, partial);
+    LAUNCH_CHECK(c);
+    return field_from_partial(p, partial, (int)nchunk, dv, 1, rho_dev, E_dev);
 }

@@ -6,6 +6,7 @@
 // All reductions are atomics-free and run in a fixed order, so electric-energy histories
 // are reproducible run to run ("hard parts").
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 // ------------------------------------------------------------------------------------------
@@ -178,4 +179,195 @@ __global__ void __launch_bounds__(256) k_ke_partial(const double* __restrict__ f
     for (long long a = threadIdx.x; a < nsp; a += 256) acc += __ldg(p + a);
     double r = slb_block_reduce(acc, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = vsq[blockIdx.x] * r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5f: the whole field solve of one initcoef! (src/poisson.jl:171-176) in ONE cooperative
+// kernel: rho = scale * sum_c partial[c] (the per-chunk sums of K4, or line sums, or a gathered
+// rho), mean subtraction (src/util_poisson.jl:77), forward DFTs over every space dim, and for
+// each component the multiplier i*k_x/|k|^2 + inverse DFTs + real part (src/poisson.jl:139-144).
+// The 11 small launches this replaces cost ~85 us per solve at 128^2 (launch gaps included),
+// 6 % of a fused Strang step on one GPU and 15 % on eight.  Phases are separated by grid-wide
+// barriers; every reduction runs in a fixed order, so histories stay reproducible.
+// Lines are distributed block-cyclically; line + twiddles sit in shared memory (2 n double2).
+// ------------------------------------------------------------------------------------------
+#define SLB_FIELD_MAXDIM 3
+struct FieldArgs {
+    const double* partial;   // [nchunk][ntot]
+    int nchunk;
+    double scale;
+    int subtract_mean;
+    int nsp;
+    int ext[SLB_FIELD_MAXDIM];
+    long long ntot;
+    const double2* tw[SLB_FIELD_MAXDIM];    // forward twiddles exp(-2 pi i m / n) per dim
+    const double* mult[SLB_FIELD_MAXDIM];   // imag part of fctv_k per component
+    double* rho;                            // out: charge density (after mean subtraction)
+    double* E[SLB_FIELD_MAXDIM];            // out: field components
+    double2* wa;                            // work: spectrum ping
+    double2* wb;                            // work: spectrum pong
+    double2* wc[SLB_FIELD_MAXDIM];          // work: one buffer per component (inverse passes)
+    double2* wd[SLB_FIELD_MAXDIM];
+    double* red;                            // work: gridDim.x block sums
+};
+
+// one DFT line: out(k) = sum_j in(j) * tw^(jk) (conjugated when INVERSE, scaled by 1/n)
+template <bool REAL_IN, bool INVERSE, bool MULT, bool REAL_OUT>
+__device__ __forceinline__ void field_dft_line(const void* in_, void* out_, long long base, long long inner, int n,
+                                               const double2* __restrict__ tw, const double* __restrict__ mult, double shift,
+                                               double2* line, double2* twd)
+{
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double2 t = tw[j];
+        if (INVERSE) t.y = -t.y;
+        twd[j] = t;
+        double2 v;
+        if (REAL_IN)
+            v = make_double2(reinterpret_cast<const double*>(in_)[base + inner * j] - shift, 0.0);
+        else
+            v = reinterpret_cast<const double2*>(in_)[base + inner * j];
+        if (MULT) {
+            const double mm = mult[base + inner * j];
+            v = make_double2(-v.y * mm, v.x * mm);
+        }
+        line[j] = v;
+    }
+    __syncthreads();
+    const double scale = INVERSE ? 1.0 / (double)n : 1.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        // four interleaved partial sums (j mod 4): the dependent FMA chain is 4x shorter; the order of
+        // the additions is fixed, so results are reproducible
+        double ar[4] = {0.0, 0.0, 0.0, 0.0}, ai[4] = {0.0, 0.0, 0.0, 0.0};
+        int mq[4];
+        const int k4 = (int)(((long long)4 * k) % n);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mq[q] = (int)(((long long)q * k) % n);
+        int j = 0;
+        for (; j + 4 <= n; j += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 t = twd[mq[q]];
+                const double2 v = line[j + q];
+                ar[q] = fma(v.x, t.x, ar[q]);
+                ar[q] = fma(-v.y, t.y, ar[q]);
+                ai[q] = fma(v.x, t.y, ai[q]);
+                ai[q] = fma(v.y, t.x, ai[q]);
+                mq[q] += k4;
+                if (mq[q] >= n) mq[q] -= n;
+            }
+        }
+        for (int q = 0; j < n; ++j, ++q) {  // n % 4 leftover elements
+            const double2 t = twd[mq[q]];
+            const double2 v = line[j];
+            ar[q] = fma(v.x, t.x, ar[q]);
+            ar[q] = fma(-v.y, t.y, ar[q]);
+            ai[q] = fma(v.x, t.y, ai[q]);
+            ai[q] = fma(v.y, t.x, ai[q]);
+        }
+        const double sr = (ar[0] + ar[1]) + (ar[2] + ar[3]);
+        const double si = (ai[0] + ai[1]) + (ai[2] + ai[3]);
+        const long long o = base + inner * k;
+        if (REAL_OUT)
+            reinterpret_cast<double*>(out_)[o] = sr * scale;
+        else
+            reinterpret_cast<double2*>(out_)[o] = make_double2(sr * scale, si * scale);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_field_solve(const __grid_constant__ FieldArgs fa)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double2 fsm2[];
+    __shared__ double redsm[32];
+    __shared__ double mean_sm;
+    const long long ntot = fa.ntot;
+    // ---- phase A: rho = scale * sum of the partial sums; block sums for the mean --------------
+    {
+        double acc = 0.0;
+        for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < ntot; a += (long long)gridDim.x * blockDim.x) {
+            double s = 0.0;
+            for (int c = 0; c < fa.nchunk; ++c) s += fa.partial[(long long)c * ntot + a];
+            s *= fa.scale;
+            fa.rho[a] = s;
+            acc += s;
+        }
+        const double r = slb_block_reduce(acc, redsm);
+        if (threadIdx.x == 0) fa.red[blockIdx.x] = r;
+    }
+    grid.sync();
+    // ---- mean (every block adds the block sums in the same order) ------------------------------
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        if (fa.subtract_mean) {
+            for (unsigned b = 0; b < gridDim.x; ++b) m += fa.red[b];
+            m /= (double)ntot;
+        }
+        mean_sm = m;
+    }
+    __syncthreads();
+    const double mean = mean_sm;
+    // ---- forward transforms ------------------------------------------------------------------------
+    const int nsp = fa.nsp;
+    double2* cur = fa.wa;
+    double2* nxt = fa.wb;
+    {
+        const int n = fa.ext[0];
+        const long long nlines = ntot / n;
+        for (long long ln = blockIdx.x; ln < nlines; ln += gridDim.x)  // reads the raw rho, subtracts the mean on the fly
+            field_dft_line<true, false, false, false>(fa.rho, cur, (long long)n * ln, 1, n, fa.tw[0], nullptr, mean, fsm2, fsm2 + n);
+    }
+    grid.sync();
+    if (fa.subtract_mean)  // nobody reads the raw rho any more: store the mean-free charge density
+        for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < ntot; a += (long long)gridDim.x * blockDim.x)
+            fa.rho[a] -= mean;
+    long long inner = fa.ext[0];
+    for (int d = 1; d < nsp; ++d) {
+        const int n = fa.ext[d];
+        const long long nlines = ntot / n;
+        for (long long ln = blockIdx.x; ln < nlines; ln += gridDim.x) {
+            const long long a = ln % inner, b = ln / inner;
+            field_dft_line<false, false, false, false>(cur, nxt, a + inner * (long long)n * b, inner, n, fa.tw[d], nullptr, 0.0, fsm2, fsm2 + n);
+        }
+        grid.sync();
+        double2* t = cur;
+        cur = nxt;
+        nxt = t;
+        inner *= n;
+    }
+    // ---- inverse transforms, all components in the same phases ---------------------------------------
+    // pass over dim 0 applies the multiplier; the last pass keeps the real part
+    {
+        const int n = fa.ext[0];
+        const long long nlines = ntot / n;
+        for (long long w = blockIdx.x; w < nlines * nsp; w += gridDim.x) {
+            const int x = (int)(w / nlines);
+            const long long ln = w % nlines;
+            if (nsp == 1)
+                field_dft_line<false, true, true, true>(cur, fa.E[x], (long long)n * ln, 1, n, fa.tw[0], fa.mult[x], 0.0, fsm2, fsm2 + n);
+            else
+                field_dft_line<false, true, true, false>(cur, fa.wc[x], (long long)n * ln, 1, n, fa.tw[0], fa.mult[x], 0.0, fsm2, fsm2 + n);
+        }
+    }
+    inner = fa.ext[0];
+    for (int d = 1; d < nsp; ++d) {
+        grid.sync();
+        const int n = fa.ext[d];
+        const long long nlines = ntot / n;
+        const bool last = d == nsp - 1;
+        for (long long w = blockIdx.x; w < nlines * nsp; w += gridDim.x) {
+            const int x = (int)(w / nlines);
+            const long long ln = w % nlines;
+            const long long a = ln % inner, b = ln / inner;
+            const long long base = a + inner * (long long)n * b;
+            const double2* src = (d % 2 == 1) ? fa.wc[x] : fa.wd[x];
+            if (last)
+                field_dft_line<false, true, false, true>(src, fa.E[x], base, inner, n, fa.tw[d], nullptr, 0.0, fsm2, fsm2 + n);
+            else
+                field_dft_line<false, true, false, false>(src, (d % 2 == 1) ? fa.wd[x] : fa.wc[x], base, inner, n, fa.tw[d], nullptr, 0.0, fsm2,
+                                                          fsm2 + n);
+        }
+        inner *= n;
+    }
 }

@@ -298,9 +298,8 @@ class ShardedAdvectionData:
             self.dist.all_gather_into_tensor(self.rho, self.rho_local, group=self.group)
         else:
             self.rho.copy_(self.rho_local)
-        _lib.check(L.slb_subtract_mean(self.ctx.h, C.c_void_p(self.rho.data_ptr()), self.rho.numel()))
         arr = (C.c_void_p * 2)(*[e.data_ptr() for e in self.E])
-        _lib.check(L.slb_poisson_solve(self.plan, C.c_void_p(self.rho.data_ptr()), arr))
+        _lib.check(L.slb_poisson_solve_raw(self.plan, C.c_void_p(self.rho.data_ptr()), 1, arr))  # mean removal + all DFT passes: one kernel
         self.has_field = True
 
     def compute_ee(self):

@@ -88,6 +88,25 @@ class PoissonVar(AbstractExtDataAdv):
             return
         _lib.check(_lib.lib().slb_charge_density(advd.grid, self.Nsp, dv, self.rho_dev))
 
+    def field_solve(self, advd):
+        """compute_charge! + compute_elfield! of one initcoef! (src/poisson.jl:171-176) as two
+        launches: the reduction over f (or over the line sums the last velocity pass left) and one
+        cooperative kernel for the rest (slb_vp_field_solve)."""
+        advd.flush()
+        dv = 1.0
+        for m in self.adv.t_mesh[self.Nsp:]:
+            dv = dv * m.step
+        L = _lib.lib()
+        d = getattr(advd, "_linesum_dim", None)
+        nv = int(np.prod(self.adv.sizeall[self.Nsp:]))
+        if d is not None and d >= self.Nsp:
+            src, nv = advd._linesum, nv // self.adv.sizeall[d]
+        else:
+            src = C.c_void_p(L.slb_grid_front(advd.grid))
+        arr = (C.c_void_p * self.Nsp)(*[p.value for p in self.E_dev])
+        _lib.check(L.slb_vp_field_solve(self.plan, src, nv, dv, self.rho_dev, arr))
+        self.has_field = True
+
     def wants_linesum(self, advd):
         """True when the NEXT advection! call starts with compute_charge! (src/poisson.jl:171-174)
         and the current sweep runs along a velocity dim, so its line sums can feed it."""
@@ -132,8 +151,7 @@ class PoissonVar(AbstractExtDataAdv):
         strides = [0] * N
         if self.isvelocity(advd):
             if (Nsp + 1) in st.perm[: st.ndims]:
-                self.compute_charge(advd)
-                self.compute_elfield()
+                self.field_solve(advd)
             if not self.has_field:
                 raise RuntimeError("velocity state before any field solve (state order must start with dim Nsp+1)")
             d = st.perm[0]

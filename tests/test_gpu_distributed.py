@@ -28,14 +28,15 @@ def _sweep_ex(f_flat_or_arr, shape, dim, interp, tab, astride, mode, bdim, nbloc
     return out
 
 
+@pytest.mark.parametrize("kind,order", [("lagrange", 7), ("bspline_lu", 5), ("bspline_fft", 11)])
 @pytest.mark.parametrize("nblocks", [2, 4, 8])
-def test_out_blocked_equals_block_major_of_plain_sweep(nblocks):
+def test_out_blocked_equals_block_major_of_plain_sweep(nblocks, kind, order):
     from slb200 import distributed as D, _lib
 
     rng = np.random.default_rng(1)
     shape = (32, 64, 6, 4)
     f = np.asfortranarray(rng.random(shape))
-    interp, ointerp = make_pair("lagrange", 7, shape[1])
+    interp, ointerp = make_pair(kind, order, shape[1])
     tab = rng.uniform(-6, 6, shape[3])
     ref = oracle_sweep(f, 1, ointerp, tab, [0, 0, 0, 1])
     out = _sweep_ex(f, shape, 1, interp, tab, [0, 0, 0, 1], _lib.SLB_RESHARD_OUT_BLOCKED, 1, nblocks)
@@ -43,14 +44,15 @@ def test_out_blocked_equals_block_major_of_plain_sweep(nblocks):
     assert relerr(got, ref) <= 1e-12
 
 
+@pytest.mark.parametrize("kind,order", [("lagrange", 7), ("bspline_lu", 5), ("bspline_fft", 11)])
 @pytest.mark.parametrize("nblocks", [2, 4, 8])
-def test_in_blocked_reads_block_major_input(nblocks):
+def test_in_blocked_reads_block_major_input(nblocks, kind, order):
     from slb200 import distributed as D, _lib
 
     rng = np.random.default_rng(2)
     shape = (128, 16, 5, 3)
     f = np.asfortranarray(rng.random(shape))
-    interp, ointerp = make_pair("lagrange", 7, shape[0])
+    interp, ointerp = make_pair(kind, order, shape[0])
     tab = rng.uniform(-6, 6, shape[2])
     ref = oracle_sweep(f, 0, ointerp, tab, [0, 0, 1, 0])
     fb = D.to_block_major(f, 1, nblocks)

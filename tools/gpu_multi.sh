@@ -10,6 +10,10 @@ for w in "$@"; do
     check)
       timeout 300 $TR tools/check_sharded.py 32 p2p 2>&1 | grep -E "rank|Error|error" | tee $OUT/check_p2p.log
       timeout 300 $TR tools/check_sharded.py 32 nccl 2>&1 | grep -E "rank|Error|error" | tee $OUT/check_nccl.log ;;
+    bspline)
+      timeout 300 $TR tools/check_sharded.py 32 p2p bspline_fft 11 2>&1 | grep -E "rank|Error|error" | tee $OUT/check_bspline_p2p.log
+      timeout 300 $TR tools/check_sharded.py 32 nccl bspline_lu 5 2>&1 | grep -E "rank|Error|error" | tee $OUT/check_bspline_nccl.log
+      timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 --interp bspline_fft --order 11 2>&1 | grep -E "^\{|Error|error" | tee $OUT/bench_${N}gpu_bspline11.json ;;
     bench)
       timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 2>&1 | grep -E "^\{|Error|error" | tee $OUT/bench_${N}gpu_p2p.json ;;
     nccl)
