@@ -267,13 +267,70 @@ class AdvectionData:
         return False
 
 
+def sol_nd(interps, b):
+    """sol(interp_t, b) for an N-D slice (src/interpolation.jl:48-94): the 1-D solve of each
+    non-identity interpolation applied along its dimension."""
+    out = np.array(b, dtype=np.float64, copy=True)
+    for d, it in enumerate(interps):
+        if it.kind in (BSPLINE_LU, BSPLINE_FFT):
+            out = np.apply_along_axis(it.sol, d, out)
+    return out
+
+
+def interpolate_nd_const(fi, dec, interps):
+    """interpolate!(fp, fi, decint::NTuple, precal::Array, interp::Vector) -- the N-D constant-shift
+    tensor stencil of src/interpolation.jl:212-231, with precal = dotprod of the 1-D weights
+    (src/interpolation.jl:112-118) and (decint, decfloat) = floor split per dim (:381-389):
+        fp[ind] = sum(res[window(ind)] .* precal),  window_d = ind_d + decint_d - order_d/2 + (0..order_d)
+    The products res .* precal are rounded, then summed (Julia's sum over < 1024 elements is a
+    plain loop; its @simd reassociation is not pinned by any test -- see oracle.c's header)."""
+    nd = fi.ndim
+    res = sol_nd(interps, fi)
+    decint = [int(np.floor(a)) for a in dec]
+    ws = [interps[d].getprecal(float(dec[d]) - decint[d]) for d in range(nd)]
+    precal = ws[0]
+    for d in range(1, nd):
+        precal = np.multiply.outer(precal, ws[d])     # dotprod: rounded products of the 1-D weights
+    out = np.zeros_like(res)
+    for idx in np.ndindex(*precal.shape):             # column-major order of Julia's sum would be
+        sh = res                                      # reversed(idx); the set of terms is the same
+        for d in range(nd):
+            off = decint[d] - interps[d].order // 2 + idx[d]
+            sh = np.roll(sh, -off, axis=d)
+        out = out + sh * precal[idx]
+    return out
+
+
+def _advection_nd(advd):
+    """advection! for a const-shift state with ndims > 1 (src/advection.jl:622-632 with the N-D
+    interpolate!): every slice over the first ndims permuted dims is shifted by getalpha(indext)."""
+    adv = advd.adv
+    st = advd.getst()
+    nd = st.ndims
+    ext = advd.parext
+    ext.initcoef(advd)
+    dims = [p - 1 for p in st.perm[:nd]]
+    rest = [p - 1 for p in st.perm[nd:]]
+    interps = [adv.t_interp[d] for d in dims]
+    f = np.transpose(advd.data, dims + rest)          # getformdata: permuted view
+    out = np.empty_like(f)
+    for ind in np.ndindex(*[adv.sizeall[d] for d in rest]):
+        alpha = ext.getalpha_nd(advd, ind)            # tuple of ndims shifts (grid units)
+        sl = (slice(None),) * nd + ind
+        out[sl] = interpolate_nd_const(np.ascontiguousarray(f[sl]), alpha, interps)
+    advd.data[...] = np.transpose(out, np.argsort(dims + rest))   # copydata!
+    return advd.nextstate()
+
+
 def advection(advd):
-    """advection!(self)  src/advection.jl:594-704, const-shift 1-D states
+    """advection!(self)  src/advection.jl:594-704, const-shift states
     (NoTimeOpt :622-632 / SimpleThreadsOpt :647-657)."""
     adv = advd.adv
     st = advd.getst()
-    if st.ndims != 1 or not st.isconstdec:
-        raise NotImplementedError("oracle covers ndims=1 const-shift states (SURVEY.md 8a)")
+    if not st.isconstdec:
+        raise NotImplementedError("oracle covers const-shift states (SURVEY.md 8a)")
+    if st.ndims != 1:
+        return _advection_nd(advd)
     interp = advd.getinterp()[0]
     ext = advd.parext
     ext.initcoef(advd)  # :407-408
@@ -442,6 +499,20 @@ class PoissonVar:
         d = st.perm[st.ndims + self.tupleind[0] - 1]
         astride[d - 1] = 1
         return tab, astride
+
+
+def _poisson_getalpha_nd(self, advd, ind):
+    """getalpha (src/poisson.jl:210-224) for a state with ndims > 1: `ind` is the 0-based trailing
+    index over dims perm[ndims:]."""
+    st = advd.getst()
+    Nsp = self.Nsp
+    if self.isvelocity(advd):
+        sub = ind[len(ind) - Nsp:]                       # ind.I[end-Nsp+1:end]
+        return tuple(b[sub] for b in self.bufcur_v)
+    return tuple(self.bufcur_sp[x][ind[self.tupleind[x] - 1]] for x in range(st.ndims))
+
+
+PoissonVar.getalpha_nd = _poisson_getalpha_nd
 
 
 def getpoissonvar(adv):

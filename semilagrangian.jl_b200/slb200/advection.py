@@ -56,6 +56,11 @@ class AbstractExtDataAdv:
     def alpha_table(self, advd):
         raise NotImplementedError
 
+    def alpha_table_nd(self, advd):
+        """states with ndims > 1: one alpha_table descriptor per swept dim (getalpha returns a tuple
+        of ndims shifts, src/advection.jl:221-224)"""
+        raise NotImplementedError
+
     def initcoef_reads_data(self, advd):
         """True when initcoef of the CURRENT state reads advd's data (e.g. a charge density).
         A provider that returns False for a state lets advection() fuse that stage with the one
@@ -307,6 +312,34 @@ def sweep_pair(advd, stageA, stageB):
     return True
 
 
+def _advection_2d(advd):
+    """A const-shift state with ndims = 2 (e.g. ([1,2,3,4], 2, 1, true), test/test_poisson2d.jl:276,
+    examples/vlasov-poisson-2d2v.jl:196): the reference shifts every 2-D slice by a constant pair
+    (alpha_1, alpha_2) with the tensor stencil of src/interpolation.jl:212-231.  That operator is
+    the product of the two 1-D stencils (and of the 1-D B-spline solves, :48-94), so it runs as ONE
+    pair-fused pass (slb_sweep_pair), or as two sweeps where the pair is not fusable; results agree
+    with the tensor form to rounding (the two forms add the same products in a different order)."""
+    st = advd.getst()
+    ext = advd.parext
+    advd.flush()
+    ext.initcoef(advd)
+    descr = ext.alpha_table_nd(advd)  # one (table, strides, scale, on_device) per swept dim
+    want = bool(getattr(ext, "wants_linesum", lambda a: False)(advd))
+    stages = []
+    for x in range(2):
+        table, strides, scale, on_device = descr[x]
+        d = st.perm[x] - 1
+        stages.append((d, advd.adv.t_interp[d], table, list(strides), scale, on_device, advd.flags, False))
+    if stages[1][0] == 0:  # the march of the fused pass cannot run along dim 0: the stencils commute
+        stages.reverse()
+    a, b = stages
+    b = b[:7] + (want,)
+    if not (advd.fuse_pairs and sweep_pair(advd, a, b)):
+        _sweep_now(advd, *a)
+        _sweep_now(advd, *b)
+    return advd.nextstate()
+
+
 def advection(advd):
     """advection!(advd) -- src/advection.jl:594-704.  One split stage; returns True while
     more stages remain in the current time step.
@@ -316,10 +349,12 @@ def advection(advd):
     both.  getdata / compute_ke / any charge density flush a recorded stage first, so every
     observable value is the one the reference's stage-by-stage execution produces."""
     st = advd.getst()
-    if st.ndims != 1 or not st.isconstdec:
+    if not st.isconstdec or st.ndims > 2:
         raise NotImplementedError(
-            "only const-shift 1-D states (ndims=1, isconstdec=true) are on the B200 path (SURVEY.md 8a/8f)"
+            "only const-shift states with ndims <= 2 are on the B200 path (SURVEY.md 8a/8f)"
         )
+    if st.ndims == 2:
+        return _advection_2d(advd)
     interp = advd.getinterp()[0]
     ext = advd.parext
     if advd._pending is not None and ext.initcoef_reads_data(advd):

@@ -154,28 +154,33 @@ class PoissonVar(AbstractExtDataAdv):
                 self.field_solve(advd)
             if not self.has_field:
                 raise RuntimeError("velocity state before any field solve (state order must start with dim Nsp+1)")
-            d = st.perm[0]
-            # bufcur_v = (dt / step(mesh_d)) * E_{d-Nsp}; indexed by ind.I[end-Nsp+1:end], i.e. E's
-            # axis i is the grid dim perm[N-Nsp+i]  (src/poisson.jl:178-189, :216-219)
+            # bufcur_v[x] = (dt / step(mesh_d)) * E_{d-Nsp}, d = perm[x]; indexed by ind.I[end-Nsp+1:end],
+            # i.e. E's axis i is the grid dim perm[N-Nsp+i]  (src/poisson.jl:178-189, :216-219)
             stride = 1
             for i in range(Nsp):
                 g = st.perm[N - Nsp + i]
                 strides[g - 1] = stride
                 stride *= self.sp_ext[i]
-            self._sweep = ((self.E_dev[d - 1 - Nsp], self.nsp_tot), strides, dt / adv.t_mesh[d - 1].step, True)
+            self._sweeps = []
+            for x in range(st.ndims):
+                d = st.perm[x]
+                self._sweeps.append(((self.E_dev[d - 1 - Nsp], self.nsp_tot), list(strides), dt / adv.t_mesh[d - 1].step, True))
         else:
             # tupleind / bufcur_sp, src/poisson.jl:191-203 (invp where perm is meant: identical for
             # the involutive permutations every reference driver uses)
-            tupleind = st.perm[st.invp[0] + Nsp - 1] - st.ndims
-            g = st.perm[st.ndims + tupleind - 1]
-            src_dim = st.invp[0] + Nsp
-            strides[g - 1] = 1
-            self._sweep = (
-                (advd.points_dev(src_dim - 1), adv.sizeall[src_dim - 1]),
-                strides,
-                -dt / adv.t_mesh[st.invp[0] - 1].step,
-                True,
-            )
+            self._sweeps = []
+            for x in range(st.ndims):
+                tupleind = st.perm[st.invp[x] + Nsp - 1] - st.ndims
+                g = st.perm[st.ndims + tupleind - 1]
+                src_dim = st.invp[x] + Nsp
+                sx = [0] * N
+                sx[g - 1] = 1
+                self._sweeps.append(((advd.points_dev(src_dim - 1), adv.sizeall[src_dim - 1]), sx,
+                                     -dt / adv.t_mesh[st.invp[x] - 1].step, True))
+        self._sweep = self._sweeps[0]
+
+    def alpha_table_nd(self, advd):
+        return self._sweeps
 
     def alpha_table(self, advd):
         return self._sweep

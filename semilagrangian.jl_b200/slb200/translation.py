@@ -13,6 +13,9 @@ class TranslationVar(AbstractExtDataAdv):
         st = advd.getst()
         self.valok = tuple(self.values[st.perm[i] - 1] * advd.getcur_t() for i in range(st.ndims))
 
+    def alpha_table_nd(self, advd):
+        return [(np.array([v]), [0] * advd.adv.N, 1.0, False) for v in self.valok]
+
     def initcoef_reads_data(self, advd):
         return False  # shifts come from the meshes / constants only
 

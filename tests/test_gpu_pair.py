@@ -226,3 +226,67 @@ def test_driver_fuses_translation_with_host_tables():
             pass
     assert a.n_fused == 4 and b.n_fused == 0
     assert np.array_equal(a.getdata(), b.getdata())
+
+
+# ---------------------------------------------------------------------------------------------
+# states with ndims = 2 and constant shifts: the reference's N-D tensor stencil == one fused pass
+# ---------------------------------------------------------------------------------------------
+def _vp_2d_states(M, sz, kind, order, states):
+    import math
+
+    ms = (M.UniformMesh(0.0, 4 * math.pi, sz[0]), M.UniformMesh(0.0, 4 * math.pi, sz[1]),
+          M.UniformMesh(-6.0, 6.0, sz[2]), M.UniformMesh(-6.0, 6.0, sz[3]))
+    mk = {"lagrange": lambda n: M.Lagrange(order), "bspline_lu": lambda n: M.BSplineLU(order, n)}[kind]
+    adv = M.Advection(ms, [mk(n) for n in sz], 0.1, states)
+    fsp = lambda x: 0.5 * np.cos(x / 2) + 1
+    fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+    f = M.dotprod((fsp(ms[0].points), fsp(ms[1].points), fv(ms[2].points), fv(ms[3].points)))
+    return M.AdvectionData(adv, f, M.getpoissonvar(adv))
+
+
+@pytest.mark.parametrize("kind,order,sz", [("lagrange", 7, (16, 18, 20, 16)), ("lagrange", 5, (12, 12, 14, 16)),
+                                           ("bspline_lu", 5, (16, 12, 16, 12))])
+def test_states_with_ndims_2_match_the_nd_tensor_stencil_oracle(kind, order, sz):
+    """test/test_poisson2d.jl:276 / examples/vlasov-poisson-2d2v.jl:196: tabst =
+    [([1,2,3,4], 2, 1, true), ([3,4,1,2], 2, 2, true)].  The oracle evaluates the N-D tensor
+    stencil of src/interpolation.jl:212-231 slice by slice; the product runs one fused pass (or two
+    sweeps for B-splines) per state."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    states = [([3, 4, 1, 2], 2, 1, True), ([1, 2, 3, 4], 2, 2, True)]
+    g = _vp_2d_states(S, sz, kind, order, states)
+    o = _vp_2d_states(R, sz, kind, order, states)
+    assert g.adv.nbstates == o.adv.nbstates == 3
+    nst = 0
+    for step in range(2):
+        more = True
+        while more:
+            more = S.advection(g)
+            assert more == R.advection(o)
+            nst += 1
+            assert relerr(g.getdata(), o.data) <= 2e-12 * nst
+        assert abs(S.compute_ee(g) - R.compute_ee(o)) <= 1e-11 * abs(R.compute_ee(o))
+    if kind == "lagrange":
+        assert g.n_fused == 6      # every 2-D state ran as one pass over HBM
+    eg, eo = S.getenergy(g), R.getenergy(o)
+    assert np.allclose(eg, eo, rtol=1e-11, atol=0)
+
+
+def test_states_with_ndims_2_space_first_and_translation():
+    """the other state order of the reference test (x pair first), and a 2-D translation state"""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    states = [([1, 2, 3, 4], 2, 1, True), ([3, 4, 1, 2], 2, 2, True)]
+    sz = (16, 16, 12, 20)
+    # the v-state comes second: the first x half-step runs before any field solve
+    g = _vp_2d_states(S, sz, "lagrange", 7, states)
+    o = _vp_2d_states(R, sz, "lagrange", 7, states)
+    for _ in range(2):
+        while S.advection(g):
+            pass
+        while R.advection(o):
+            pass
+    assert relerr(g.getdata(), o.data) <= 2e-12 * 6
+    assert g.n_fused == 6

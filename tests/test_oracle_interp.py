@@ -270,3 +270,33 @@ def test_sweep_equals_line_loop_and_threads():
                              clib.dp(tab.reshape(-1, order="F").copy()), clib.lp(astride), nth)
             assert rc == 0
             assert np.array_equal(g, ref)
+
+
+def test_oracle_nd_constant_shift_state_equals_split_1d_states():
+    """src/interpolation.jl:212-231: the N-D constant-shift tensor stencil of a state with ndims = 2
+    (test/test_poisson2d.jl:276) is the product of the 1-D stencils, so a 2D2V Vlasov-Poisson run
+    with states [(v1 v2), (x1 x2)] must agree with the run whose states are the four 1-D sweeps
+    (examples/vlasov-poisson-2d2v.jl:126-131) to rounding."""
+    import math
+
+    from oracle import refmodel as R
+
+    def build(states, n=10):
+        ms = (R.UniformMesh(0.0, 4 * math.pi, n), R.UniformMesh(0.0, 4 * math.pi, n + 2),
+              R.UniformMesh(-6.0, 6.0, n + 4), R.UniformMesh(-6.0, 6.0, n))
+        adv = R.Advection(ms, [R.Lagrange(5)] * 4, 0.1, states)
+        fsp = lambda x: 0.5 * np.cos(x / 2) + 1
+        fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+        f = R.dotprod((fsp(ms[0].points), fsp(ms[1].points), fv(ms[2].points), fv(ms[3].points)))
+        return R.AdvectionData(adv, f, R.getpoissonvar(adv))
+
+    a = build([([3, 4, 1, 2], 2, 1, True), ([1, 2, 3, 4], 2, 2, True)])
+    b = build([([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)])
+    assert a.adv.nbstates == 3 and b.adv.nbstates == 6
+    for _ in range(2):
+        while R.advection(a):
+            pass
+        while R.advection(b):
+            pass
+    assert np.max(np.abs(a.data - b.data)) <= 1e-13 * np.max(np.abs(b.data))
+    assert abs(R.compute_ee(a) - R.compute_ee(b)) <= 1e-12 * abs(R.compute_ee(b))
