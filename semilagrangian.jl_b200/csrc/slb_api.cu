@@ -86,7 +86,8 @@ struct slb_interp {
     CoefTab tab;
     double* coef_dev;
     BsplineDev bsp;            // LU factors / circulant symbol on the device (B-spline kinds)
-    BspParamTab* bsptab;       // the same factors laid out as kernel parameters (fused sweep), or NULL
+    double* bsptab_dev;        // the same factors in the fused sweep's record layout (device), or NULL
+    BspFusedTab bsptab;
 };
 
 struct slb_poisson {
@@ -430,7 +431,8 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
         cudaGetLastError();
         return fail(SLB_E_CUDA, "slb_interp_create: %s", cudaGetErrorString(e));
     }
-    it->bsptab = nullptr;
+    it->bsptab_dev = nullptr;
+    memset(&it->bsptab, 0, sizeof(it->bsptab));
     if (bs) {
         std::string msg;
         BsplineHost hb;
@@ -441,11 +443,15 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
             return fail(rc, "slb_interp_create: %s", msg.c_str());
         }
         if (it->fast && slb_bspfused_supported(hb.h, hb.n)) {
-            it->bsptab = new BspParamTab();
-            if (!slb_bspfused_fill(it->bsptab, hb.h, hb.n, hb.N, hb.L.data(), hb.U.data(), hb.invd.data(), hb.Ri.data(), hb.G.data(),
-                                   hb.Sinv.data())) {
-                delete it->bsptab;
-                it->bsptab = nullptr;
+            std::vector<double> v((size_t)slb_bspfused_tab_doubles(hb.h, hb.n));
+            slb_bspfused_fill(&it->bsptab, v.data(), hb.h, hb.n, hb.N, hb.L.data(), hb.U.data(), hb.invd.data(), hb.Ri.data(),
+                              hb.G.data(), hb.Sinv.data());
+            cudaError_t e2 = cudaMalloc(&it->bsptab_dev, v.size() * sizeof(double));
+            if (e2 == cudaSuccess) e2 = cudaMemcpy(it->bsptab_dev, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+            if (e2 != cudaSuccess) {
+                if (it->bsptab_dev) cudaFree(it->bsptab_dev);
+                it->bsptab_dev = nullptr;
+                cudaGetLastError();
             }
         }
     }
@@ -459,7 +465,7 @@ extern "C" void slb_interp_destroy(slb_interp* it)
     cudaStreamSynchronize(it->ctx->stream);
     cudaFree(it->coef_dev);
     bspline_free(&it->bsp);
-    delete it->bsptab;
+    if (it->bsptab_dev) cudaFree(it->bsptab_dev);
     delete it;
 }
 
@@ -648,7 +654,7 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
     int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, on_device, &am);
     if (rc) return rc;
     const double* src = g->front;
-    if (bs && it->bsptab && !(flags & SLB_SWEEP_EXACT) && !(g->linesum && dim == 0) && !(omp && dim == 0) && !(imp && dim != 0) &&
+    if (bs && it->bsptab_dev && !(flags & SLB_SWEEP_EXACT) && !(g->linesum && dim == 0) && !(omp && dim == 0) && !(imp && dim != 0) &&
         env_ll("SLB_BSPLINE_FUSED", 1) != 0) {
         // pre-solve + stencil in one pass over HBM (slb_bspfused.cuh): front -> back, then swap
         BspFusedArgs a;
@@ -668,7 +674,10 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         }
         if (imp) a.im = *imp;
         a.linesum = g->linesum;
-        int lrc = slb_bspfused_launch(a, *it->bsptab, it->tab, c->sm_count, c->stream);
+        a.tab_dev = it->bsptab_dev;
+        a.tab = it->bsptab;
+        a.warps = slb_bspfused_warps(it->bsptab.h, v.n, v.inner == 1);
+        int lrc = slb_bspfused_launch(a, it->tab, c->sm_count, c->stream);
         if (lrc != 0) return fail(lrc < 0 ? SLB_E_UNSUPPORTED : SLB_E_CUDA, "slb_sweep: fused B-spline launch failed (%d)", lrc);
         c->launches++;
         return slb_grid_swap(g);

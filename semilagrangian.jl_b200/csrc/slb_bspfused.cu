@@ -5,63 +5,73 @@
 #include <string.h>
 
 #define SLB_BSPF_FOR_H(X) X(1) X(2) X(3) X(4) X(5) X(6)
+#define SLB_BSPF_SMEM_MAX (226 * 1024)   // dynamic shared memory available to one block on sm_100
 
-bool slb_bspfused_supported(int h, int n)
+int slb_bspfused_tab_doubles(int h, int n)
 {
-    if (h < 1 || h > 6) return false;                      // orders 3 .. 13
-    if (n < 2 * h + 2) return false;
-    if ((size_t)n * 33 * sizeof(double) > 200 * 1024) return false;   // one tile of 32 lines per warp in shared memory
     const int N = n - h;
-    return (long long)N * (1 + 4 * h) + h * h <= SLB_BSPF_TAB;
+    return N * (2 * h) + N * (2 * h + 2) + h * h;
 }
 
-bool slb_bspfused_fill(BspParamTab* tab, int h, int n, int N, const double* L, const double* U, const double* invd,
+int slb_bspfused_warps(int h, int n, bool contig)
+{
+    if (h < 1 || h > 6 || n < 2 * h + 2) return 0;   // orders 3 .. 13
+    const size_t tab = ((size_t)slb_bspfused_tab_doubles(h, n) + 1) / 2 * 2 * sizeof(double);
+    const size_t tile = (size_t)n * (contig ? 33 : 32) * sizeof(double);
+    if (tab + tile > SLB_BSPF_SMEM_MAX) return 0;
+    size_t w = (SLB_BSPF_SMEM_MAX - tab) / tile;
+    return (int)(w > 8 ? 8 : w);
+}
+
+bool slb_bspfused_supported(int h, int n) { return slb_bspfused_warps(h, n, true) > 0; }
+
+void slb_bspfused_fill(BspFusedTab* tab, double* v, int h, int n, int N, const double* L, const double* U, const double* invd,
                        const double* Ri, const double* G, const double* Sinv)
 {
-    if (!slb_bspfused_supported(h, n)) return false;
-    memset(tab, 0, sizeof(*tab));
+    const int FR = 2 * h, BR = 2 * h + 2;
     tab->h = h;
     tab->n = n;
     tab->N = N;
-    const int TS = 4 * h + 1;
+    tab->o_bwd = N * FR;
+    tab->o_S = tab->o_bwd + N * BR;
+    tab->ndoubles = tab->o_S + h * h;
     for (int i = 0; i < N; ++i) {
-        double* T = tab->v + (size_t)i * TS;
-        T[0] = invd[i];
+        double* F = v + (size_t)i * FR;
+        double* B = v + tab->o_bwd + (size_t)i * BR;
+        B[0] = invd[i];
         for (int j = 0; j < h; ++j) {
-            T[1 + j] = L[(size_t)i * h + j];
-            T[1 + h + j] = (double)((long double)U[(size_t)i * h + j] * (long double)invd[i]);
-            T[1 + 2 * h + j] = Ri[(size_t)i * h + j];
-            T[1 + 3 * h + j] = G[(size_t)i * h + j];
+            F[j] = L[(size_t)i * h + j];
+            F[h + j] = Ri[(size_t)i * h + j];
+            B[1 + j] = (double)((long double)U[(size_t)i * h + j] * (long double)invd[i]);
+            B[1 + h + j] = G[(size_t)i * h + j];
         }
+        B[2 * h + 1] = 0.0;
     }
-    tab->o_S = N * TS;
-    memcpy(tab->v + tab->o_S, Sinv, (size_t)h * h * sizeof(double));
-    return true;
+    memcpy(v + tab->o_S, Sinv, (size_t)h * h * sizeof(double));
 }
 
 template <int H, bool CONTIG>
-static int launch1(const BspFusedArgs& a, const BspParamTab& tab, const CoefTab& ct, cudaStream_t stream)
+static int launch1(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream)
 {
     auto kern = k_bspline_fused<H, CONTIG>;
-    const size_t smem = (size_t)a.n * (CONTIG ? 33 : 32) * sizeof(double);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    const size_t tab = ((size_t)a.tab.ndoubles + 1) / 2 * 2 * sizeof(double);
+    const size_t smem = tab + (size_t)a.warps * a.n * (CONTIG ? 33 : 32) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
     const long long tiles = (a.nlines + 31) / 32;
-    if (tiles >= 0x7fffffffLL) return -1;
-    kern<<<(unsigned)tiles, 32, smem, stream>>>(a, tab, ct);
+    long long blocks = (tiles + a.warps - 1) / a.warps;
+    if (blocks > sm_count) blocks = sm_count;   // persistent: one block per SM, each warp loops over tiles
+    kern<<<(unsigned)blocks, 32 * a.warps, smem, stream>>>(a, ct);
     return (int)cudaGetLastError();
 }
 
-int slb_bspfused_launch(const BspFusedArgs& a, const BspParamTab& tab, const CoefTab& ct, int sm_count, cudaStream_t stream)
+int slb_bspfused_launch(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream)
 {
-    (void)sm_count;
     const bool contig = (a.inner == 1);
-    switch (tab.h) {
+    switch (a.tab.h) {
 #define X(H) \
     case H:  \
-        return contig ? launch1<H, true>(a, tab, ct, stream) : launch1<H, false>(a, tab, ct, stream);
+        return contig ? launch1<H, true>(a, ct, sm_count, stream) : launch1<H, false>(a, ct, sm_count, stream);
         SLB_BSPF_FOR_H(X)
 #undef X
     }

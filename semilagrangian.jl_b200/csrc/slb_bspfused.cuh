@@ -12,10 +12,12 @@
 //                tile pitch 32; dim 0: lines are contiguous, lanes run along the line and the tile
 //                is stored transposed with pitch 33 -- conflict-free both ways);
 //   2. solve  : thread-per-line bordered banded LU substitution, in place in shared memory
-//               (the formulation of slb_bspline.cuh; 4h+1 FMAs per cell).  All factor tables live
-//               in the KERNEL PARAMETERS (constant bank; every table read is warp-uniform and
-//               costs no load/store-unit slot), which is what makes the thread-per-line
-//               recurrence run at the FP64 pipe's pace instead of L1 latency;
+//               (the formulation of slb_bspline.cuh; 4h+1 FMAs per cell).  The factor tables sit in
+//               shared memory too, one copy per (persistent) block; each row's record is fetched
+//               with 16-byte broadcast loads ONE ROW AHEAD of its use, so the recurrence never
+//               waits for a table read (the first version read them from global memory through L1
+//               and ran at L1 latency; a second one kept them in the kernel parameters, where the
+//               63 uniform registers cannot hold a row ahead);
 //   3. stencil: thread-per-line march with a rotating register window fed from shared memory;
 //               strided dims store each output row straight to HBM (coalesced); dim 0 writes the
 //               outputs back into the tile in place (output i overwrites the oldest window entry,
@@ -30,14 +32,14 @@
 
 #include "slb_sweep.cuh"
 
-// factor tables as kernel parameters, one record of 4h+1 doubles per row i < N:
-//   { invd_i, L[i][0..h), invd_i * U[i][0..h), Ri[i][0..h), G[i][0..h) }   followed by Sinv[h][h]
+// Factor tables (device memory, copied to shared memory by every block):
+//   forward  record i < N : { L[i][0..h), Ri[i][0..h) }                        2h doubles
+//   backward record i < N : { 1/d_i, U[i][0..h)/d_i, G[i][0..h), pad }         2h+2 doubles
+//   Sinv[h][h]
 // (U is pre-scaled by 1/diag so that the backward recurrence is one FMA deep per row)
-#define SLB_BSPF_TAB 3560
-struct BspParamTab {
+struct BspFusedTab {
     int h, n, N;
-    int o_S;
-    double v[SLB_BSPF_TAB];
+    int o_bwd, o_S, ndoubles;   // offsets (doubles) of the backward records and of Sinv; total size
 };
 
 struct BspFusedArgs {
@@ -47,17 +49,23 @@ struct BspFusedArgs {
     long long nlines;
     int n;
     int nc;            // polynomial coefficients per stencil weight
+    int warps;         // warps (tiles in flight) per block
     AlphaMap am;
     OutMap om;         // strided variant: re-shard fused into the stores (plain: kc >= n)
     InMap im;          // contiguous variant: block-major input lines (plain: c == 0)
     double* linesum;   // strided variant, optional: per-line sums of the outputs
+    const double* tab_dev;
+    BspFusedTab tab;
 };
 
-int slb_bspfused_launch(const BspFusedArgs& a, const BspParamTab& tab, const CoefTab& ct, int sm_count, cudaStream_t stream);
+int slb_bspfused_launch(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream);
+// warps per block that fit the shared memory next to the tables; 0: unsupported
+int slb_bspfused_warps(int h, int n, bool contig);
 bool slb_bspfused_supported(int h, int n);
-// fills `tab` from the host factor tables; false when they do not fit the parameter space
-bool slb_bspfused_fill(BspParamTab* tab, int h, int n, int N, const double* L, const double* U, const double* invd,
+// host table in the kernel's layout
+void slb_bspfused_fill(BspFusedTab* tab, double* v, int h, int n, int N, const double* L, const double* U, const double* invd,
                        const double* Ri, const double* G, const double* Sinv);
+int slb_bspfused_tab_doubles(int h, int n);
 
 #ifdef SLB_BSPF_IMPL
 __device__ __forceinline__ void bspf_cp_async8(unsigned smem_dst, const void* gsrc)
@@ -65,21 +73,47 @@ __device__ __forceinline__ void bspf_cp_async8(unsigned smem_dst, const void* gs
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
+template <int NV>
+__device__ __forceinline__ void bspf_ldrec(double (&dst)[NV], const double* src)
+{
+    static_assert(NV % 2 == 0, "records are whole 16-byte words");
+#pragma unroll
+    for (int q = 0; q < NV; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(src + q);
+        dst[q] = v.x;
+        dst[q + 1] = v.y;
+    }
+}
+
 template <int H, bool CONTIG>
-__global__ void __launch_bounds__(32)
-k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__ BspParamTab tab, const __grid_constant__ CoefTab ct)
+__global__ void __launch_bounds__(256, 1)
+k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__ CoefTab ct)
 {
     constexpr int P1 = 2 * H + 2;           // order + 1 stencil points, order = 2h + 1
     constexpr int PITCH = CONTIG ? 33 : 32;
-    extern __shared__ __align__(16) double tile[];
-    __shared__ int s0s[32];
-    const int lane = threadIdx.x;
-    const int n = fa.n, N = tab.N;
-    const long long line0 = (long long)blockIdx.x * 32;
+    constexpr int FR = 2 * H, BR = 2 * H + 2;  // doubles per forward / backward record
+    extern __shared__ __align__(16) double bsm[];
+    __shared__ int s0s_all[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = fa.n, N = fa.tab.N;
+    // ---- factor tables: one copy per block --------------------------------------------------------
+    double* tabs = bsm;
+    for (int i = threadIdx.x; i < fa.tab.ndoubles; i += blockDim.x) tabs[i] = __ldg(fa.tab_dev + i);
+    __syncthreads();
+    const double* tF = tabs;
+    const double* tB = tabs + fa.tab.o_bwd;
+    const double* tS = tabs + fa.tab.o_S;
+    double* tile = bsm + ((fa.tab.ndoubles + 1) & ~1) + (size_t)wid * n * PITCH;
+    int* s0s = s0s_all[wid];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
+    double* col = tile + lane;
+    const long long ntiles = (fa.nlines + 31) / 32;
+
+    for (long long t = (long long)blockIdx.x * fa.warps + wid; t < ntiles; t += (long long)gridDim.x * fa.warps) {
+    const long long line0 = t * 32;
     const long long line = line0 + lane;
     const bool active = line < fa.nlines;
     const long long lc = active ? line : fa.nlines - 1;
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
 
     // ---- 1. load the tile --------------------------------------------------------------------
     long long a = 0, b = 0;
@@ -108,14 +142,14 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
     {
         const double alpha = fa.am.scale * __ldg(fa.am.tab + (CONTIG ? slb_alpha_off(fa.am, 0u, (unsigned)lc)
                                                                       : slb_alpha_off(fa.am, (unsigned)a, (unsigned)b)));
-        double t;
-        slb_split(alpha, n, (P1 - 1) / 2, t, s0);
+        double tt;
+        slb_split(alpha, n, (P1 - 1) / 2, tt, s0);
         const int nc = fa.nc;
 #pragma unroll
         for (int j = 0; j < P1; ++j) w[j] = ct.c[j * SLB_NCMAX + nc - 1];
         for (int k = nc - 2; k >= 0; --k) {
 #pragma unroll
-            for (int j = 0; j < P1; ++j) w[j] = fma(t, w[j], ct.c[j * SLB_NCMAX + k]);
+            for (int j = 0; j < P1; ++j) w[j] = fma(tt, w[j], ct.c[j * SLB_NCMAX + k]);
         }
     }
     if (CONTIG) s0s[lane] = s0;
@@ -124,42 +158,43 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
 
     // ---- 2. bordered banded LU solve, in place, thread per line ---------------------------------
     // Both recurrences are arranged so that the newest dependency enters LAST: the terms that use
-    // older results are summed first (they are ready), the right-hand side is added, and only one
-    // FMA per row waits for the previous row.  Right-hand sides are fetched one group of h rows ahead.
-    constexpr int TS = 4 * H + 1;
-    double* col = tile + lane;
-    const double* tS = tab.v + tab.o_S;
+    // older results are summed first, the right-hand side is added, and only one FMA per row waits
+    // for the previous row.  Right-hand sides are fetched a group of h rows ahead, table records one
+    // row ahead.
     double x2[H];
     {
-        double yw[H], acc[H], un[H];
+        double yw[H], acc[H], un[H], Tn[FR];
 #pragma unroll
         for (int s = 0; s < H; ++s) {
             yw[s] = 0.0;
             acc[s] = 0.0;
             un[s] = s < N ? col[s * PITCH] : 0.0;
         }
+        bspf_ldrec<FR>(Tn, tF);
 #define BSPF_FWD_ROW(r, GUARD)                                                                        \
     {                                                                                                 \
         const int i = i0 + (r);                                                                       \
         if (!(GUARD) || i < N) {                                                                      \
-            const double* T = tab.v + i * TS;                                                         \
+            double T[FR];                                                                             \
+            _Pragma("unroll") for (int q = 0; q < FR; ++q) T[q] = Tn[q];                              \
+            if (!(GUARD) || i + 1 < N) bspf_ldrec<FR>(Tn, tF + (i + 1) * FR);                         \
             double y;                                                                                 \
             if (H >= 2) {                                                                             \
-                double sacc = -T[1 + H - 1] * yw[((r) - H + 2 * H) % H];                              \
+                double sacc = -T[H - 1] * yw[((r) - H + 2 * H) % H];                                  \
                 _Pragma("unroll") for (int j = H - 1; j >= 2; --j)                                    \
-                    sacc = fma(-T[1 + j - 1], yw[((r) - j + 2 * H) % H], sacc);                       \
-                y = fma(-T[1], yw[((r) - 1 + 2 * H) % H], u[(r)] + sacc);                             \
+                    sacc = fma(-T[j - 1], yw[((r) - j + 2 * H) % H], sacc);                           \
+                y = fma(-T[0], yw[((r) - 1 + 2 * H) % H], u[(r)] + sacc);                             \
             } else {                                                                                  \
-                y = fma(-T[1], yw[0], u[(r)]);                                                        \
+                y = fma(-T[0], yw[0], u[(r)]);                                                        \
             }                                                                                         \
             yw[(r)] = y;                                                                              \
-            _Pragma("unroll") for (int q = 0; q < H; ++q) acc[q] = fma(T[1 + 2 * H + q], y, acc[q]);  \
+            _Pragma("unroll") for (int q = 0; q < H; ++q) acc[q] = fma(T[H + q], y, acc[q]);          \
             col[i * PITCH] = y;                                                                       \
         }                                                                                             \
     }
         int i0 = 0;
-        for (; i0 + 2 * H <= N; i0 += H) {  // whole groups, the next group's right-hand sides exist: no guards,
-            double u[H];                    // so that the rows of a group can overlap
+        for (; i0 + 2 * H <= N; i0 += H) {  // whole groups, the next group's right-hand sides exist: no guards
+            double u[H];
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 u[r] = un[r];
@@ -194,30 +229,34 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
         for (int q = 0; q < H; ++q) col[(N + q) * PITCH] = x2[q];
     }
     {
-        double ww[H], un[H];
+        double ww[H], un[H], Tn[BR];
         const int ilast = ((N - 1) / H) * H;
 #pragma unroll
         for (int s = 0; s < H; ++s) {
             ww[s] = 0.0;
             un[s] = ilast + s < N ? col[(ilast + s) * PITCH] : 0.0;
         }
+        bspf_ldrec<BR>(Tn, tB + (N - 1) * BR);
+        // record layout: T[0] = 1/d, T[1..h] = U/d, T[1+h..2h] = G
 #define BSPF_BWD_ROW(r, GUARD)                                                                        \
     {                                                                                                 \
         const int i = i0 + (r);                                                                       \
         if (!(GUARD) || i < N) {                                                                      \
-            const double* T = tab.v + i * TS;                                                         \
-            double v; /* w_i = invd_i * (y_i - sum_j U[i][j-1] w_{i+j}), U pre-scaled by invd_i */    \
+            double T[BR];                                                                             \
+            _Pragma("unroll") for (int q = 0; q < BR; ++q) T[q] = Tn[q];                              \
+            if (i > 0) bspf_ldrec<BR>(Tn, tB + (i - 1) * BR);                                         \
+            double v; /* w_i = (y_i - sum_j U[i][j-1] w_{i+j}) / d_i */                               \
             if (H >= 2) {                                                                             \
-                double sacc = -T[1 + H + H - 1] * ww[((r) + H) % H];                                  \
+                double sacc = -T[1 + H - 1] * ww[((r) + H) % H];                                      \
                 _Pragma("unroll") for (int j = H - 1; j >= 2; --j)                                    \
-                    sacc = fma(-T[1 + H + j - 1], ww[((r) + j) % H], sacc);                           \
-                v = fma(-T[1 + H], ww[((r) + 1) % H], fma(T[0], u[(r)], sacc));                       \
+                    sacc = fma(-T[1 + j - 1], ww[((r) + j) % H], sacc);                               \
+                v = fma(-T[1], ww[((r) + 1) % H], fma(T[0], u[(r)], sacc));                           \
             } else {                                                                                  \
-                v = fma(-T[1 + H], ww[0], T[0] * u[(r)]);                                             \
+                v = fma(-T[1], ww[0], T[0] * u[(r)]);                                                 \
             }                                                                                         \
             ww[(r)] = v;                                                                              \
             double x = v;                                                                             \
-            _Pragma("unroll") for (int q = 0; q < H; ++q) x = fma(-T[1 + 3 * H + q], x2[q], x);       \
+            _Pragma("unroll") for (int q = 0; q < H; ++q) x = fma(-T[1 + H + q], x2[q], x);           \
             col[i * PITCH] = x;                                                                       \
         }                                                                                             \
     }
@@ -234,8 +273,7 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
 #pragma unroll
             for (int r = H - 1; r >= 0; --r) BSPF_BWD_ROW(r, true)
         }
-        // whole groups, counted upwards so that the table index stays in the uniform datapath
-        for (int gq = 1; gq < ngroups; ++gq) {
+        for (int gq = 1; gq < ngroups; ++gq) {  // whole groups
             const int i0 = (ngroups - 1 - gq) * H;
             double u[H];
 #pragma unroll
@@ -383,5 +421,7 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
         }
     }
 #undef BSPF_NEXT
+    __syncwarp();  // the tile is reused by this warp's next iteration
+    }  // persistent loop over tiles
 }
 #endif  // SLB_BSPF_IMPL
