@@ -423,6 +423,7 @@ def main():
     ap.add_argument("--order", type=int, default=7)
     ap.add_argument("--interp", default="lagrange", choices=["lagrange", "bspline_lu", "bspline_fft", "hermite"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true", help="sharded runs: skip the host-buffer end-to-end leg (large grids)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU re-shard: peer stores fused into the sweep (p2p) or NCCL all-to-all")
     args = ap.parse_args()

@@ -96,22 +96,25 @@ def run_distributed(args, B):
     # e2e: host slab in, host slab out, every step (pinned host memory)
     from slb200 import _lib
 
-    host, _hp = _lib.pinned_empty((n**4 // world,))
-    torch.cuda.synchronize()
-    sh.download_local(host)
     e2e_steps = max(1, min(args.steps, 3))
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sh.upload_local(host)       # H2D of this rank's slab (pinned), on the driver's stream
-        step()
-        _ = sh.compute_ee()         # D2H scalar
-        sh.download_local(host)     # D2H of the slab; synchronises
-    dist.barrier()
-    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-    e2e_val = cells_per_step * e2e_steps / float(wall.item()) / 1e9
+    if getattr(args, "no_e2e", False):
+        e2e_val = None
+    else:
+        host, _hp = _lib.pinned_empty((n**4 // world,))
+        torch.cuda.synchronize()
+        sh.download_local(host)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sh.upload_local(host)       # H2D of this rank's slab (pinned), on the driver's stream
+            step()
+            _ = sh.compute_ee()         # D2H scalar
+            sh.download_local(host)     # D2H of the slab; synchronises
+        dist.barrier()
+        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e_val = cells_per_step * e2e_steps / float(wall.item()) / 1e9
 
     if rank == 0:
         peak, peak_src = B.read_peaks()

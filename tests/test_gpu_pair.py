@@ -290,3 +290,42 @@ def test_states_with_ndims_2_space_first_and_translation():
             pass
     assert relerr(g.getdata(), o.data) <= 2e-12 * 6
     assert g.n_fused == 6
+
+
+def test_fused_pair_full_size_properties_128_4():
+    """BASELINE's full size (2D2V 128^4, Lagrange 7), where the oracle is too slow for a point-wise
+    check: (i) integer shifts in both sweeps of a fused pass are an exact 2-D circular shift,
+    (ii) the fused pass equals two sweeps bit for bit, (iii) a slab that contains whole (v1, v2)
+    planes matches the oracle applied to that slab."""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    n = 128
+    rng = np.random.default_rng(20240611)
+    a = [rng.random(n) + 0.5 for _ in range(4)]
+    f = S.dotprod(a)
+    it, oit = S.Lagrange(7), R.Lagrange(7)
+    z = [0, 0, 0, 0]
+    for dA, dB in ((2, 3), (0, 1)):
+        g = DeviceGrid(f)
+        g.sweep_pair(dA, it, np.array([3.0]), z, dB, it, np.array([-5.0]), z)
+        out = g.get()
+        assert np.array_equal(out, np.roll(np.roll(f, -3, axis=dA), 5, axis=dB)), (dA, dB)
+        g.close()
+    # fractional shifts that depend on the other dims like the Vlasov providers' do
+    g1, g2 = DeviceGrid(f), DeviceGrid(f)
+    tE1, tE2 = rng.uniform(-0.6, 0.6, n * n), rng.uniform(-0.6, 0.6, n * n)
+    sE = [1, n, 0, 0]
+    g1.sweep(2, it, tE1, sE)
+    g1.sweep(3, it, tE2, sE)
+    g2.sweep_pair(2, it, tE1, sE, 3, it, tE2, sE)
+    two, fused = g1.get(), g2.get()
+    g1.close()
+    g2.close()
+    assert np.array_equal(two, fused)
+    sl = (slice(40, 44), slice(7, 9), slice(None), slice(None))   # whole (v1, v2) planes of a few x
+    sub = np.asfortranarray(f[sl])
+    t1 = tE1.reshape((n, n), order="F")[sl[0], sl[1]].reshape(-1, order="F")
+    t2 = tE2.reshape((n, n), order="F")[sl[0], sl[1]].reshape(-1, order="F")
+    ref = oracle_sweep(oracle_sweep(sub, 2, oit, t1, [1, 4, 0, 0]), 3, oit, t2, [1, 4, 0, 0])
+    assert relerr(fused[sl], ref) <= 2e-12
