@@ -916,7 +916,7 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     } else {
         gg = 16;  // 128 B rows; smaller only when dim 0 is not a multiple
         while (gg > 1 && (fa.elo % gg != 0 || !slb_fused_supported(P1, false, gg))) gg >>= 1;
-        int64_t want = 2 * env_ll("SLB_FUSED_THREADS", 256) / gg;  // cross outputs per tile
+        int64_t want = 2 * env_ll("SLB_FUSED_THREADS", P1 >= 12 ? 128 : 256) / gg;  // cross outputs per tile (order 11: 188 registers)
         if (want > 2 * SLB_FUSED_MAXTHREADS / gg) want = 2 * SLB_FUSED_MAXTHREADS / gg;
         if (want < 16) want = 16;
         want &= ~(int64_t)1;

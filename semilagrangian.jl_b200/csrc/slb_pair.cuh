@@ -147,7 +147,7 @@ __device__ __forceinline__ void fused_weights(const CoefTab& ct, int nc, double 
 // G > 0: passive points per tile fixed at compile time (CC = false); G == 0: run-time fa.g (CC = true)
 // W16: rows are fetched with 16-byte cp.async (pairs of doubles; the host checks alignment)
 template <int P1, bool EXACT, bool CC, int G, bool W16>
-__global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, (P1 <= 8 ? 2 : 1))  // orders <= 7: 128 registers, two blocks per SM
+__global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, (P1 <= 10 ? 2 : 1))  // orders <= 9: 128 registers, two blocks per SM
 k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ CoefTab ctA, const __grid_constant__ CoefTab ctB)
 {
     constexpr int D = SLB_FUSED_STAGES;
