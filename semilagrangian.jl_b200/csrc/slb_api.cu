@@ -914,7 +914,7 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
             gg = 1;
         }
     } else {
-        gg = 16;  // 128 B rows; smaller only when dim 0 is not a multiple
+        gg = (int)env_ll("SLB_FUSED_G", P1 >= 12 ? 16 : 32);  // 256 B rows (128^4 L7: 0.786 ms vs 0.805 with 128 B); smaller when dim 0 is not a multiple
         while (gg > 1 && (fa.elo % gg != 0 || !slb_fused_supported(P1, false, gg))) gg >>= 1;
         int64_t want = 2 * env_ll("SLB_FUSED_THREADS", P1 >= 12 ? 128 : 256) / gg;  // cross outputs per tile (order 11: 188 registers)
         if (want > 2 * SLB_FUSED_MAXTHREADS / gg) want = 2 * SLB_FUSED_MAXTHREADS / gg;

@@ -14,7 +14,7 @@ bool slb_fused_supported(int P1, bool cc, int g)
 #undef X
     if (!okp) return false;
     if (cc) return g >= 1;
-    return g == 16 || g == 4 || g == 1;
+    return g == 32 || g == 16 || g == 4 || g == 1;
 }
 
 size_t slb_fused_smem_bytes(int nrows_max, int g)
@@ -43,6 +43,7 @@ static int launch2(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, 
         return fa.w16 ? launch1<P1, EXACT, true, 0, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream)
                       : launch1<P1, EXACT, true, 0, false>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
     switch (fa.g) {  // g = 16 and 4 imply even strides: always 16-byte fetches (the host checks the base pointer)
+    case 32: return fa.w16 ? launch1<P1, EXACT, false, 32, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream) : -1;
     case 16: return fa.w16 ? launch1<P1, EXACT, false, 16, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream) : -1;
     case 4: return fa.w16 ? launch1<P1, EXACT, false, 4, true>(fa, ctA, ctB, nblocks, nthreads, smem, stream) : -1;
     case 1: return fa.w16 ? -1 : launch1<P1, EXACT, false, 1, false>(fa, ctA, ctB, nblocks, nthreads, smem, stream);

@@ -21,7 +21,7 @@
 // stencils use the same operation order as k_sweep_strided / k_sweep_contig, so the result is
 // BIT-IDENTICAL to two slb_sweep calls.  Lane order follows the memory-contiguous index:
 // CC = true  (cross dim is dim 0, e.g. x1 x2): lanes run along the cross index;
-// CC = false (dim 0 is passive, e.g. v1 v2)  : lanes run along the passive index (g = 16: 128 B rows).
+// CC = false (dim 0 is passive, e.g. v1 v2)  : lanes run along the passive index (g = 32: 256 B rows).
 // Shifts may differ between the passive points of a tile: the staged row range is the union over
 // the tile (up to SLB_FUSED_SPREAD_MAX extra rows); beyond that the CTA reads its stencil inputs
 // straight from global memory (correct, slower).  alpha_A must not depend on the march index
