@@ -98,9 +98,17 @@ __device__ __forceinline__ void fused_cp_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void fused_st_v2(double* p, double a, double b)
+// predicated streaming stores (no branch around them: the flags are per-thread constants)
+__device__ __forceinline__ void fused_st_v2(bool on, double* p, double a, double b)
 {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    // no "memory" clobber: nothing in the kernel reads the output array, and a clobber would pin
+    // the shared-memory loads of the next rows behind every store
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q st.global.cs.v2.f64 [%0], {%1, %2}; }" ::"l"(p), "d"(a), "d"(b),
+                 "r"((unsigned)on));
+}
+__device__ __forceinline__ void fused_st(bool on, double* p, double a)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.global.cs.f64 [%0], %1; }" ::"l"(p), "d"(a), "r"((unsigned)on));
 }
 
 // one term of slb_dot: same rounding as its EXACT / FMA branches
@@ -244,7 +252,12 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         ol = iout - oq * okc;
     }
     const long long othr = obase + (long long)ac * oscel;
-    double* pob = fa.oblk[oq] + othr;
+    // running output pointer: advances by one march row per emitted output; `oleft` outputs remain
+    // in the current output block (plain layout: until the periodic wrap)
+    double* po = fa.oblk[oq] + othr + (long long)ol * osmel;
+    int oleft = okc - ol;
+    const bool st_pair = CC && W16 && act1;          // 16-byte store of both outputs
+    const bool st_a = act0 && !st_pair, st_b = act1 && !st_pair;
     double winA[P1], winB[P1];           // last order+1 values of T for the two cross outputs
 #pragma unroll
     for (int j = 0; j < P1; ++j) winA[j] = winB[j] = 0.0;
@@ -253,20 +266,18 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     auto emit = [&](double accA, double accB) {
         lsumA += accA;
         lsumB += accB;
-        double* po = pob + (long long)ol * osmel;
-        if (CC && W16) {  // neighbouring outputs are neighbours in memory, 16-byte aligned
-            if (act1)
-                fused_st_v2(po, accA, accB);
-            else if (act0)
-                __stcs(po, accA);
+        if (CC && W16) {  // neighbours in memory, 16-byte aligned: one store; the odd last column is rare
+            fused_st_v2(st_pair, po, accA, accB);
+            if (st_a) __stcs(po, accA);
         } else {
-            if (act0) __stcs(po, accA);
-            if (act1) __stcs(po + oscel, accB);
+            fused_st(st_a, po, accA);
+            fused_st(st_b, po + oscel, accB);
         }
-        if (++ol == okc) {  // next output block (plain layout: wrap around the periodic line)
-            ol = 0;
+        po += osmel;
+        if (--oleft == 0) {  // next output block (plain layout: wrap around the periodic line) -- rare
             oq = (oq + 1) * okc >= nm ? 0 : oq + 1;
-            pob = fa.oblk[oq] + othr;
+            po = fa.oblk[oq] + othr;
+            oleft = okc;
         }
     };
 
@@ -311,14 +322,16 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
                       8 * ((long long)(Pq % fa.elo) * fa.islo + (long long)(Pq / fa.elo) * fa.ishi + (long long)rc * scel);
             sdst[s] = sbase + 8u * (unsigned)(CC ? pe * fa.nrows_max + j : j * g + pe);
         }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) asm volatile("" : "+l"(gsrc[s]));  // keep base + offset folded into one pointer
         const unsigned row_b = 8u * (unsigned)row_elems, ring_b = row_b * R * D;
         // block-uniform bookkeeping of the fetch pipeline (kept in the uniform datapath)
-        int b_iss = fa.march0, k_iss = 0;   // march index / step number of the next row to fetch
         const int ikc = fa.ikc;
-        int il = fa.march0 % ikc;           // its position inside its input block
         const long long smb = 8 * smel, blkjump = 8 * (fa.iblk - (long long)ikc * smel);
-        long long boff = 8 * ((long long)(fa.march0 / ikc) * fa.iblk + (long long)il * smel);  // its byte offset
-        unsigned off_iss = 0;       // byte offset of that row's slot in the ring
+        int b_iss = fa.march0, k_iss = 0;   // march index / step number of the next row to fetch
+        int ileft = ikc - b_iss % ikc;      // rows left in its input block
+        long long boff = 8 * ((long long)(b_iss / ikc) * fa.iblk + (long long)(b_iss % ikc) * smel);  // its byte offset
+        unsigned off_iss = 0;               // byte offset of that row's slot in the ring
         auto issue_stage = [&]() {
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
@@ -333,13 +346,15 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
                         }
                     }
                     boff += smb;
-                    if (++il == ikc) {  // next input block
-                        il = 0;
-                        boff += blkjump;
-                    }
-                    if (++b_iss == nm) {
-                        b_iss = 0;
-                        boff = 0;
+                    ++b_iss;
+                    if (--ileft == 0) {  // input block boundary or periodic wrap -- rare
+                        if (b_iss == nm) {
+                            b_iss = 0;
+                            boff = 0;
+                        } else {
+                            boff += blkjump;
+                        }
+                        ileft = ikc;
                     }
                 }
                 ++k_iss;
