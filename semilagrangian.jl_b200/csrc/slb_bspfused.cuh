@@ -411,11 +411,12 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
             if (lj < fa.nlines) {
                 double* dst = fa.out + lj * n;
                 int pos = s0s[j] + lane;
-                pos %= n;
+                while (pos >= n) pos -= n;
+                const int step = 32 % n;  // == 32 for every n > 32: no division in the loop
                 for (int k = lane; k < n; k += 32) {
-                    dst[k] = tile[pos * PITCH + j];
-                    pos += 32;
-                    pos = pos >= n ? pos % n : pos;
+                    __stcs(dst + k, tile[pos * PITCH + j]);
+                    pos += step;
+                    pos -= pos >= n ? n : 0;
                 }
             }
         }
