@@ -240,6 +240,34 @@ int slb_reduce_sum(slb_ctx* ctx, const double* dev, int64_t n, double* host_out)
  * holds prod(extents[nsp..)) doubles on the device; scale = dsp*dv.  Synchronises. */
 int slb_kinetic_energy(slb_grid* g, int nsp, const double* v_square_dev, double scale, double* host_out);
 
+/* ---- N-D per-point interpolation: the unsplit 2-D solvers ------------------- */
+/* interpolate!(fp, fi, bufdec::Array{OpTuple{2}}, interp_t) (src/interpolation.jl:561-621) and its
+ * closure form interpolate!(fp, fi, dec::Function, interp_t) (:401-429) for N = 2: every point
+ * (i, j) of an [n1, n2] slice has its own displacement (dec[i,j,0], dec[i,j,1]) in grid units,
+ *     d_x = floor(a_x), w^x = tabfct_x(a_x - d_x),
+ *     out[i,j,c] = sum_{a,b} res[(i + d_1 - p_1/2 + a) mod n1, (j + d_2 - p_2/2 + b) mod n2, c] * w^1_a * w^2_b,
+ * res = sol(interp_t, in) (the 1-D B-spline solves along each dim, :48-94).  `ncomp` component
+ * planes share the displacements: 1 for a scalar field, 2 for the OpTuple{2} displacement fields the
+ * Adams-Bashforth time algorithms interpolate (autointerp!/interpbufc!, :626-682).  All arrays are
+ * device pointers, column-major [n1, n2, ncomp] / [n1, n2, 2].  out must not alias in.  work_dev
+ * ([n1, n2, ncomp]) is required when an interpolation is a B-spline and in_dev is then overwritten
+ * by intermediate solves.  SLB_SWEEP_EXACT in flags: rounded products summed in column-major order
+ * (the reference's sum(res[...] .* tab)) instead of FMA chains.
+ * Replaces the single-state branch of advection! (src/advection.jl:607-619). */
+int slb_interp2d_points(slb_ctx* ctx, const slb_interp* it1, const slb_interp* it2, int64_t n1, int64_t n2, int ncomp,
+                        double* in_dev, const double* dec_dev, double* out_dev, double* work_dev, int flags);
+/* dec[i,j,0] = scale_j * tab_j[j], dec[i,j,1] = scale_i * tab_i[i]: the bufcur fill loops of
+ * initcoef! for StdPoisson2d (src/poisson.jl:229-247: tab_j = v nodes, tab_i = E) and the unsplit
+ * rotation (src/rotation.jl:36-54).  Device pointers. */
+int slb_fill_dec2d(slb_ctx* ctx, double* dec_dev, int64_t n1, int64_t n2, const double* tab_j_dev, double scale_j,
+                   const double* tab_i_dev, double scale_i);
+/* out = sum_k coefs[k] * x[k] on device arrays of n doubles, products rounded and summed left to
+ * right: sum(map(k -> c(abcoef, k, ord) * t_bufc[k], 1:ord)) (src/advection.jl:431, :479, :506,
+ * :540).  coefs and the pointer list are host arrays; nterms <= 8; out may be one of the x[k]. */
+int slb_lincomb(slb_ctx* ctx, double* out_dev, int nterms, const double* coefs, const double* const* x_dev, int64_t n);
+/* device-to-device copy on the context's stream (copy(buf), fmr .= to in src/interpolation.jl:636-655) */
+int slb_memcpy_d2d(slb_ctx* ctx, void* dst_dev, const void* src_dev, int64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,6 +403,60 @@ void orc_sol_line(const orc_interp *it, double *X, const double *fi)
 }
 
 /* ------------------------------------------------------------------------------------
+ * src/interpolation.jl:561-621 (and its closure twin :401-429), N = 2:
+ * interpolate!(fp, fi, bufdec::Array{OpTuple{2}}, interp_t).  `res` = sol(interp_t, fi) is
+ * done by the caller (per dim, src/interpolation.jl:48-94).  Per point ind = (i, j):
+ *     dint, tab = getprecal(cache, bufdec[ind])          :345-353: dint = Int.(floor.(alpha)),
+ *                                                         tab = dotprod(getprecal per dim) (:112-118)
+ *     deb_i = dint .+ decall .+ ind.I, decall = (5sz + origin) % sz + sz, origin = -div(order, 2)
+ *     fp[ind] = sum(res[tabmod[1][deb:end], tabmod[2][deb:end]] .* tab)
+ * tab[a, b] = wA[a] * wB[b] (rounded); the products res .* tab are rounded, then summed in
+ * column-major order (a fastest).  Julia's sum of a (p+1)^2 array is a plain loop below 1024
+ * elements; @simd reassociation is unpinned (see the header).
+ * Arrays: res, fp [n1, n2, ncomp] column-major (ncomp planes = the components of an OpTuple
+ * field), dec [n1, n2, 2].  fp must not alias res.
+ * ---------------------------------------------------------------------------------- */
+void orc_interpolate_points2d(const orc_interp *itA, const orc_interp *itB, double *fp, const double *res,
+                              const double *dec, long n1, long n2, int ncomp, int nthreads)
+{
+    const int pA = itA->order + 1, pB = itB->order + 1;
+    const long plane = n1 * n2;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+    for (long j = 0; j < n2; ++j) {
+        double wA[ORC_MAXP], wB[ORC_MAXP], tA, tB;
+        double tab[ORC_MAXP * ORC_MAXP];
+        for (long i = 0; i < n1; ++i) {
+            long idx = i + n1 * j;
+            long dA = orc_split_alpha(dec[idx], &tA);
+            long dB = orc_split_alpha(dec[plane + idx], &tB);
+            orc_getprecal(itA->coef, pA, itA->nc, tA, wA);
+            orc_getprecal(itB->coef, pB, itB->nc, tB, wB);
+            for (int b = 0; b < pB; ++b)
+                for (int a = 0; a < pA; ++a) tab[a + pA * b] = wA[a] * wB[b];
+            long ia0 = modn(i + dA - itA->order / 2, n1);
+            long jb0 = modn(j + dB - itB->order / 2, n2);
+            for (int c = 0; c < ncomp; ++c) {
+                const double *r = res + (size_t)c * plane;
+                double s = 0.0;
+                long jb = jb0;
+                for (int b = 0; b < pB; ++b) {
+                    long ia = ia0;
+                    for (int a = 0; a < pA; ++a) {
+                        double prod = r[ia + n1 * jb] * tab[a + pA * b];
+                        s = (a == 0 && b == 0) ? prod : s + prod;
+                        if (++ia == n1) ia = 0;
+                    }
+                    if (++jb == n2) jb = 0;
+                }
+                fp[(size_t)c * plane + idx] = s;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------
  * permutedims! with the advected dim first (src/advection.jl:372-376) and back
  * (:385).  data is column-major with extents ext[0..nd); view = [inner, n, outer].
  *   f[k + n*(a + inner*b)] = data[a + inner*(k + n*b)]

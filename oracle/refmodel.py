@@ -187,6 +187,10 @@ def invperm(p):
     return q
 
 
+# src/advection.jl:2  @enum TimeAlgorithm
+NoTimeAlg, ABTimeAlg_ip, ABTimeAlg_new, ABTimeAlg_init = 1, 2, 3, 4
+
+
 class StateAdv:
     def __init__(self, ind, perm, ndims, stcoef, isconstdec):
         self.ind, self.perm, self.invp = ind, list(perm), invperm(perm)
@@ -196,8 +200,12 @@ class StateAdv:
 class Advection:
     """src/advection.jl:73-141"""
 
-    def __init__(self, t_mesh, t_interp, dt_base, states, tab_coef=None, nthreads=1):
+    def __init__(self, t_mesh, t_interp, dt_base, states, tab_coef=None, nthreads=1, timealg=NoTimeAlg, ordalg=None):
         N = len(t_mesh)
+        # :96-97 timealg::TimeAlgorithm = NoTimeAlg, ordalg::Int = timealg != NoTimeAlg ? 4 : 0
+        self.timealg = timealg
+        self.ordalg = (4 if timealg != NoTimeAlg else 0) if ordalg is None else int(ordalg)
+        self.abcoef = tables.abcoef_rat(self.ordalg + 1)  # :136 ABcoef(ordalg + 1)
         if len(t_interp) != N:
             raise ValueError(f"size of vector of Interpolation must be equal to N={N}")
         self.sizeall = tuple(len(m) for m in t_mesh)
@@ -229,10 +237,13 @@ class Advection:
 class AdvectionData:
     """src/advection.jl:229-313 (state + data); advection! is `advection(advd)` below."""
 
-    def __init__(self, adv, data, parext, time_init=0.0):
+    def __init__(self, adv, data, parext, time_init=0.0, initdatas=None):
         if tuple(data.shape) != adv.sizeall:
             raise ValueError(f"size(data)={data.shape} it must be {adv.sizeall}")
         self.adv = adv
+        self.bufcur = None          # :241 bufcur (missing): per-point displacement field [sizeall..., N]
+        self.t_bufc = []            # :242 t_bufc: history of displacement fields (AB time algorithms)
+        self.initdatas = initdatas  # :243
         self.state_gen = 1
         self.time_cur = float(time_init)
         self.data = np.array(data, dtype=np.float64, order="F", copy=True)  # :264-267
@@ -328,7 +339,9 @@ def advection(advd):
     adv = advd.adv
     st = advd.getst()
     if not st.isconstdec:
-        raise NotImplementedError("oracle covers const-shift states (SURVEY.md 8a)")
+        from . import unsplit2d
+
+        return unsplit2d.advection_single_state(advd)
     if st.ndims != 1:
         return _advection_nd(advd)
     interp = advd.getinterp()[0]

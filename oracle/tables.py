@@ -93,6 +93,24 @@ def lagrange_tabfct_rat(order):
     return [getpolylagrange(i, order, origin) for i in range(order + 1)]
 
 
+
+def p_integrate(a):
+    """Polynomials.integrate: antiderivative with zero constant term"""
+    return p_trim([Fraction(0)] + [Fraction(c) / (i + 1) for i, c in enumerate(a)])
+
+
+def abcoef_rat(ordermax):
+    """src/lagrange.jl:74-88  ABcoef(ordermax): tab[i, j] = _c(i-1, j-1) for i <= j, with
+    _c(k, n) = P(0) - P(-1), P = integrate(_getpolylagrange(k, n, 0)): the Adams-Bashforth
+    weights (integral over [-1, 0] of the Lagrange basis on the nodes 0..n).  Returned 0-based:
+    tab[i][j] (Fraction), zero above the diagonal."""
+    tab = [[Fraction(0)] * ordermax for _ in range(ordermax)]
+    for j in range(1, ordermax + 1):
+        for i in range(1, j + 1):
+            P = p_integrate(getpolylagrange(i - 1, j - 1, 0))
+            tab[i - 1][j - 1] = p_eval(P, Fraction(0)) - p_eval(P, Fraction(-1))
+    return tab
+
 # --------------------------------------------------------------------------------------
 # cardinal B-spline -- src/spline.jl:6-97
 # A Spline is a list of polynomial pieces; piece i is valid on [i, i+1).

@@ -2,6 +2,7 @@
 // routine the kernels run), callable from tests/ through ctypes without a GPU.
 // Not part of libslb200.so's ABI: built as a separate test helper (lib/libslb200_hosttest.so).
 #include "slb_bspline.cuh"
+#include "slb_points.cuh"
 
 extern "C" int slbt_bspline_solve_host(int order, long long n, const double* node_vals, const double* b, double* x)
 {
@@ -21,5 +22,34 @@ extern "C" int slbt_bspline_solve_host(int order, long long n, const double* nod
 #undef X
         default: return SLB_E_UNSUPPORTED;
     }
+    return 0;
+}
+
+// Host run of the per-point 2-D interpolation body (slb_point_eval, the code k_interp2d_points runs
+// per thread) over a whole [n1, n2, ncomp] field.  coefA / coefB: (order+1) x nc rows, row-major.
+// templated != 0 exercises the unrolled instantiation (needs equal orders, order + 1 <= 14).
+extern "C" int slbt_points_host(const double* res, const double* dec, double* out, int n1, int n2, int ncomp, int pA, int ncA,
+                                const double* coefA, int pB, int ncB, const double* coefB, int exact, int templated)
+{
+    PointsArgs pa;
+    pa.res = res; pa.dec = dec; pa.out = out;
+    pa.n1 = n1; pa.n2 = n2; pa.ncomp = ncomp;
+    pa.pA = pA; pa.pB = pB; pa.ncA = ncA; pa.ncB = ncB;
+    if (pA > SLB_POINTS_MAXP1 || pB > SLB_POINTS_MAXP1) return SLB_E_ARG;
+    for (int j = 0; j < n2; ++j)
+        for (int i = 0; i < n1; ++i) {
+            if (templated) {
+                if (pA != pB) return SLB_E_ARG;
+                switch (pA) {
+#define X(P) case P: if (exact) slb_point_eval<P, true>(pa, coefA, ncA, coefB, ncB, i, j); else slb_point_eval<P, false>(pa, coefA, ncA, coefB, ncB, i, j); break;
+                    X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
+#undef X
+                    default: return SLB_E_UNSUPPORTED;
+                }
+            } else if (exact)
+                slb_point_eval<0, true>(pa, coefA, ncA, coefB, ncB, i, j);
+            else
+                slb_point_eval<0, false>(pa, coefA, ncA, coefB, ncB, i, j);
+        }
     return 0;
 }

@@ -18,6 +18,7 @@
 #include "slb_bspline.cuh"
 #include "slb_bspfused.cuh"
 #include "slb_field.cuh"
+#include "slb_points.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -1363,4 +1364,115 @@ extern "C" int slb_vp_field_solve(slb_poisson* p, const double* f_dev, int64_t n
     k_charge_partial<<<grid, block, 0, c->stream>>>(f_dev, ns, nv, chunk, partial);
     LAUNCH_CHECK(c);
     return field_from_partial(p, partial, (int)nchunk, dv, 1, rho_dev, E_dev);
+}
+
+// ------------------------------------------------------------------------------------------
+// N-D per-point interpolation (unsplit 2-D solvers) and the small array
+// operations of the Adams-Bashforth time algorithms
+// ------------------------------------------------------------------------------------------
+extern "C" int slb_memcpy_d2d(slb_ctx* c, void* dst, const void* src, int64_t bytes)
+{
+    if (!c || !dst || !src || bytes < 0) return fail(SLB_E_ARG, "slb_memcpy_d2d: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return SLB_OK;
+}
+
+template <bool EXACT>
+static void launch_points(slb_ctx* c, const PointsArgs& pa, const slb_interp* itA, const slb_interp* itB)
+{
+    dim3 grid((unsigned)((pa.n1 + 127) / 128), (unsigned)pa.n2);
+    if (itA->fast && itB->fast && itA->order == itB->order) {
+        switch (pa.pA) {
+#define X(P) case P: k_interp2d_points<P, EXACT><<<grid, 128, 0, c->stream>>>(pa, itA->tab, itB->tab); return;
+            SLB_FOR_P1(X)
+#undef X
+        }
+    }
+    k_interp2d_points_generic<EXACT><<<grid, 128, 0, c->stream>>>(pa, itA->coef_dev, itB->coef_dev);
+}
+
+extern "C" int slb_interp2d_points(slb_ctx* c, const slb_interp* it1, const slb_interp* it2, int64_t n1, int64_t n2,
+                                   int ncomp, double* in_dev, const double* dec_dev, double* out_dev, double* work_dev,
+                                   int flags)
+{
+    if (!c || !it1 || !it2 || !in_dev || !dec_dev || !out_dev) return fail(SLB_E_ARG, "slb_interp2d_points: NULL argument");
+    if (n1 < 1 || n2 < 1 || n1 > 0x7fffffffLL || n2 > 65535 || ncomp < 1 || ncomp > 16)
+        return fail(SLB_E_ARG, "slb_interp2d_points: extents (%lld, %lld) x %d components out of range", (long long)n1, (long long)n2, ncomp);
+    if (in_dev == out_dev) return fail(SLB_E_ARG, "slb_interp2d_points: fp and fi must not alias");
+    if (it1->order + 1 > SLB_POINTS_MAXP1 || it2->order + 1 > SLB_POINTS_MAXP1)
+        return fail(SLB_E_ARG, "slb_interp2d_points: order + 1 must not exceed %d", SLB_POINTS_MAXP1);
+    const slb_interp* its[2] = {it1, it2};
+    const int64_t ns[2] = {n1, n2};
+    bool bs[2];
+    for (int x = 0; x < 2; ++x) {
+        bs[x] = (its[x]->kind == SLB_BSPLINE_LU || its[x]->kind == SLB_BSPLINE_FFT);
+        if (bs[x] && its[x]->n != ns[x])
+            return fail(SLB_E_ARG, "slb_interp2d_points: B-spline object %d built for n=%lld, extent is %lld", x + 1,
+                        (long long)its[x]->n, (long long)ns[x]);
+    }
+    if ((bs[0] || bs[1]) && (!work_dev || work_dev == in_dev || work_dev == out_dev))
+        return fail(SLB_E_ARG, "slb_interp2d_points: B-spline interpolations need a distinct work buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // res = sol(interp_t, fi): the 1-D solves along each dim, src/interpolation.jl:48-94
+    const double* res = in_dev;
+    if (bs[0]) {
+        int rc = bspline_presolve(c->stream, &it1->bsp, res, work_dev, 1, (int)n1, n2 * ncomp, &c->launches);
+        if (rc) return fail(rc, "slb_interp2d_points: pre-solve along dim 1 failed: %s", cudaGetErrorString(cudaGetLastError()));
+        res = work_dev;
+    }
+    if (bs[1]) {
+        double* dst = (res == in_dev) ? work_dev : in_dev;
+        int rc = bspline_presolve(c->stream, &it2->bsp, res, dst, n1, (int)n2, ncomp, &c->launches);
+        if (rc) return fail(rc, "slb_interp2d_points: pre-solve along dim 2 failed: %s", cudaGetErrorString(cudaGetLastError()));
+        res = dst;
+    }
+    PointsArgs pa;
+    pa.res = res;
+    pa.dec = dec_dev;
+    pa.out = out_dev;
+    pa.n1 = (int)n1;
+    pa.n2 = (int)n2;
+    pa.ncomp = ncomp;
+    pa.pA = it1->order + 1;
+    pa.pB = it2->order + 1;
+    pa.ncA = it1->nc;
+    pa.ncB = it2->nc;
+    if (flags & SLB_SWEEP_EXACT)
+        launch_points<true>(c, pa, it1, it2);
+    else
+        launch_points<false>(c, pa, it1, it2);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+extern "C" int slb_fill_dec2d(slb_ctx* c, double* dec_dev, int64_t n1, int64_t n2, const double* tab_j_dev, double scale_j,
+                              const double* tab_i_dev, double scale_i)
+{
+    if (!c || !dec_dev || !tab_j_dev || !tab_i_dev) return fail(SLB_E_ARG, "slb_fill_dec2d: NULL argument");
+    if (n1 < 1 || n2 < 1 || n1 > 0x7fffffffLL || n2 > 65535) return fail(SLB_E_ARG, "slb_fill_dec2d: extents out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    dim3 grid((unsigned)((n1 + 127) / 128), (unsigned)n2);
+    k_fill_dec2d<<<grid, 128, 0, c->stream>>>(dec_dev, (int)n1, (int)n2, tab_j_dev, scale_j, tab_i_dev, scale_i);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+extern "C" int slb_lincomb(slb_ctx* c, double* out_dev, int nterms, const double* coefs, const double* const* x_dev, int64_t n)
+{
+    if (!c || !out_dev || !coefs || !x_dev || n < 1) return fail(SLB_E_ARG, "slb_lincomb: bad argument");
+    if (nterms < 1 || nterms > SLB_LINCOMB_MAX) return fail(SLB_E_ARG, "slb_lincomb: nterms=%d not in [1,%d]", nterms, SLB_LINCOMB_MAX);
+    LincombArgs la;
+    memset(&la, 0, sizeof(la));
+    la.nterms = nterms;
+    for (int k = 0; k < nterms; ++k) {
+        if (!x_dev[k]) return fail(SLB_E_ARG, "slb_lincomb: x_dev[%d] is NULL", k);
+        la.coef[k] = coefs[k];
+        la.x[k] = x_dev[k];
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    k_lincomb<<<blocks, 256, 0, c->stream>>>(out_dev, n, la);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
 }

@@ -14,7 +14,10 @@ from .splitting import (nosplit, standardsplit, strangsplit, magicsplit, triplej
                         hamsplit_3_11)
 from .advection import (Advection, AdvectionData, AbstractExtDataAdv, StateAdv, advection, getdata, sizeall,
                         sweep, sweep_pair, modone, invperm)
-from .poisson import (PoissonVar, getpoissonvar, compute_ee, compute_ke, getenergy, getenergyall, dotprod)
+from .poisson import (PoissonVar, getpoissonvar, compute_ee, compute_ke, getenergy, getenergyall, dotprod,
+                      StdPoisson, StdPoisson2d)
+from .unsplit2d import (NoTimeAlg, ABTimeAlg_ip, ABTimeAlg_new, ABTimeAlg_init, DeviceField, interpolate_points,
+                        autointerp, interpbufc, abcoef)
 from .rotation import RotationVar, getrotationvar
 from .translation import TranslationVar, gettranslationvar
-from .interpolate import interpolate, interpolate_lines, sol
+from .interpolate import interpolate, interpolate_lines, interpolate_nd, sol

@@ -67,6 +67,11 @@ SIGNATURES = [
     ("slb_reduce_sumsq", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
     ("slb_reduce_sum", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
     ("slb_kinetic_energy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, c_double_p]),
+    ("slb_interp2d_points", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int]),
+    ("slb_fill_dec2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_double]),
+    ("slb_lincomb", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_void_pp, C.c_int64]),
+    ("slb_memcpy_d2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 ]
 
 SLB_SWEEP_EXACT = 1

@@ -22,6 +22,8 @@ import numpy as np
 from . import _lib
 from .interp import HERMITE, LAGRANGE
 from .splitting import strangsplit
+from . import unsplit2d
+from .unsplit2d import NoTimeAlg
 
 
 def modone(ind, n):
@@ -72,8 +74,17 @@ class Advection:
     """Advection(t_mesh, t_interp, dt_base, states; tab_coef=strangsplit(dt_base))
     -- src/advection.jl:73-141.  `states` = [(perm, ndims, stcoef, isconstdec), ...]."""
 
-    def __init__(self, t_mesh, t_interp, dt_base, states, tab_coef=None, ctx=None):
+    def __init__(self, t_mesh, t_interp, dt_base, states, tab_coef=None, ctx=None, timealg=NoTimeAlg, ordalg=None):
         N = len(t_mesh)
+        # timealg::TimeAlgorithm = NoTimeAlg, ordalg = timealg != NoTimeAlg ? 4 : 0, abcoef = ABcoef(ordalg + 1)
+        # (src/advection.jl:96-97, :136)
+        if timealg not in (unsplit2d.NoTimeAlg, unsplit2d.ABTimeAlg_ip, unsplit2d.ABTimeAlg_new, unsplit2d.ABTimeAlg_init):
+            raise ValueError(f"unknown timealg {timealg}")
+        self.timealg = timealg
+        self.ordalg = (4 if timealg != NoTimeAlg else 0) if ordalg is None else int(ordalg)
+        if timealg != NoTimeAlg and not (1 <= self.ordalg <= 7):
+            raise ValueError(f"ordalg={self.ordalg} must be in 1..7 for the Adams-Bashforth time algorithms")
+        self.abcoef = unsplit2d.abcoef(self.ordalg + 1)
         if len(t_interp) != N:
             raise ValueError(f"size of vector of Interpolation must be equal to N={N}")
         self.N = N
@@ -115,7 +126,7 @@ class AdvectionData:
     """AdvectionData(adv, data, parext; time_init=0) -- src/advection.jl:229-313.
     Copies `data` to the device (the reference copies it too, :264-267)."""
 
-    def __init__(self, adv, data, parext, time_init=0.0, ctx=None):
+    def __init__(self, adv, data, parext, time_init=0.0, ctx=None, initdatas=None):
         data = np.asarray(data)
         if tuple(data.shape) != adv.sizeall:
             raise ValueError(f"size(data)={tuple(data.shape)} it must be {adv.sizeall}")
@@ -125,6 +136,11 @@ class AdvectionData:
         self.time_cur = float(time_init)
         self.parext = parext
         self.flags = 0
+        # per-point displacement field (bufcur), its history (t_bufc) and the start-up data of
+        # ABTimeAlg_init (initdatas): src/advection.jl:241-243
+        self.bufcur = None
+        self.t_bufc = []
+        self.initdatas = initdatas
         h = C.c_void_p()
         _lib.check(_lib.lib().slb_grid_create(self.ctx.h, adv.N, _lib.i64(adv.sizeall), C.byref(h)))
         self.grid = h
@@ -163,6 +179,29 @@ class AdvectionData:
         assert out.flags.f_contiguous and out.dtype == np.float64
         _lib.check(_lib.lib().slb_grid_download(self.grid, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def data_field(self):
+        """the current f of a 2-D grid as a (non-owning) device field"""
+        n1, n2 = self.adv.sizeall
+        return unsplit2d.DeviceField.view(self.ctx, n1, n2, 1, C.c_void_p(_lib.lib().slb_grid_front(self.grid)))
+
+    def interpolate_data(self):
+        """data <- interpolate!(f, data, bufcur, t_interp) (src/advection.jl:607-619, :703): front ->
+        back with the per-point kernel, then the grid's buffers swap roles"""
+        L = _lib.lib()
+        n1, n2 = self.adv.sizeall
+        back = unsplit2d.DeviceField.view(self.ctx, n1, n2, 1, C.c_void_p(L.slb_grid_back(self.grid)))
+        its = self.adv.t_interp
+        h1, h2 = its[0].handle(self.ctx, n1), its[1].handle(self.ctx, n2)
+        work = back.like() if any(unsplit2d._is_bspline(it) for it in its) else None
+        try:
+            _lib.check(L.slb_interp2d_points(self.ctx.h, h1, h2, n1, n2, 1, self.data_field().ptr, self.bufcur.ptr, back.ptr,
+                                             work.ptr if work is not None else None, int(self.flags)))
+        finally:
+            if work is not None:
+                work.free()
+        _lib.check(L.slb_grid_swap(self.grid))
+        self._linesum_dim = None
 
     def points_dev(self, dim0):
         p = self._points_dev.get(dim0)
@@ -207,6 +246,10 @@ class AdvectionData:
         if self._linesum is not None:
             self.ctx.free(self._linesum)
             self._linesum = None
+        for fld in [self.bufcur] + list(self.t_bufc):
+            if fld is not None:
+                fld.free()
+        self.bufcur, self.t_bufc = None, []
         if hasattr(self.parext, "close"):
             self.parext.close()
 
@@ -349,9 +392,13 @@ def advection(advd):
     both.  getdata / compute_ke / any charge density flush a recorded stage first, so every
     observable value is the one the reference's stage-by-stage execution produces."""
     st = advd.getst()
-    if not st.isconstdec or st.ndims > 2:
+    if not st.isconstdec:
+        return unsplit2d.advection_single_state(advd)
+    if advd.adv.timealg != NoTimeAlg:
+        raise NotImplementedError("the Adams-Bashforth time algorithms drive states with per-point shifts only")
+    if st.ndims > 2:
         raise NotImplementedError(
-            "only const-shift states with ndims <= 2 are on the B200 path (SURVEY.md 8a/8f)"
+            "const-shift states with ndims <= 2 are on the B200 path (SURVEY.md 8a/8f)"
         )
     if st.ndims == 2:
         return _advection_2d(advd)

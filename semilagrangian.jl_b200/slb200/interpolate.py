@@ -47,6 +47,41 @@ def interpolate(fp, fi, dec, interp, ctx=None, flags=0):
     return None
 
 
+def interpolate_nd(fp, fi, dec, interp_t, ctx=None, flags=0):
+    """interpolate!(fp, fi, dec, interp_t) for N = 2 with per-point shifts -- src/interpolation.jl:401-429
+    (dec a function of the 0-based index tuple) and :561-621 (dec an [n1, n2, 2] array of shifts in
+    grid units, the OpTuple field).  fi: [n1, n2] or [n1, n2, ncomp] host array; fp receives the
+    result.  Host buffers in and out; the arithmetic runs in slb_interp2d_points."""
+    from .unsplit2d import DeviceField, interpolate_points
+
+    ctx = ctx or _lib.default_context()
+    fi = np.asarray(fi, dtype=np.float64)
+    if fp is fi:
+        raise ValueError("fp and fi must not alias")
+    if len(interp_t) != fi.ndim and not (fi.ndim == 3 and len(interp_t) == 2):
+        raise ValueError(f"The number of Interpolation {len(interp_t)} is different of N={fi.ndim}")
+    n1, n2 = fi.shape[:2]
+    if callable(dec):
+        d = np.empty((n1, n2, 2), order="F")
+        for j in range(n2):
+            for i in range(n1):
+                d[i, j, :] = dec((i, j))
+        dec = d
+    dec = np.asarray(dec, dtype=np.float64)
+    if dec.shape != (n1, n2, 2):
+        raise ValueError(f"dec must have shape {(n1, n2, 2)}")
+    src = DeviceField.from_host(ctx, fi)
+    dfl = DeviceField.from_host(ctx, dec)
+    dst = src.like()
+    try:
+        interpolate_points(dst, src, dfl, interp_t, flags)
+        fp[...] = dst.to_host()
+    finally:
+        for f in (src, dfl, dst):
+            f.free()
+    return None
+
+
 def sol(interp, b, ctx=None):
     """sol(interp, b) -- src/interpolation.jl:40, src/bsplinelu.jl:282-284, src/bsplinefft.jl:49-51;
     b: vector or [n, nlines] array (lines along axis 0)."""

@@ -13,6 +13,10 @@ import numpy as np
 from . import _lib
 from .advection import AbstractExtDataAdv
 from .mesh import vec_k_fft
+from .unsplit2d import DeviceField
+
+# @enum TypePoisson, src/poisson.jl:2
+StdPoisson, StdPoisson2d, StdABp = 1, 2, 3
 
 
 def _get_fctv_k_imag(adv):
@@ -48,10 +52,17 @@ def dotprod(vs):
 
 
 class PoissonVar(AbstractExtDataAdv):
-    """getpoissonvar(adv): PoissonConst + PoissonVar, StdPoisson (src/poisson.jl:35-107)."""
+    """getpoissonvar(adv; type): PoissonConst + PoissonVar (src/poisson.jl:35-107).  type =
+    StdPoisson: split sweeps (initcoef! :164-205); StdPoisson2d: one unsplit 2-D state with per-point
+    shifts (initcoef! :229-247)."""
 
-    def __init__(self, adv, ctx=None):
+    def __init__(self, adv, ctx=None, type=StdPoisson):  # noqa: A002 (the reference's keyword)
         N = adv.N
+        if type not in (StdPoisson, StdPoisson2d):
+            raise ValueError("TypePoisson must be StdPoisson or StdPoisson2d (StdABp has no initcoef! in the reference)")
+        if type == StdPoisson2d and N != 2:
+            raise ValueError("StdPoisson2d needs a 1D1V grid")
+        self.type = type
         if N % 2 != 0:
             raise ValueError(f"N={N} must be a multiple of 2")
         self.adv = adv
@@ -142,8 +153,23 @@ class PoissonVar(AbstractExtDataAdv):
         st = advd.getst()
         return self.isvelocity(advd) and (self.Nsp + 1) in st.perm[: st.ndims]
 
+    def _initcoef_2d(self, advd):
+        """initcoef!(pv::PoissonVar{..,StdPoisson2d}, advd) -- src/poisson.jl:229-247:
+        bufcur[i, j] = ((-dt/dx) * v_j, (dt/dv) * E_i), filled on the device from the resident E and
+        velocity nodes."""
+        adv = advd.adv
+        self.field_solve(advd)
+        dt = advd.getcur_t()
+        n1, n2 = adv.sizeall
+        if advd.bufcur is None:
+            advd.bufcur = DeviceField(self.ctx, n1, n2, 2)
+        _lib.check(_lib.lib().slb_fill_dec2d(self.ctx.h, advd.bufcur.ptr, n1, n2, advd.points_dev(1), -dt / adv.t_mesh[0].step,
+                                             self.E_dev[0], dt / adv.t_mesh[1].step))
+
     def initcoef(self, advd):
         """initcoef!(pv, advd) -- src/poisson.jl:164-205"""
+        if self.type == StdPoisson2d:
+            return self._initcoef_2d(advd)
         st = advd.getst()
         adv = advd.adv
         dt = advd.getcur_t()
@@ -199,8 +225,9 @@ class PoissonVar(AbstractExtDataAdv):
             pass
 
 
-def getpoissonvar(adv, ctx=None):
-    return PoissonVar(adv, ctx=ctx)
+def getpoissonvar(adv, ctx=None, type=StdPoisson, typeadd=0):  # noqa: A002, ARG001
+    """getpoissonvar(adv; type = StdPoisson, typeadd = 0) -- src/poisson.jl:100-103"""
+    return PoissonVar(adv, ctx=ctx, type=type)
 
 
 def compute_ee(advd):

@@ -1,5 +1,7 @@
 """Rotation displacement provider -- host mirror of src/rotation.jl:4-31, :59-71."""
+from . import _lib
 from .advection import AbstractExtDataAdv
+from .unsplit2d import ABTimeAlg_ip, ABTimeAlg_new, DeviceField, NoTimeAlg
 
 
 class RotationVar(AbstractExtDataAdv):
@@ -8,7 +10,25 @@ class RotationVar(AbstractExtDataAdv):
             raise ValueError("rotation needs a 2-D grid")
         self.decfl = None
 
+    def _initcoef_2d(self, advd):
+        """initcoef!(pv::RotationVar{T,2}, ::AdvectionData{T,2,timeopt,ABTimeAlg_ip|ABTimeAlg_new})
+        -- src/rotation.jl:36-54: bufcur[i, j] = (-dt/dx1 * x2_j, dt/dx2 * x1_i)"""
+        adv = advd.adv
+        n1, n2 = adv.sizeall
+        dt = advd.getcur_t()
+        if advd.bufcur is None:
+            advd.bufcur = DeviceField(advd.ctx, n1, n2, 2)
+        _lib.check(_lib.lib().slb_fill_dec2d(advd.ctx.h, advd.bufcur.ptr, n1, n2, advd.points_dev(1), -dt / adv.t_mesh[0].step,
+                                             advd.points_dev(0), dt / adv.t_mesh[1].step))
+
     def initcoef(self, advd):
+        if advd.adv.timealg in (ABTimeAlg_ip, ABTimeAlg_new):
+            return self._initcoef_2d(advd)
+        if advd.adv.timealg != NoTimeAlg:
+            raise NotImplementedError("the reference defines no rotation initcoef! for this time algorithm (src/rotation.jl:21-42)")
+        return self._initcoef_1d(advd)
+
+    def _initcoef_1d(self, advd):
         """decfl = sign * dt_cur / step(mesh_cur) * mesh_other.points  (src/rotation.jl:21-31):
         kept as (scale, device-resident points) so nothing is uploaded per stage."""
         st_cur, st_other = advd.getst().perm
