@@ -1,0 +1,80 @@
+"""Host sequencing logic of the unsplit 2-D layer (slb200/unsplit2d.py, the StdPoisson2d / rotation
+providers, interpolate_nd) on a machine WITHOUT a GPU: libslb200's entry points are replaced by the
+test double of tests/fake_device.py (host memory + the CUDA per-point body compiled for the host), the
+results are compared with the oracle.  The same comparisons run against the real library in
+tests/test_gpu_unsplit2d.py."""
+import numpy as np
+import pytest
+
+import fake_device
+from helpers import relerr
+from oracle import refmodel as R, unsplit2d as U
+import test_gpu_unsplit2d as G
+from test_oracle_unsplit2d import poisson2d_run
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    return fake_device.install(monkeypatch)
+
+
+def test_interpolate_nd_seam(fake):
+    import slb200 as S
+
+    rng = np.random.default_rng(1)
+    for spec, n1, n2, ncomp in G.SPECS[:1] + G.SPECS[3:4] + G.SPECS[7:8] + G.SPECS[10:]:
+        its, rits = G._pairs(spec, n1, n2)
+        f = np.asfortranarray(rng.random((n1, n2, ncomp)))
+        fin = f if ncomp > 1 else np.asfortranarray(f[:, :, 0])
+        dec = np.asfortranarray(rng.uniform(-8, 8, (n1, n2, 2)))
+        out = np.empty_like(fin)
+        S.interpolate_nd(out, fin, dec, its)
+        assert relerr(out, U.interpolate_points(fin, dec, rits)) <= 1e-12
+    assert "interp2d_points" in fake.calls
+
+
+@pytest.mark.parametrize("spec,alg,ordalg", [((("lagrange", 5), ("lagrange", 5)), "NoTimeAlg", 0),
+                                            ((("bspline_lu", 5), ("bspline_lu", 5)), "NoTimeAlg", 0),
+                                            ((("lagrange", 5), ("lagrange", 5)), "ABTimeAlg_init", 3)])
+def test_swirling_driver_sequencing(fake, spec, alg, ordalg):
+    worst, g, _ = G._swirling_both(spec, 50, 6, alg, ordalg, sz=(40, 40))
+    assert worst <= 1e-11
+    if alg != "NoTimeAlg":
+        assert len(g.t_bufc) == ordalg - 1
+
+
+@pytest.mark.parametrize("alg,ordalg", [("ABTimeAlg_ip", 2), ("ABTimeAlg_ip", 4), ("ABTimeAlg_new", 2), ("ABTimeAlg_new", 3), ("NoTimeAlg", 0)])
+def test_poisson2d_driver_sequencing(fake, alg, ordalg):
+    import slb200 as S
+
+    sz = (32, 40)
+    its, rits = G._pairs((("lagrange", 5), ("lagrange", 5)), *sz)
+    dg, g = poisson2d_run(S, lambda adv: S.getpoissonvar(adv, type=S.StdPoisson2d), sz, its, 0.1, 4, getattr(S, alg), ordalg)
+    do, o = poisson2d_run(R, U.getpoissonvar2d, sz, rits, 0.1, 4, getattr(R, alg), ordalg)
+    assert relerr(g.getdata(), o.data) <= 1e-11
+    assert abs(dg - do) <= 1e-11 * abs(R.getenergy(o)[2])
+    if alg != "NoTimeAlg":
+        assert len(g.t_bufc) == len(o.t_bufc) >= ordalg - 1
+        hist_g = [f.to_host() for f in g.t_bufc]
+        for a, b in zip(hist_g, o.t_bufc):
+            assert relerr(a, b) <= 1e-10
+    assert relerr(g.bufcur.to_host(), o.bufcur) <= 1e-10
+
+
+def test_rotation2d_driver_sequencing(fake):
+    G.test_rotation2d_abtimealg_matches_oracle()
+
+
+def test_pool_recycles_storage(fake):
+    import slb200 as S
+    from slb200 import _lib
+
+    ctx = _lib.default_context()
+    a = S.DeviceField(ctx, 8, 8, 2)
+    p = a.ptr.value
+    a.free()
+    b = S.DeviceField(ctx, 8, 8, 2)
+    assert b.ptr.value == p and a.ptr is None
+    v = S.DeviceField.view(ctx, 8, 8, 2, b.ptr)
+    v.free()  # a view never returns storage it does not own
+    assert not S.DeviceField._pool.get((id(ctx), 128))
