@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,memory
 for w in $WHAT; do
   case $w in
     tests)
-      timeout 1200 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1
+      timeout 1200 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1
       echo "pytest rc=$?"; tail -3 "$OUT/pytest_gpu.log" ;;
     bench)
       timeout 600 python bench.py --steps 10 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"
@@ -34,6 +34,12 @@ for w in $WHAT; do
       echo "bspline rc=$?"
       timeout 600 python bench.py --steps 5 --warmup 3 --interp bspline_fft --order 11 --no-cpu > "$OUT/bench_bspline.json" 2> "$OUT/bench_bspline.err"
       cat "$OUT/bench_bspline.json" ;;
+    points)
+      timeout 300 python tools/bench_points.py > "$OUT/bench_points.json" 2> "$OUT/bench_points.err"
+      echo "points rc=$?"; cat "$OUT/bench_points.json"; tail -3 "$OUT/bench_points.err" ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
+      echo "smoke rc=$?"; tail -2 "$OUT/smoke.log" ;;
     *)
       echo "unknown item $w" ;;
   esac
