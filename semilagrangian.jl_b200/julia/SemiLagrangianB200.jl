@@ -139,9 +139,35 @@ end
 # (Poisson: only the velocity state that recomputes rho, src/poisson.jl:171-176).
 initcoef_reads_data(parext, self) = true
 
+# ---- unsplit 2-D states with per-point shifts (src/advection.jl:607-619) -------------------------
+# The provider's initcoef! fills BUFCUR[self]: a device buffer [n1, n2, 2] holding the OpTuple{2}
+# displacement field as two planes (slb_fill_dec2d for StdPoisson2d / rotation, src/poisson.jl:229-247,
+# src/rotation.jl:36-54; slb_lincomb or an upload for user providers such as test/test_swirling.jl:153-167).
+# The Adams-Bashforth time algorithms (src/advection.jl:404-580) sequence the same four calls
+# (slb_interp2d_points, slb_lincomb, slb_memcpy_d2d, slb_fill_dec2d) exactly as slb200/unsplit2d.py does.
+const BUFCUR = IdDict{Any,Ptr{Cvoid}}()
+
+function advection_points!(self::B200AdvectionData{T,2}) where {T}
+    (length(self.adv.states) == 1 && getst(self).perm == [1, 2]) ||
+        throw(ArgumentError("B200 path: per-point shifts need one unsplit 2-D state ([1, 2], 2, 1, false)"))
+    initcoef!(self.parext, self)
+    n1, n2 = sizeall(self.adv)
+    front = ccall((:slb_grid_front, LIB), Ptr{Cvoid}, (Ptr{Cvoid},), self.grid)
+    back = ccall((:slb_grid_back, LIB), Ptr{Cvoid}, (Ptr{Cvoid},), self.grid)
+    bs = any(x -> x isa Union{BSplineLU,BSplineFFT}, self.adv.t_interp)
+    work = bs ? devalloc(self.ctx, 8 * n1 * n2) : C_NULL
+    check(ccall((:slb_interp2d_points, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+        self.ctx.h, self.interps[1], self.interps[2], n1, n2, 1, front, BUFCUR[self], back, work, 0))
+    bs && check(ccall((:slb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), self.ctx.h, work))
+    check(ccall((:slb_grid_swap, LIB), Cint, (Ptr{Cvoid},), self.grid))
+    return nextstate!(self)
+end
+
 function advection!(self::B200AdvectionData{T,N}) where {T,N}     # src/advection.jl:594-704
     st = getst(self)
-    (st.ndims == 1 && st.isconstdec) || throw(ArgumentError("B200 path: const-shift 1-D states only"))
+    st.isconstdec || return advection_points!(self)
+    st.ndims == 1 || throw(ArgumentError("B200 Julia veneer: const-shift states with ndims = 1 (ndims = 2: see slb200/advection.py)"))
     haskey(PENDING, self) && initcoef_reads_data(self.parext, self) && flush!(self)
     initcoef!(self.parext, self)
     tab, len, strides, scale, ondev = alphatable(self.parext, self)
