@@ -244,7 +244,7 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
         if (!(GUARD) || i < N) {                                                                      \
             double T[BR];                                                                             \
             _Pragma("unroll") for (int q = 0; q < BR; ++q) T[q] = Tn[q];                              \
-            if (i > 0) bspf_ldrec<BR>(Tn, tB + (i - 1) * BR);                                         \
+            bspf_ldrec<BR>(Tn, tB + (i > 0 ? i - 1 : 0) * BR); /* clamped, not predicated: no MOVs */ \
             double v; /* w_i = (y_i - sum_j U[i][j-1] w_{i+j}) / d_i */                               \
             if (H >= 2) {                                                                             \
                 double sacc = -T[1 + H - 1] * ww[((r) + H) % H];                                      \
@@ -279,7 +279,7 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 u[r] = un[r];
-                un[r] = i0 >= H ? col[(i0 - H + r) * PITCH] : 0.0;
+                un[r] = col[((i0 >= H ? i0 - H : 0) + r) * PITCH];  // clamped: the last group's prefetch is unused
             }
 #pragma unroll
             for (int r = H - 1; r >= 0; --r) BSPF_BWD_ROW(r, false)

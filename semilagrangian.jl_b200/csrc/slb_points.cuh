@@ -52,8 +52,14 @@ __host__ __device__ __forceinline__ void slb_pt_split(double alpha, int n, int h
     s0 = (int)(r < 0 ? r + n : r);
 }
 
-// P1 > 0: both dims have order + 1 == P1 (loops unrolled, weights in registers); P1 == 0: run-time
-// orders up to 63 each (weights in local memory).  cA / cB: weight polynomial rows, row stride sA / sB.
+// P1 > 0: both dims have order + 1 == P1 (tap loop unrolled, dim-1 weights in registers); P1 == 0:
+// run-time orders up to 63 each (dim-1 weights in local memory).  cA / cB: weight polynomial rows, row
+// stride sA / sB.
+// Register budget decides this kernel: unrolling all (p+1)^2 taps lets the compiler hoist a hundred
+// gathers and costs 250 registers (8 warps per SM, every gather at full L2 latency).  Only the taps of
+// ONE stencil row are unrolled; the row loop stays rolled and evaluates its dim-2 weight on the fly
+// (each w^2_b is used by exactly one row, so nothing is computed twice), two component planes share a
+// pass.  Windows that do not wrap around dim 1 use immediate offsets.
 template <int P1, bool EXACT>
 __host__ __device__ __forceinline__ void slb_point_eval(const PointsArgs& pa, const double* cA, int sA, const double* cB,
                                                         int sB, int i, int j)
@@ -61,54 +67,80 @@ __host__ __device__ __forceinline__ void slb_point_eval(const PointsArgs& pa, co
     constexpr int W = P1 > 0 ? P1 : SLB_POINTS_MAXP1;
     const int pA = P1 > 0 ? P1 : pa.pA;
     const int pB = P1 > 0 ? P1 : pa.pB;
-    const long long plane = (long long)pa.n1 * pa.n2;
-    const long long idx = (long long)j * pa.n1 + i;
+    const int n1 = pa.n1, n2 = pa.n2;
+    const long long plane = (long long)n1 * n2;
+    const long long idx = (long long)j * n1 + i;
     double tA, tB;
     int sa0, sb0;
-    slb_pt_split(pa.dec[idx], pa.n1, (pA - 1) / 2, tA, sa0);
-    slb_pt_split(pa.dec[plane + idx], pa.n2, (pB - 1) / 2, tB, sb0);
-    double wA[W], wB[W];
+    slb_pt_split(pa.dec[idx], n1, (pA - 1) / 2, tA, sa0);
+    slb_pt_split(pa.dec[plane + idx], n2, (pB - 1) / 2, tB, sb0);
+    double wA[W];
 #pragma unroll
     for (int a = 0; a < pA; ++a) {
         double ex = cA[a * sA + pa.ncA - 1];
         for (int k = pa.ncA - 2; k >= 0; --k) ex = fma(tA, ex, cA[a * sA + k]);
         wA[a] = ex;
     }
-#pragma unroll
-    for (int b = 0; b < pB; ++b) {
-        double ex = cB[b * sB + pa.ncB - 1];
-        for (int k = pa.ncB - 2; k >= 0; --k) ex = fma(tB, ex, cB[b * sB + k]);
-        wB[b] = ex;
-    }
     // start of the periodic windows: (i + d - p/2) mod n
     int ia0 = i + sa0;
-    if (ia0 >= pa.n1) ia0 -= pa.n1;
+    if (ia0 >= n1) ia0 -= n1;
     int jb0 = j + sb0;
-    if (jb0 >= pa.n2) jb0 -= pa.n2;
-    for (int c = 0; c < pa.ncomp; ++c) {
-        const double* r = pa.res + (long long)c * plane;
-        double acc = 0.0;
+    if (jb0 >= n2) jb0 -= n2;
+    const bool nowrap = ia0 + pA <= n1;
+    for (int c = 0; c < pa.ncomp; c += 2) {
+        const bool two = c + 1 < pa.ncomp;
+        const double* r0 = pa.res + (long long)c * plane;
+        const double* r1 = two ? r0 + plane : r0;
+        double acc0 = 0.0, acc1 = 0.0;
         int jb = jb0;
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < pB; ++b) {
-            const double* row = r + (long long)jb * pa.n1;
-            int ia = ia0;
-            double inner = 0.0;
+            double wb = cB[b * sB + pa.ncB - 1];
+            for (int k = pa.ncB - 2; k >= 0; --k) wb = fma(tB, wb, cB[b * sB + k]);
+            const double* row0 = r0 + (long long)jb * n1;
+            const double* row1 = r1 + (long long)jb * n1;
+            double in0 = 0.0, in1 = 0.0;
+            if (nowrap) {
 #pragma unroll
-            for (int a = 0; a < pA; ++a) {
-                double v = row[ia];
-                if (EXACT) {
-                    double term = SLB_PT_MUL(v, SLB_PT_MUL(wA[a], wB[b]));
-                    acc = (a == 0 && b == 0) ? term : SLB_PT_ADD(acc, term);
-                } else {
-                    inner = (a == 0) ? v * wA[a] : fma(v, wA[a], inner);
+                for (int a = 0; a < pA; ++a) {
+                    const double v0 = row0[ia0 + a];
+                    const double v1 = two ? row1[ia0 + a] : 0.0;
+                    if (EXACT) {
+                        const double tab = SLB_PT_MUL(wA[a], wb);
+                        const double t0 = SLB_PT_MUL(v0, tab), t1 = SLB_PT_MUL(v1, tab);
+                        acc0 = (a == 0 && b == 0) ? t0 : SLB_PT_ADD(acc0, t0);
+                        acc1 = (a == 0 && b == 0) ? t1 : SLB_PT_ADD(acc1, t1);
+                    } else {
+                        in0 = (a == 0) ? v0 * wA[a] : fma(v0, wA[a], in0);
+                        in1 = (a == 0) ? v1 * wA[a] : fma(v1, wA[a], in1);
+                    }
                 }
-                if (++ia == pa.n1) ia = 0;
+            } else {
+                int ia = ia0;
+#pragma unroll
+                for (int a = 0; a < pA; ++a) {
+                    const double v0 = row0[ia];
+                    const double v1 = two ? row1[ia] : 0.0;
+                    if (EXACT) {
+                        const double tab = SLB_PT_MUL(wA[a], wb);
+                        const double t0 = SLB_PT_MUL(v0, tab), t1 = SLB_PT_MUL(v1, tab);
+                        acc0 = (a == 0 && b == 0) ? t0 : SLB_PT_ADD(acc0, t0);
+                        acc1 = (a == 0 && b == 0) ? t1 : SLB_PT_ADD(acc1, t1);
+                    } else {
+                        in0 = (a == 0) ? v0 * wA[a] : fma(v0, wA[a], in0);
+                        in1 = (a == 0) ? v1 * wA[a] : fma(v1, wA[a], in1);
+                    }
+                    if (++ia == n1) ia = 0;
+                }
             }
-            if (!EXACT) acc = (b == 0) ? inner * wB[b] : fma(inner, wB[b], acc);
-            if (++jb == pa.n2) jb = 0;
+            if (!EXACT) {
+                acc0 = (b == 0) ? in0 * wb : fma(in0, wb, acc0);
+                acc1 = (b == 0) ? in1 * wb : fma(in1, wb, acc1);
+            }
+            if (++jb == n2) jb = 0;
         }
-        pa.out[(long long)c * plane + idx] = acc;
+        pa.out[(long long)c * plane + idx] = acc0;
+        if (two) pa.out[(long long)(c + 1) * plane + idx] = acc1;
     }
 }
 

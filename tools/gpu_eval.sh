@@ -34,6 +34,18 @@ for w in $WHAT; do
       echo "bspline rc=$?"
       timeout 600 python bench.py --steps 5 --warmup 3 --interp bspline_fft --order 11 --no-cpu > "$OUT/bench_bspline.json" 2> "$OUT/bench_bspline.err"
       cat "$OUT/bench_bspline.json" ;;
+    bsp)
+      for cfg in "bspline_fft 11" "bspline_lu 5" "bspline_lu 3"; do
+        set -- $cfg
+        timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu --no-e2e 2>>"$OUT/bench_bsp.err" | tail -1 >> "$OUT/bench_bsp.jsonl"
+      done
+      python - <<PY
+import json
+for ln in open("$OUT/bench_bsp.jsonl"):
+    d = json.loads(ln); k = d["roofline"]["all_kernels"]; c = d["config"]
+    print(c["interp"], c["order"], "ms/step %.3f" % d["ms_per_step"], "Gcell/s %.1f" % d["value"], {n: round(v["ms"], 3) for n, v in k.items()})
+PY
+      ;;
     points)
       timeout 300 python tools/bench_points.py > "$OUT/bench_points.json" 2> "$OUT/bench_points.err"
       echo "points rc=$?"; cat "$OUT/bench_points.json"; tail -3 "$OUT/bench_points.err" ;;
