@@ -3,6 +3,7 @@
 // Not part of libslb200.so's ABI: built as a separate test helper (lib/libslb200_hosttest.so).
 #include "slb_bspline.cuh"
 #include "slb_points.cuh"
+#include "slb_bspsplit.cuh"
 
 extern "C" int slbt_bspline_solve_host(int order, long long n, const double* node_vals, const double* b, double* x)
 {
@@ -51,5 +52,21 @@ extern "C" int slbt_points_host(const double* res, const double* dec, double* ou
             else
                 slb_point_eval<0, false>(pa, coefA, ncA, coefB, ncB, i, j);
         }
+    return 0;
+}
+
+// Host run of the split-line (two halves + two separators) B-spline solver: factorisation, the
+// kernel's table layout and the reference form of its per-line arithmetic (slb_bspsplit.cuh).
+extern "C" int slbt_bspsplit_solve_host(int order, long long n, const double* node_vals, const double* b, double* x)
+{
+    BspSplitHost hb;
+    std::string msg;
+    int rc = bspsplit_factor(order, n, node_vals, &hb, msg);
+    if (rc) return rc;
+    BspSplitTab tab;
+    std::vector<double> v;
+    bspsplit_fill(&tab, v, hb);
+    for (long long i = 0; i < n; ++i) x[i] = b[i];
+    bspsplit_solve_line(tab, v.data(), x, x);
     return 0;
 }

@@ -17,6 +17,7 @@
 #include "slb_pair.cuh"
 #include "slb_bspline.cuh"
 #include "slb_bspfused.cuh"
+#include "slb_bspsplit.cuh"
 #include "slb_field.cuh"
 #include "slb_points.cuh"
 
@@ -89,6 +90,8 @@ struct slb_interp {
     BsplineDev bsp;            // LU factors / circulant symbol on the device (B-spline kinds)
     double* bsptab_dev;        // the same factors in the fused sweep's record layout (device), or NULL
     BspFusedTab bsptab;
+    double* bspstab_dev;       // tables of the split-line fused sweep (two warps per tile, slb_bspsplit.cuh), or NULL
+    BspSplitTab bspstab;
 };
 
 struct slb_poisson {
@@ -434,6 +437,8 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
     }
     it->bsptab_dev = nullptr;
     memset(&it->bsptab, 0, sizeof(it->bsptab));
+    it->bspstab_dev = nullptr;
+    memset(&it->bspstab, 0, sizeof(it->bspstab));
     if (bs) {
         std::string msg;
         BsplineHost hb;
@@ -455,6 +460,21 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
                 cudaGetLastError();
             }
         }
+        if (it->fast && slb_bspsplit_tiles(hb.h, hb.n) > 0) {
+            BspSplitHost hs;
+            std::string msg2;
+            if (bspsplit_factor(order, n, node_vals, &hs, msg2) == SLB_OK) {
+                std::vector<double> v;
+                bspsplit_fill(&it->bspstab, v, hs);
+                cudaError_t e2 = cudaMalloc(&it->bspstab_dev, v.size() * sizeof(double));
+                if (e2 == cudaSuccess) e2 = cudaMemcpy(it->bspstab_dev, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+                if (e2 != cudaSuccess) {
+                    if (it->bspstab_dev) cudaFree(it->bspstab_dev);
+                    it->bspstab_dev = nullptr;
+                    cudaGetLastError();
+                }
+            }
+        }
     }
     *out = it;
     return SLB_OK;
@@ -467,6 +487,7 @@ extern "C" void slb_interp_destroy(slb_interp* it)
     cudaFree(it->coef_dev);
     bspline_free(&it->bsp);
     if (it->bsptab_dev) cudaFree(it->bsptab_dev);
+    if (it->bspstab_dev) cudaFree(it->bspstab_dev);
     delete it;
 }
 
@@ -655,6 +676,28 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
     int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, on_device, &am);
     if (rc) return rc;
     const double* src = g->front;
+    if (bs && it->bspstab_dev && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) && env_ll("SLB_BSPLINE_FUSED", 1) != 0 &&
+        env_ll("SLB_BSPLINE_SPLIT", 1) != 0) {
+        // strided dims: pre-solve + stencil in one pass with two warps per tile of lines (slb_bspsplit.cuh)
+        BspSplitArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = g->front;
+        a.out = g->back;
+        a.inner = v.inner;
+        a.nlines = v.inner * v.outer;
+        a.bstride = (long long)v.n * v.inner;
+        a.n = v.n;
+        a.nc = it->nc;
+        a.tiles = slb_bspsplit_tiles(it->bspstab.h, v.n);
+        a.am = am;
+        a.linesum = g->linesum;
+        a.tab_dev = it->bspstab_dev;
+        a.tab = it->bspstab;
+        int lrc = slb_bspsplit_launch(a, it->tab, c->sm_count, c->stream);
+        if (lrc != 0) return fail(lrc < 0 ? SLB_E_UNSUPPORTED : SLB_E_CUDA, "slb_sweep: split B-spline launch failed (%d)", lrc);
+        c->launches++;
+        return slb_grid_swap(g);
+    }
     if (bs && it->bsptab_dev && !(flags & SLB_SWEEP_EXACT) && !(g->linesum && dim == 0) && !(omp && dim == 0) && !(imp && dim != 0) &&
         env_ll("SLB_BSPLINE_FUSED", 1) != 0) {
         // pre-solve + stencil in one pass over HBM (slb_bspfused.cuh): front -> back, then swap

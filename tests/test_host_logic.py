@@ -126,6 +126,24 @@ def test_bordered_lu_solver_host(order, n):
     assert np.max(np.abs(x - ref)) <= 1e-13 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("order,n", [(3, 16), (3, 128), (5, 64), (5, 128), (7, 128), (9, 30), (9, 100), (11, 128), (11, 256), (13, 64)])
+def test_split_line_solver_host(order, n):
+    """The two-halves + two-separators formulation of the fused B-spline sweep (slb_bspsplit.cuh:
+    bspsplit_factor, the kernel's table layout, the per-line arithmetic), executed on the host,
+    equals the reference's cyclic LU solve."""
+    so = os.path.join(ROOT, "semilagrangian.jl_b200", "lib", "libslb200_hosttest.so")
+    L = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    L.slbt_bspsplit_solve_host.argtypes = [C.c_int, C.c_longlong, dp, dp, dp]
+    rng = np.random.default_rng(77)
+    nodes = np.array([float(x) for x in T.bspline_node_values_rat(order)])
+    b = rng.random(n)
+    x = np.empty(n)
+    assert L.slbt_bspsplit_solve_host(order, n, nodes.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp)) == 0
+    ref = R.BSplineLU(order, n).sol(b)
+    assert np.max(np.abs(x - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
 def test_driver_level_oracle_kats():
     """Oracle driver pinned by the reference's integration tests: rotation returns to the
     start (test/test_rotation.jl:237-252, err < 1e-3) and Poisson pieces are consistent
