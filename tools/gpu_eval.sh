@@ -62,6 +62,10 @@ PY
           cat "$OUT/tmp.json" >> "$OUT/bench_bspab_split$split.jsonl"
         done
       done ;;
+    ncusplit)
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bspline_split -s 3 -c 1 \
+        -f -o "$OUT/prof_split" python tools/prof_step.py --steps 1 --interp bspline_fft --order 11 > "$OUT/ncusplit.log" 2>&1
+      echo "ncusplit rc=$?"; tail -3 "$OUT/ncusplit.log"; ls -la "$OUT" ;;
     points)
       timeout 300 python tools/bench_points.py > "$OUT/bench_points.json" 2> "$OUT/bench_points.err"
       echo "points rc=$?"; cat "$OUT/bench_points.json"; tail -3 "$OUT/bench_points.err" ;;
