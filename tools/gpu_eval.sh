@@ -21,7 +21,7 @@ for w in $WHAT; do
       echo "ref rc=$?"; cat "$OUT/bench_ref.json" ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-        --log-file "$OUT/launches.csv" python tools/prof_step.py --steps 2 > "$OUT/launches.log" 2>&1
+        --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 3 --no-cpu > "$OUT/launches.log" 2>&1
       echo "launches rc=$?" ;;
     full)
       # skip the warm-up step's launches; 1 capture each of the strided and contiguous sweep kernels
@@ -66,6 +66,9 @@ PY
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bspline_split -s 3 -c 1 \
         -f -o "$OUT/prof_split" python tools/prof_step.py --steps 1 --interp bspline_fft --order 11 > "$OUT/ncusplit.log" 2>&1
       echo "ncusplit rc=$?"; tail -3 "$OUT/ncusplit.log"; ls -la "$OUT" ;;
+    configs)
+      timeout 300 python tools/bench_configs.py > "$OUT/bench_configs.json" 2> "$OUT/bench_configs.err"
+      echo "configs rc=$?"; cat "$OUT/bench_configs.json"; tail -3 "$OUT/bench_configs.err" ;;
     points)
       timeout 300 python tools/bench_points.py > "$OUT/bench_points.json" 2> "$OUT/bench_points.err"
       echo "points rc=$?"; cat "$OUT/bench_points.json"; tail -3 "$OUT/bench_points.err" ;;
