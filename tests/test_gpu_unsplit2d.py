@@ -10,7 +10,7 @@ import pytest
 
 from helpers import make_pair, relerr
 from oracle import refmodel as R, unsplit2d as U
-from test_oracle_unsplit2d import poisson2d_run, swirling_setup
+from test_oracle_unsplit2d import interp2d_kat_inputs, poisson2d_run, swirling_setup
 
 pytestmark = pytest.mark.gpu
 
@@ -79,6 +79,31 @@ def test_interp2d_points_function_form_and_errors():
         S.interpolate_nd(a, f, dec, its[:1])
     with pytest.raises(ValueError):  # a B-spline object bound to another line length
         S.interpolate_nd(a, f, dec, [S.BSplineLU(3, 16), S.Lagrange(3)])
+
+
+def test_interp2d_reference_kat():
+    """test/test_interpolation.jl:120-178, :486 (test_interp2d, Lagrange 11, (128, 100)) on the device: scalar
+    and two-component fields, array and function form, within 1000 eps of each other and 1e-12 of the
+    oracle"""
+    import slb200 as S
+
+    prec = 1000 * np.finfo(np.float64).eps
+    dec, ref, ref2, op = interp2d_kat_inputs()
+    its, rits = _pairs((("lagrange", 11), ("lagrange", 11)), 128, 100)
+    res1, res3, res4 = np.empty_like(ref), np.empty_like(ref), np.empty_like(ref)
+    S.interpolate_nd(res1, ref, dec, its)
+    S.interpolate_nd(res3, ref, lambda ind: (dec[ind[0], ind[1], 0], dec[ind[0], ind[1], 1]), its)
+    S.interpolate_nd(res4, ref2, dec, its)
+    assert np.linalg.norm(res1 - res3) < prec
+    both = np.empty(ref.shape + (2,), order="F")
+    both[:, :, 0], both[:, :, 1] = ref, ref2
+    r = np.empty_like(both)
+    S.interpolate_nd(r, both, dec, its)
+    assert np.linalg.norm(r[:, :, 0] - res1) < prec and np.linalg.norm(r[:, :, 1] - res4) < prec
+    opres = np.empty_like(op)
+    S.interpolate_nd(opres, op, dec, its)
+    assert relerr(opres, U.interpolate_points(op, dec, rits)) <= 1e-12
+    assert relerr(res1, U.interpolate_points(ref, dec, rits)) <= 1e-12
 
 
 def test_device_array_operations_are_bitwise():

@@ -64,6 +64,45 @@ def test_function_form_equals_array_form():
     assert np.array_equal(a, b)
 
 
+def interp2d_kat_inputs(sz=(128, 100), coeff=1.25):
+    """the fields of test/test_interpolation.jl:120-150 (test_interp2d): a smooth displacement field
+    of amplitude 1.25 cells, two scalar fields and a two-component field"""
+    i = np.arange(1, sz[0] + 1)[:, None] / sz[0]
+    j = np.arange(1, sz[1] + 1)[None, :] / sz[1]
+    x = 2 * math.pi * (i + j)
+    dec = np.empty(sz + (2,), order="F")
+    dec[:, :, 0], dec[:, :, 1] = coeff * np.cos(x + 1), coeff * np.cos(x + 2)
+    ref = np.asfortranarray(np.sin(x + 3) + np.cos(x - 1))
+    ref2 = np.asfortranarray(np.sin(x + 1) + 3 * np.cos(-x + 2) / 5)
+    op = np.empty(sz + (2,), order="F")
+    op[:, :, 0], op[:, :, 1] = coeff * np.sin(x + 4), coeff * np.cos(x + 5)
+    return dec, ref, ref2, op
+
+
+def test_interp2d_forms_agree():
+    """test/test_interpolation.jl:120-178, :486 (test_interp2d, Lagrange 11, (128, 100)): the array form,
+    the function form and the component-wise interpolation of a two-component field agree to 1000 eps
+    (they are the same arithmetic here: exactly)"""
+    prec = 1000 * np.finfo(np.float64).eps
+    dec, ref, ref2, op = interp2d_kat_inputs()
+    interps = [R.Lagrange(11), R.Lagrange(11)]
+    res1 = U.interpolate_points(ref, dec, interps)
+    res3 = U.interpolate_fct(ref, lambda ind: (dec[ind[0], ind[1], 0], dec[ind[0], ind[1], 1]), interps)
+    res4 = U.interpolate_points(ref2, dec, interps)
+    assert np.linalg.norm(res1 - res3) < prec
+    both = np.empty(ref.shape + (2,), order="F")
+    both[:, :, 0], both[:, :, 1] = ref, ref2
+    r = U.interpolate_points(both, dec, interps)
+    assert np.linalg.norm(r[:, :, 0] - res1) < prec and np.linalg.norm(r[:, :, 1] - res4) < prec
+    opres = U.interpolate_points(op, dec, interps)
+    assert np.linalg.norm(opres[:, :, 0] - U.interpolate_points(np.asfortranarray(op[:, :, 0]), dec, interps)) < prec
+    # and the result is the field moved along the displacement: compare with the analytic composition
+    i = np.arange(1, 129)[:, None]
+    j = np.arange(1, 101)[None, :]
+    xs = 2 * math.pi * ((i + dec[:, :, 0]) / 128 + (j + dec[:, :, 1]) / 100)
+    assert np.max(np.abs(res1 - (np.sin(xs + 3) + np.cos(xs - 1)))) < 1e-9
+
+
 def test_host_build_of_the_cuda_point_body_matches_the_oracle():
     """slb_point_eval (the per-thread body of k_interp2d_points) compiled for the host: EXACT mode is
     bit-identical to the oracle, the FMA mode agrees to rounding; templated and run-time-order
