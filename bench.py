@@ -310,7 +310,7 @@ def run_ours(args):
     dom = "k_sweep_fused/v1v2"
     ach = kern[dom]["GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": ach / peak, "traffic": NCU_TRAFFIC.get(n), "traffic_source": "profiles/r1_ncu_full_fused_L7_128.txt (ncu --set full, per launch)",
+                "frac": ach / peak, "traffic": NCU_TRAFFIC.get(n), "traffic_source": "profiles/r1_ncu_full_fused_L7_128_s4f.txt (ncu --set full, per launch)",
                 "bytes_per_launch": n**4 * BYTES_PER_CELL,
                 "note": "one launch reads f once and writes it once (16 B per cell) and performs TWO sweeps (2 cell-updates per cell); "
                         "in SURVEY.md 8(d)'s per-sweep unit (16 B per cell-update) that is twice the single-sweep roofline rate",

@@ -44,6 +44,11 @@ extern "C" {
                               reference's `sum(res[...] .* precal)`, src/interpolation.jl:190)
                               instead of an FMA chain */
 
+#define SLB_SWEEP_INSIDE_EDGE 2  /* non-periodic InsideEdge interpolation (src/interpolation.jl:123-132, :250-286):
+                                    one-sided stencils near the ends of the line instead of the periodic wrap;
+                                    Lagrange / Hermite kinds, -order <= floor(alpha) - order/2 <= 0 required
+                                    (SLB_E_ARG for host tables, NaN-filled lines for device tables) */
+
 #define SLB_MAX_DIMS 6
 #define SLB_MAX_ORDER 63
 

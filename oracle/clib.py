@@ -63,6 +63,8 @@ def lib():
     L.orc_sol_line.restype = None
     L.orc_interpolate_points2d.argtypes = [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_long, C.c_long, C.c_int, C.c_int]
     L.orc_interpolate_points2d.restype = None
+    L.orc_interpolate_inside.argtypes = [c_double_p, c_double_p, C.c_long, C.c_long, C.c_double, c_double_p, C.c_int, C.c_int]
+    L.orc_interpolate_inside.restype = C.c_int
     L.orc_sweep.argtypes = [c_double_p, c_double_p, C.c_int, c_long_p, C.c_int, C.c_void_p, c_double_p, c_long_p, C.c_int]
     L.orc_sweep.restype = C.c_int
     L.orc_compute_charge.argtypes = [c_double_p, c_double_p, C.c_long, C.c_long, C.c_double, C.c_int]

@@ -403,6 +403,42 @@ void orc_sol_line(const orc_interp *it, double *X, const double *fi)
 }
 
 /* ------------------------------------------------------------------------------------
+ * InsideEdge (non-periodic) interpolation, "a marginal case" in the reference's words:
+ * src/interpolation.jl:123-132  get_allprecal: allprecal[k] = getprecal(interp, decfloat + indbeg + k - 1),
+ *                                k = 1..order+1, indbeg = -div(order, 2) + decint
+ * src/interpolation.jl:250-286  interpolate!(fp, fi, decint, allprecal, interp::InsideEdge):
+ *   the window never leaves the array: the first borne1 = -indbeg outputs use res[1:order+1], the last
+ *   ones res[lg-order:lg], each with the weights of its own offset; in between the standard window.
+ * Products rounded, summed left to right.  Returns -1 when the reference's loops would index outside
+ * the arrays (indbeg > 0 or indbeg + order < 0).
+ * ---------------------------------------------------------------------------------- */
+int orc_interpolate_inside(double *fp, const double *res, long lg, long decint, double decfloat, const double *coef,
+                           int order, int nc)
+{
+    long origin = -(long)(order / 2);
+    long indbeg = origin + decint;
+    long borne1 = -decint - origin;           /* = -indbeg */
+    long borne2 = lg - decint + origin - 1;
+    int lgp = order + 1;
+    if (borne1 < 0 || borne1 > order || lg < order + 1) return -1;
+    double w[ORC_MAXP];
+    for (long i = 1; i <= lg; ++i) {          /* 1-based, as the Julia text */
+        long first, ind;
+        if (i <= borne1) { first = 1; ind = i; }
+        else if (i <= borne2) { first = i - borne1; ind = borne1 + 1; }
+        else { first = lg - order; ind = lgp - (lg - i); }
+        orc_getprecal(coef, order + 1, nc, decfloat + (double)(indbeg + ind - 1), w);
+        double s = 0.0;
+        for (int j = 0; j <= order; ++j) {
+            double prod = res[first - 1 + j] * w[j];
+            s = (j == 0) ? prod : s + prod;
+        }
+        fp[i - 1] = s;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * src/interpolation.jl:561-621 (and its closure twin :401-429), N = 2:
  * interpolate!(fp, fi, bufdec::Array{OpTuple{2}}, interp_t).  `res` = sol(interp_t, fi) is
  * done by the caller (per dim, src/interpolation.jl:48-94).  Per point ind = (i, j):

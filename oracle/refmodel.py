@@ -62,9 +62,13 @@ def vec_k_fft(mesh):
 # interpolation types: src/lagrange.jl:58-72, src/bsplinelu.jl:253-270,
 # src/bsplinefft.jl:25-45, src/hermite.jl:99-132
 # ---------------------------------------------------------------------------------------
+# src/interpolation.jl:3  @enum EdgeType
+CircEdge, InsideEdge = 1, 2
+
+
 class Interp:
-    def __init__(self, kind, order, n=0, flbis=False):
-        self.kind, self.order, self.n = kind, order, n
+    def __init__(self, kind, order, n=0, flbis=False, edge=CircEdge):
+        self.kind, self.order, self.n, self.edge = kind, order, n, edge
         if kind == LAGRANGE:
             rat = tables.lagrange_tabfct_rat(order)
             nodes = None
@@ -112,8 +116,8 @@ class Interp:
         return b.copy()
 
 
-def Lagrange(order):
-    return Interp(LAGRANGE, order)
+def Lagrange(order, edge=CircEdge):
+    return Interp(LAGRANGE, order, edge=edge)
 
 
 def BSplineLU(order, n):
@@ -133,6 +137,15 @@ def interpolate(fp, fi, dec, interp):
     interpolate!(fp, fi, decint, getprecal(interp, decfloat), interp)."""
     fi = np.ascontiguousarray(fi, dtype=np.float64)
     assert fp.flags.c_contiguous and fp is not fi
+    if interp.edge == InsideEdge:
+        # :308-314: interpolate!(fp, fi, decint, get_allprecal(interp, decint, decfloat), interp)
+        decint = int(np.floor(dec))
+        res = interp.sol(fi)
+        rc = clib.lib().orc_interpolate_inside(clib.dp(fp), clib.dp(res), len(fi), decint, float(dec) - decint, clib.dp(interp.tabfct),
+                                               interp.order, interp.tabfct.shape[1])
+        if rc != 0:
+            raise ValueError("InsideEdge: the shift moves the stencil window outside the array")
+        return None
     clib.lib().orc_interpolate_alpha(interp._h, clib.dp(fp), clib.dp(fi), len(fi), float(dec))
     return None
 

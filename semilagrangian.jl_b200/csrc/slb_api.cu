@@ -676,6 +676,26 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
     int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, on_device, &am);
     if (rc) return rc;
     const double* src = g->front;
+    if (flags & SLB_SWEEP_INSIDE_EDGE) {
+        // InsideEdge: one-sided stencils near the line ends (kernel-seam feature, not a hot path)
+        if (bs) return fail(SLB_E_UNSUPPORTED, "slb_sweep: InsideEdge is implemented for Lagrange / Hermite interpolations");
+        if (omp || imp || g->linesum) return fail(SLB_E_UNSUPPORTED, "slb_sweep: InsideEdge does not combine with re-shard maps or line sums");
+        if (v.n < it->order + 1) return fail(SLB_E_ARG, "slb_sweep: InsideEdge needs n >= order + 1");
+        if (!on_device) {  // the reference's loops index out of bounds for such shifts: refuse them
+            for (int64_t k = 0; k < alpha_len; ++k) {
+                double ib = floor(scale * alpha_tab[k]) - (double)(it->order / 2);
+                if (!(ib <= 0.0 && ib >= -(double)it->order))
+                    return fail(SLB_E_ARG, "slb_sweep: InsideEdge shift %g moves the stencil window outside the line (order %d)",
+                                scale * alpha_tab[k], it->order);
+            }
+        }
+        long long nlines = v.inner * v.outer;
+        unsigned blocks = (unsigned)((nlines + 127) / 128);
+        k_sweep_inside<<<blocks, 128, 0, c->stream>>>(g->front, g->back, v.inner, v.n, nlines, am, it->coef_dev, it->order + 1, it->nc,
+                                                       (flags & SLB_SWEEP_EXACT) ? 1 : 0);
+        LAUNCH_CHECK(c);
+        return slb_grid_swap(g);
+    }
     if (bs && it->bspstab_dev && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) && env_ll("SLB_BSPLINE_FUSED", 1) != 0 &&
         env_ll("SLB_BSPLINE_SPLIT", 1) != 0) {
         // strided dims: pre-solve + stencil in one pass with two warps per tile of lines (slb_bspsplit.cuh)
@@ -866,6 +886,7 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     if (rc) return rc;
     rc = check_alpha_table(g, dimB, alphaB, alenB, astrB);
     if (rc) return rc;
+    if (flags & SLB_SWEEP_INSIDE_EDGE) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: InsideEdge sweeps are not pair-fused");
     if (nd > 4) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: grids with more than 4 dims are not pair-fused");
     if (dimB == 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: the second sweep must not run along dim 0");
     auto plain = [](const slb_interp* it) { return it->fast && it->kind != SLB_BSPLINE_LU && it->kind != SLB_BSPLINE_FFT; };

@@ -436,3 +436,80 @@ k_sweep_generic(const double* __restrict__ in, double* __restrict__ out, long lo
         if (++k0 == n) k0 = 0;
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// InsideEdge (non-periodic) sweep -- "a marginal case" in the reference's words
+// (src/interpolation.jl:123-132 get_allprecal, :250-286 interpolate!(..., interp::InsideEdge)): the
+// stencil window never leaves the line.  With indbeg = decint - order/2 (must satisfy
+// -order <= indbeg <= 0), 1-based output i uses
+//     i <= -indbeg              : res[1 : order+1]            weights tabfct(t + indbeg + i - 1)
+//     -indbeg < i <= n+indbeg   : res[i+indbeg : i+indbeg+order]   weights tabfct(t)      (the usual ones)
+//     else                      : res[n-order : n]            weights tabfct(t + indbeg + order - (n - i))
+// i.e. near the ends the same polynomial is evaluated outside [0, 1] (one-sided stencils).  Thread per
+// line, any dim, run-time order; lines whose shift violates the bound are filled with NaN (the reference
+// indexes out of bounds there).  Not a hot path: kernel-seam calls only.
+// ------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128)
+k_sweep_inside(const double* __restrict__ in, double* __restrict__ out, long long inner, int n, long long nlines,
+               AlphaMap am, const double* __restrict__ coef, int np, int nc, int exact)
+{
+    long long gid = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (gid >= nlines) return;
+    long long b = gid / inner;
+    long long a = gid - b * inner;
+    const double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, (unsigned)a, (unsigned)b));
+    const double fl = floor(alpha);
+    const double t = alpha - fl;
+    const int order = np - 1;
+    const double* pin = in + (b * n) * inner + a;
+    double* pout = out + (b * n) * inner + a;
+    const double dib = fl - (double)(order / 2);  // indbeg
+    if (!(dib <= 0.0 && dib >= -(double)order)) {
+        for (int i = 0; i < n; ++i) pout[(long long)i * inner] = nan("");
+        return;
+    }
+    const int indbeg = (int)dib;
+    const int borne1 = -indbeg, borne2 = n + indbeg;  // 1-based bounds of the three regimes
+    double wmid[64], we[64];
+    for (int j = 0; j < np; ++j) {
+        const double* c = coef + j * nc;
+        double ex = __ldg(c + nc - 1);
+        for (int k = nc - 2; k >= 0; --k) ex = fma(t, ex, __ldg(c + k));
+        wmid[j] = ex;
+    }
+    for (int i = 1; i <= n; ++i) {
+        int first;
+        const double* w = wmid;
+        if (i <= borne1 || i > borne2) {
+            int ind;
+            if (i <= borne1) {
+                first = 1;
+                ind = i;
+            } else {
+                first = n - order;
+                ind = np - (n - i);
+            }
+            const double targ = t + (double)(indbeg + ind - 1);
+            for (int j = 0; j < np; ++j) {
+                const double* c = coef + j * nc;
+                double ex = __ldg(c + nc - 1);
+                for (int k = nc - 2; k >= 0; --k) ex = fma(targ, ex, __ldg(c + k));
+                we[j] = ex;
+            }
+            w = we;
+        } else {
+            first = i - borne1;
+        }
+        double acc = 0.0;
+        for (int j = 0; j < np; ++j) {
+            const double v = __ldg(pin + (long long)(first - 1 + j) * inner);
+            if (exact) {
+                const double pr = __dmul_rn(v, w[j]);
+                acc = (j == 0) ? pr : __dadd_rn(acc, pr);
+            } else {
+                acc = (j == 0) ? v * w[j] : fma(v, w[j], acc);
+            }
+        }
+        pout[(long long)(i - 1) * inner] = acc;
+    }
+}

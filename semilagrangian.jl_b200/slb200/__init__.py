@@ -6,10 +6,10 @@ Advection / AdvectionData / advection (== advection!), and the Poisson / rotatio
 translation displacement providers.  Everything numerical runs in the CUDA library through
 its C ABI (include/slb200.h); there is no CPU fallback.
 """
-from ._lib import Context, SlbError, default_context, LIB_PATH, SLB_SWEEP_EXACT
+from ._lib import Context, SlbError, default_context, LIB_PATH, SLB_SWEEP_EXACT, SLB_SWEEP_INSIDE_EDGE
 from .mesh import UniformMesh, step, points, width, start, stop, vec_k_fft
 from .interp import (AbstractInterpolation, Lagrange, BSplineLU, BSplineFFT, Hermite, get_order, get_kl_ku,
-                     LAGRANGE, BSPLINE_LU, BSPLINE_FFT, HERMITE)
+                     LAGRANGE, BSPLINE_LU, BSPLINE_FFT, HERMITE, CircEdge, InsideEdge)
 from .splitting import (nosplit, standardsplit, strangsplit, magicsplit, triplejumpsplit, order6split,
                         hamsplit_3_11)
 from .advection import (Advection, AdvectionData, AbstractExtDataAdv, StateAdv, advection, getdata, sizeall,

@@ -75,6 +75,7 @@ SIGNATURES = [
 ]
 
 SLB_SWEEP_EXACT = 1
+SLB_SWEEP_INSIDE_EDGE = 2
 SLB_E_UNSUPPORTED = -4
 SLB_RESHARD_NONE, SLB_RESHARD_OUT_BLOCKED, SLB_RESHARD_IN_BLOCKED = 0, 1, 2
 

@@ -91,6 +91,10 @@ class Advection:
         self.sizeall = tuple(len(m) for m in t_mesh)
         self.t_mesh = tuple(t_mesh)
         self.t_interp = list(t_interp)
+        if any(getattr(it, "edge", 1) != 1 for it in self.t_interp):
+            # the reference's advection! has no method for InsideEdge interpolations (its per-line call passes
+            # one weight vector, src/advection.jl:627-631); they exist at the kernel seam only
+            raise ValueError("InsideEdge interpolations are available through interpolate() only, not through Advection")
         self.dt_base = float(dt_base)
         self.states = [StateAdv(i + 1, *s) for i, s in enumerate(states)]
         for s in self.states:

@@ -248,15 +248,24 @@ class AbstractInterpolation:
         return f"{type(self).__name__}{{Float64,CircEdge,{self.order}}}"
 
 
+# @enum EdgeType, src/interpolation.jl:3
+CircEdge, InsideEdge = 1, 2
+
+
 class Lagrange(AbstractInterpolation):
-    """Lagrange(order) -- src/lagrange.jl:58-72"""
+    """Lagrange(order; edge = CircEdge) -- src/lagrange.jl:58-72.  edge = InsideEdge selects the
+    non-periodic variant of the kernel seam (src/interpolation.jl:123-132, :250-286): one-sided stencils
+    near the ends of the line instead of the periodic wrap."""
 
     kind = LAGRANGE
 
-    def __init__(self, order):
+    def __init__(self, order, edge=CircEdge):
         super().__init__(order)
         if order < 1:
             raise ValueError("order must be >= 1")
+        if edge not in (CircEdge, InsideEdge):
+            raise ValueError("edge must be CircEdge or InsideEdge")
+        self.edge = edge
         self.tabfct = _to_float_table(lagrange_table(order))
 
 

@@ -30,6 +30,8 @@ def interpolate_lines(fi, dec, interp, ctx=None, flags=0, axis=0):
         strides = [0, 0]
         strides[other] = 1
         h = interp.handle(ctx, fi.shape[axis])
+        if getattr(interp, "edge", 1) == 2:  # InsideEdge: src/interpolation.jl:308-314
+            flags = int(flags) | _lib.SLB_SWEEP_INSIDE_EDGE
         _lib.check(L.slb_sweep(g, axis, h, dec.ctypes.data_as(C.c_void_p), nl, _lib.i64(strides), 1.0, 0, int(flags)))
         out = np.empty(fi.shape, dtype=np.float64, order="F")
         _lib.check(L.slb_grid_download(g, out.ctypes.data_as(C.c_void_p)))

@@ -4,10 +4,13 @@ Tolerance (BASELINE.json north_star): per sweep, max|gpu - oracle| / max|oracle|
 With SLB_SWEEP_EXACT the Lagrange/Hermite stencil is evaluated in the reference's own
 operation order and must agree with the oracle BIT FOR BIT.
 """
+import math
+
 import numpy as np
 import pytest
 
 from helpers import DeviceGrid, make_pair, oracle_sweep, relerr
+from oracle import refmodel as R
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -159,3 +162,46 @@ def test_error_behaviour():
     # alpha table too short
     with pytest.raises(ValueError):
         g.sweep(0, S.Lagrange(5), np.zeros(2), [0, 1])
+
+
+@pytest.mark.gpu
+def test_inside_edge_matches_oracle():
+    """InsideEdge Lagrange at the kernel seam (src/interpolation.jl:123-132, :250-286): SLB_SWEEP_EXACT is
+    bitwise the oracle, the FMA form within 1e-12; the reference's cubic KAT holds on the device; lines
+    along either axis; shifts that leave the array raise."""
+    import slb200 as S
+    from test_oracle_interp import TABDEC_INSIDE
+
+    rng = np.random.default_rng(8)
+    for order, n in ((3, 128), (7, 128), (5, 40), (9, 64)):
+        its, ito = S.Lagrange(order, edge=S.InsideEdge), R.Lagrange(order, edge=R.InsideEdge)
+        decs = [d for d in TABDEC_INSIDE if abs(math.floor(d)) <= order // 2 - 1] + [0.0, float(order // 2) - 0.25, -float(order // 2) + 0.5]
+        f = np.asfortranarray(rng.random((n, len(decs))))
+        ref = np.empty_like(f)
+        for k, d in enumerate(decs):
+            col = np.empty(n)
+            R.interpolate(col, np.ascontiguousarray(f[:, k]), d, ito)
+            ref[:, k] = col
+        out = S.interpolate_lines(f, decs, its, flags=S.SLB_SWEEP_EXACT)
+        assert np.array_equal(out, ref)
+        out = S.interpolate_lines(f, decs, its)
+        assert relerr(out, ref) <= TOL
+        out_t = S.interpolate_lines(np.asfortranarray(f.T), decs, its, axis=1)  # lines along the strided axis
+        assert relerr(out_t.T, ref) <= TOL
+    mesh = np.arange(128) / 128
+    cubic = lambda x: x**3 - x**2 - x / 6 + 0.25
+    fp = np.empty(128)
+    S.interpolate(fp, cubic(mesh), 3 / 1024, S.Lagrange(3, edge=S.InsideEdge))
+    assert np.max(np.abs(fp - cubic(mesh + (3 / 1024) / 128))) < 1e-15   # test/test_interpolation.jl:488
+    with pytest.raises(ValueError):
+        S.interpolate(fp, cubic(mesh), 5.7, S.Lagrange(7, edge=S.InsideEdge))
+    with pytest.raises(S.SlbError):
+        S.interpolate_lines(np.zeros((64, 2), order="F"), [0.1, 0.2], S.BSplineLU(5, 64), flags=S.SLB_SWEEP_INSIDE_EDGE)
+
+
+def test_inside_edge_is_a_kernel_seam_feature_only():
+    import slb200 as S
+
+    m = S.UniformMesh(0.0, 1.0, 16)
+    with pytest.raises(ValueError):
+        S.Advection((m, m), [S.Lagrange(3, edge=S.InsideEdge)] * 2, 0.1, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)])

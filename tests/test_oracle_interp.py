@@ -300,3 +300,39 @@ def test_oracle_nd_constant_shift_state_equals_split_1d_states():
             pass
     assert np.max(np.abs(a.data - b.data)) <= 1e-13 * np.max(np.abs(b.data))
     assert abs(R.compute_ee(a) - R.compute_ee(b)) <= 1e-12 * abs(R.compute_ee(b))
+
+
+TABDEC_INSIDE = [0.345141526199181716726626262655544, -0.3859416191876155241320011187619, -1.28561390114441619187615524132001118762519,
+                 -0.885901390114441619187615524132001118762519, 0.186666659416191876155241320011187619,
+                 0.590999232323232323232365566787878898898, 1.231098015934444444444444788888888878878]
+
+
+def test_inside_edge_kats():
+    """InsideEdge Lagrange (src/interpolation.jl:123-132, :250-286), pinned by the reference's own tests:
+    a cubic is reproduced at EVERY point, ends included (test/test_interpolation.jl:22-75, :488: exact in
+    rational arithmetic there, to rounding here), and the analytic shifts of test_interpfloat
+    (:424-483, :498: Lagrange 7, n = 128, 3 repeated shifts, tolerance 1e-3, |decint| <= 2)."""
+    sz = 128
+    mesh = np.arange(sz) / sz
+    cubic = lambda x: x**3 - x**2 - x / 6 + 0.25
+    fp = np.empty(sz)
+    R.interpolate(fp, cubic(mesh), 3 / 1024, R.Lagrange(3, edge=R.InsideEdge))
+    assert np.max(np.abs(fp - cubic(mesh + (3 / 1024) / sz))) < 1e-15
+    it = R.Lagrange(7, edge=R.InsideEdge)
+    for fct in (lambda x: np.cos(2 * np.pi * x + 0.25), lambda x: np.exp(-((np.cos(2 * np.pi * x + 0.25) - 1) ** 2))):
+        for dec in TABDEC_INSIDE:
+            fp = fct(mesh)
+            for i in range(1, 4):
+                fi = fp.copy()
+                fp = np.empty(sz)
+                R.interpolate(fp, fi, dec, it)
+                assert np.max(np.abs(fp - fct(mesh + i * dec / sz))) < 1e-3
+    # a shift whose window leaves the array is an error (the reference indexes out of bounds)
+    with pytest.raises(ValueError):
+        R.interpolate(np.empty(sz), cubic(mesh), 5.7, it)
+    # away from the ends InsideEdge and CircEdge agree
+    a, b = np.empty(sz), np.empty(sz)
+    f = np.random.default_rng(2).random(sz)
+    R.interpolate(a, f, 1.3, it)
+    R.interpolate(b, f, 1.3, R.Lagrange(7))
+    assert np.array_equal(a[8:-8], b[8:-8]) and not np.array_equal(a[:3], b[:3])
