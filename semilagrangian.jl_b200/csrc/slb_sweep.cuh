@@ -443,7 +443,7 @@ k_sweep_generic(const double* __restrict__ in, double* __restrict__ out, long lo
 // stencil window never leaves the line.  With indbeg = decint - order/2 (must satisfy
 // -order <= indbeg <= 0), 1-based output i uses
 //     i <= -indbeg              : res[1 : order+1]            weights tabfct(t + indbeg + i - 1)
-//     -indbeg < i <= n+indbeg   : res[i+indbeg : i+indbeg+order]   weights tabfct(t)      (the usual ones)
+//     -indbeg < i <= n-decint-order/2-1 : res[i+indbeg : i+indbeg+order]   weights tabfct(t)  (the usual ones)
 //     else                      : res[n-order : n]            weights tabfct(t + indbeg + order - (n - i))
 // i.e. near the ends the same polynomial is evaluated outside [0, 1] (one-sided stencils).  Thread per
 // line, any dim, run-time order; lines whose shift violates the bound are filled with NaN (the reference
@@ -469,7 +469,8 @@ k_sweep_inside(const double* __restrict__ in, double* __restrict__ out, long lon
         return;
     }
     const int indbeg = (int)dib;
-    const int borne1 = -indbeg, borne2 = n + indbeg;  // 1-based bounds of the three regimes
+    // 1-based bounds of the three regimes: borne1 = -decint - origin, borne2 = lg - decint + origin - 1 (:264-265)
+    const int borne1 = -indbeg, borne2 = n - (int)fl - order / 2 - 1;
     double wmid[64], we[64];
     for (int j = 0; j < np; ++j) {
         const double* c = coef + j * nc;
