@@ -4,6 +4,7 @@
 #include "slb_bspline.cuh"
 #include "slb_points.cuh"
 #include "slb_bspsplit.cuh"
+#include "slb_bsprf.cuh"
 
 extern "C" int slbt_bspline_solve_host(int order, long long n, const double* node_vals, const double* b, double* x)
 {
@@ -68,5 +69,28 @@ extern "C" int slbt_bspsplit_solve_host(int order, long long n, const double* no
     bspsplit_fill(&tab, v, hb);
     for (long long i = 0; i < n; ++i) x[i] = b[i];
     bspsplit_solve_line(tab, v.data(), x, x);
+    return 0;
+}
+
+// Host run of the recursive-filter B-spline solver (slb_bsprf.cuh): pole search, start-up tables, the
+// kernel's table layout and its per-line arithmetic; x = A^{-1} b.
+extern "C" int slbt_bsprf_solve_host(int order, long long n, const double* node_vals, const double* b, double* x, int* K_out)
+{
+    BspRfHost hb;
+    std::string msg;
+    int rc = bsprf_factor(order, n, node_vals, &hb, msg);
+    if (rc) return rc;
+    BspRfTab tab;
+    std::vector<double> v;
+    bsprf_fill(&tab, v, hb);
+    for (long long i = 0; i < n; ++i) x[i] = b[i];
+    switch (hb.h) {
+#define X(H) case H: bsprf_solve_line<H>(tab, v.data(), x, 1); break;
+        X(1) X(2) X(3) X(4) X(5) X(6)
+#undef X
+        default: return SLB_E_UNSUPPORTED;
+    }
+    for (long long i = 0; i < n; ++i) x[i] *= v[hb.h];
+    if (K_out) for (int k = 0; k < hb.h; ++k) K_out[k] = hb.K[k];
     return 0;
 }

@@ -90,6 +90,8 @@ struct slb_interp {
     BsplineDev bsp;            // LU factors / circulant symbol on the device (B-spline kinds)
     double* bsptab_dev;        // the same factors in the fused sweep's record layout (device), or NULL
     BspFusedTab bsptab;
+    double* bsprf_dev;         // table of the recursive-filter form of the pre-solve (slb_bsprf.cuh), or NULL
+    BspRfTab bsprf;
     double* bspstab_dev;       // tables of the split-line fused sweep (two warps per tile, slb_bspsplit.cuh), or NULL
     BspSplitTab bspstab;
 };
@@ -439,6 +441,8 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
     memset(&it->bsptab, 0, sizeof(it->bsptab));
     it->bspstab_dev = nullptr;
     memset(&it->bspstab, 0, sizeof(it->bspstab));
+    it->bsprf_dev = nullptr;
+    memset(&it->bsprf, 0, sizeof(it->bsprf));
     if (bs) {
         std::string msg;
         BsplineHost hb;
@@ -458,6 +462,23 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
                 if (it->bsptab_dev) cudaFree(it->bsptab_dev);
                 it->bsptab_dev = nullptr;
                 cudaGetLastError();
+            }
+        }
+        if (it->fast && hb.h <= SLB_BSPRF_HMAX) {
+            BspRfHost hr;
+            std::string msg2;
+            if (bsprf_factor(order, n, node_vals, &hr, msg2) == SLB_OK) {
+                std::vector<double> v;
+                bsprf_fill(&it->bsprf, v, hr);
+                if (slb_bspfused_warps_rf(it->bsprf.ndoubles, hb.n, true) > 0) {
+                    cudaError_t e2 = cudaMalloc(&it->bsprf_dev, v.size() * sizeof(double));
+                    if (e2 == cudaSuccess) e2 = cudaMemcpy(it->bsprf_dev, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+                    if (e2 != cudaSuccess) {
+                        if (it->bsprf_dev) cudaFree(it->bsprf_dev);
+                        it->bsprf_dev = nullptr;
+                        cudaGetLastError();
+                    }
+                }
             }
         }
         if (it->fast && slb_bspsplit_tiles(hb.h, hb.n) > 0) {
@@ -488,6 +509,7 @@ extern "C" void slb_interp_destroy(slb_interp* it)
     bspline_free(&it->bsp);
     if (it->bsptab_dev) cudaFree(it->bsptab_dev);
     if (it->bspstab_dev) cudaFree(it->bspstab_dev);
+    if (it->bsprf_dev) cudaFree(it->bsprf_dev);
     delete it;
 }
 
@@ -696,7 +718,8 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         LAUNCH_CHECK(c);
         return slb_grid_swap(g);
     }
-    if (bs && it->bspstab_dev && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) && env_ll("SLB_BSPLINE_FUSED", 1) != 0 &&
+    const bool use_rf = bs && it->bsprf_dev && env_ll("SLB_BSPLINE_RF", 1) != 0;
+    if (!use_rf && bs && it->bspstab_dev && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) && env_ll("SLB_BSPLINE_FUSED", 1) != 0 &&
         env_ll("SLB_BSPLINE_SPLIT", 1) != 0) {
         // strided dims: pre-solve + stencil in one pass with two warps per tile of lines (slb_bspsplit.cuh)
         BspSplitArgs a;
@@ -718,7 +741,7 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         c->launches++;
         return slb_grid_swap(g);
     }
-    if (bs && it->bsptab_dev && !(flags & SLB_SWEEP_EXACT) && !(g->linesum && dim == 0) && !(omp && dim == 0) && !(imp && dim != 0) &&
+    if (bs && (use_rf || it->bsptab_dev) && !(flags & SLB_SWEEP_EXACT) && !(g->linesum && dim == 0) && !(omp && dim == 0) && !(imp && dim != 0) &&
         env_ll("SLB_BSPLINE_FUSED", 1) != 0) {
         // pre-solve + stencil in one pass over HBM (slb_bspfused.cuh): front -> back, then swap
         BspFusedArgs a;
@@ -738,9 +761,16 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         }
         if (imp) a.im = *imp;
         a.linesum = g->linesum;
-        a.tab_dev = it->bsptab_dev;
-        a.tab = it->bsptab;
-        a.warps = slb_bspfused_warps(it->bsptab.h, v.n, v.inner == 1);
+        if (use_rf) {
+            a.use_rf = 1;
+            a.rf = it->bsprf;
+            a.tab_dev = it->bsprf_dev;
+            a.warps = slb_bspfused_warps_rf(it->bsprf.ndoubles, v.n, v.inner == 1);
+        } else {
+            a.tab_dev = it->bsptab_dev;
+            a.tab = it->bsptab;
+            a.warps = slb_bspfused_warps(it->bsptab.h, v.n, v.inner == 1);
+        }
         int lrc = slb_bspfused_launch(a, it->tab, c->sm_count, c->stream);
         if (lrc != 0) return fail(lrc < 0 ? SLB_E_UNSUPPORTED : SLB_E_CUDA, "slb_sweep: fused B-spline launch failed (%d)", lrc);
         c->launches++;

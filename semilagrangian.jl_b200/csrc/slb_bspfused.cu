@@ -23,6 +23,15 @@ int slb_bspfused_warps(int h, int n, bool contig)
     return (int)(w > 8 ? 8 : w);
 }
 
+int slb_bspfused_warps_rf(int ndoubles, int n, bool contig)
+{
+    const size_t tab = ((size_t)ndoubles + 1) / 2 * 2 * sizeof(double);
+    const size_t tile = (size_t)n * (contig ? 33 : 32) * sizeof(double);
+    if (tab + tile > SLB_BSPF_SMEM_MAX) return 0;
+    size_t w = (SLB_BSPF_SMEM_MAX - tab) / tile;
+    return (int)(w > 8 ? 8 : w);
+}
+
 bool slb_bspfused_supported(int h, int n) { return slb_bspfused_warps(h, n, true) > 0; }
 
 void slb_bspfused_fill(BspFusedTab* tab, double* v, int h, int n, int N, const double* L, const double* U, const double* invd,
@@ -50,11 +59,11 @@ void slb_bspfused_fill(BspFusedTab* tab, double* v, int h, int n, int N, const d
     memcpy(v + tab->o_S, Sinv, (size_t)h * h * sizeof(double));
 }
 
-template <int H, bool CONTIG>
+template <int H, bool CONTIG, bool RF>
 static int launch1(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream)
 {
-    auto kern = k_bspline_fused<H, CONTIG>;
-    const size_t tab = ((size_t)a.tab.ndoubles + 1) / 2 * 2 * sizeof(double);
+    auto kern = k_bspline_fused<H, CONTIG, RF>;
+    const size_t tab = ((size_t)(RF ? a.rf.ndoubles : a.tab.ndoubles) + 1) / 2 * 2 * sizeof(double);
     const size_t smem = tab + (size_t)a.warps * a.n * (CONTIG ? 33 : 32) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -68,10 +77,21 @@ static int launch1(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaS
 int slb_bspfused_launch(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream)
 {
     const bool contig = (a.inner == 1);
+    if (a.warps < 1 || a.warps > 8) return -1;
+    if (a.use_rf) {
+        switch (a.rf.h) {
+#define X(H) \
+    case H:  \
+        return contig ? launch1<H, true, true>(a, ct, sm_count, stream) : launch1<H, false, true>(a, ct, sm_count, stream);
+            SLB_BSPF_FOR_H(X)
+#undef X
+        }
+        return -1;
+    }
     switch (a.tab.h) {
 #define X(H) \
     case H:  \
-        return contig ? launch1<H, true>(a, ct, sm_count, stream) : launch1<H, false>(a, ct, sm_count, stream);
+        return contig ? launch1<H, true, false>(a, ct, sm_count, stream) : launch1<H, false, false>(a, ct, sm_count, stream);
         SLB_BSPF_FOR_H(X)
 #undef X
     }

@@ -31,6 +31,7 @@
 #include <stdint.h>
 
 #include "slb_sweep.cuh"
+#include "slb_bsprf.cuh"
 
 // Factor tables (device memory, copied to shared memory by every block):
 //   forward  record i < N : { L[i][0..h), Ri[i][0..h) }                        2h doubles
@@ -56,11 +57,14 @@ struct BspFusedArgs {
     double* linesum;   // strided variant, optional: per-line sums of the outputs
     const double* tab_dev;
     BspFusedTab tab;
+    int use_rf;        // 1: the solve is the constant-coefficient recursive-filter cascade (slb_bsprf.cuh);
+    BspRfTab rf;       //    tab_dev then holds its table (poles, gain, start-up responses)
 };
 
 int slb_bspfused_launch(const BspFusedArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream);
 // warps per block that fit the shared memory next to the tables; 0: unsupported
 int slb_bspfused_warps(int h, int n, bool contig);
+int slb_bspfused_warps_rf(int ndoubles, int n, bool contig);
 bool slb_bspfused_supported(int h, int n);
 // host table in the kernel's layout
 void slb_bspfused_fill(BspFusedTab* tab, double* v, int h, int n, int N, const double* L, const double* U, const double* invd,
@@ -85,7 +89,7 @@ __device__ __forceinline__ void bspf_ldrec(double (&dst)[NV], const double* src)
     }
 }
 
-template <int H, bool CONTIG>
+template <int H, bool CONTIG, bool RF>
 __global__ void __launch_bounds__(256, 1)
 k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__ CoefTab ct)
 {
@@ -97,13 +101,14 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = fa.n, N = fa.tab.N;
     // ---- factor tables: one copy per block --------------------------------------------------------
+    const int ntab = RF ? fa.rf.ndoubles : fa.tab.ndoubles;
     double* tabs = bsm;
-    for (int i = threadIdx.x; i < fa.tab.ndoubles; i += blockDim.x) tabs[i] = __ldg(fa.tab_dev + i);
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) tabs[i] = __ldg(fa.tab_dev + i);
     __syncthreads();
     const double* tF = tabs;
     const double* tB = tabs + fa.tab.o_bwd;
     const double* tS = tabs + fa.tab.o_S;
-    double* tile = bsm + ((fa.tab.ndoubles + 1) & ~1) + (size_t)wid * n * PITCH;
+    double* tile = bsm + ((ntab + 1) & ~1) + (size_t)wid * n * PITCH;
     int* s0s = s0s_all[wid];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
     double* col = tile + lane;
@@ -151,11 +156,21 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < P1; ++j) w[j] = fma(tt, w[j], ct.c[j * SLB_NCMAX + k]);
         }
+        if (RF) {  // the cascade returns C A^{-1} u: the gain goes into the stencil weights
+            const double invC = tabs[H];
+#pragma unroll
+            for (int j = 0; j < P1; ++j) w[j] *= invC;
+        }
     }
     if (CONTIG) s0s[lane] = s0;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
+    if (RF) {
+        // ---- 2'. recursive-filter cascade, in place, thread per line (slb_bsprf.cuh): 2h FMAs per cell,
+        // poles in registers, no per-row tables
+        bsprf_solve_line<H>(fa.rf, tabs, col, PITCH);
+    } else {
     // ---- 2. bordered banded LU solve, in place, thread per line ---------------------------------
     // Both recurrences are arranged so that the newest dependency enters LAST: the terms that use
     // older results are summed first, the right-hand side is added, and only one FMA per row waits
@@ -286,6 +301,7 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
         }
 #undef BSPF_BWD_ROW
     }
+    }  // !RF
 
     // ---- 3. stencil, thread per line ---------------------------------------------------------------
     // window slot convention of slb_dot: logical element j of output i lives in win[(i + j) % P1]

@@ -144,6 +144,27 @@ def test_split_line_solver_host(order, n):
     assert np.max(np.abs(x - ref)) <= 1e-13 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("order,n", [(3, 16), (3, 128), (5, 64), (5, 128), (5, 1024), (7, 128), (9, 30), (9, 100), (11, 128), (11, 256), (13, 64), (13, 14)])
+def test_recursive_filter_solver_host(order, n):
+    """The constant-coefficient recursive-filter form of the periodic B-spline pre-solve
+    (slb_bsprf.cuh: pole search, aliased start-up tables, per-line cascade), executed on the host,
+    equals the reference's cyclic LU solve; odd and non-power-of-two n included."""
+    so = os.path.join(ROOT, "semilagrangian.jl_b200", "lib", "libslb200_hosttest.so")
+    L = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    L.slbt_bsprf_solve_host.argtypes = [C.c_int, C.c_longlong, dp, dp, dp, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(78)
+    nodes = np.array([float(x) for x in T.bspline_node_values_rat(order)])
+    b = rng.random(n)
+    x = np.empty(n)
+    K = (C.c_int * 6)()
+    assert L.slbt_bsprf_solve_host(order, n, nodes.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp), K) == 0
+    ref = R.BSplineLU(order, n).sol(b)
+    assert np.max(np.abs(x - ref)) <= 1e-13 * np.max(np.abs(ref))
+    h = (order - 1) // 2
+    assert all(1 <= K[k] <= n for k in range(h)) and list(K[:h]) == sorted(K[:h])
+
+
 def test_driver_level_oracle_kats():
     """Oracle driver pinned by the reference's integration tests: rotation returns to the
     start (test/test_rotation.jl:237-252, err < 1e-3) and Poisson pieces are consistent

@@ -50,16 +50,16 @@ PY
       timeout 300 python -m pytest tests/test_gpu_sweep.py tests/test_gpu_driver.py -q -x -k "bspline or spline" > "$OUT/pytest_bsp.log" 2>&1
       echo "bsptest rc=$?"; tail -5 "$OUT/pytest_bsp.log" ;;
     bspab)
-      for split in 1 0; do
+      for split in ${BSPAB_MODES:-1 0}; do
         for cfg in "bspline_fft 11" "bspline_lu 5" "bspline_lu 3"; do
           set -- $cfg
-          SLB_BSPLINE_SPLIT=$split timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu 2>>"$OUT/bench_bspab.err" | tail -1 > "$OUT/tmp.json"
+          SLB_BSPLINE_RF=$split timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu 2>>"$OUT/bench_bspab.err" | tail -1 > "$OUT/tmp.json"
           python - <<PY
 import json
 d = json.load(open("$OUT/tmp.json")); k = d["roofline"]["all_kernels"]; c = d["config"]
-print("split=$split", c["interp"], c["order"], "ms/step %.3f" % d["ms_per_step"], "Gcell/s %.1f" % d["value"], {n.split("/")[1]: round(v["ms"], 3) for n, v in k.items() if "fused" not in n})
+print("rf=$split", c["interp"], c["order"], "ms/step %.3f" % d["ms_per_step"], "Gcell/s %.1f" % d["value"], {n.split("/")[1]: round(v["ms"], 3) for n, v in k.items() if "fused" not in n})
 PY
-          cat "$OUT/tmp.json" >> "$OUT/bench_bspab_split$split.jsonl"
+          cat "$OUT/tmp.json" >> "$OUT/bench_bspab_rf$split.jsonl"
         done
       done ;;
     ncusplit)
