@@ -719,8 +719,9 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         return slb_grid_swap(g);
     }
     const bool use_rf = bs && it->bsprf_dev && env_ll("SLB_BSPLINE_RF", 1) != 0;
-    if (!use_rf && bs && it->bspstab_dev && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) && env_ll("SLB_BSPLINE_FUSED", 1) != 0 &&
-        env_ll("SLB_BSPLINE_SPLIT", 1) != 0) {
+    const bool rf_split = use_rf && dim > 0 && !omp && !imp && slb_bspsplit_tiles_rf(it->bsprf.ndoubles, v.n) > 0;
+    if (bs && (rf_split || (!use_rf && it->bspstab_dev)) && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) &&
+        env_ll("SLB_BSPLINE_FUSED", 1) != 0 && env_ll("SLB_BSPLINE_SPLIT", 1) != 0) {
         // strided dims: pre-solve + stencil in one pass with two warps per tile of lines (slb_bspsplit.cuh)
         BspSplitArgs a;
         memset(&a, 0, sizeof(a));
@@ -731,11 +732,18 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         a.bstride = (long long)v.n * v.inner;
         a.n = v.n;
         a.nc = it->nc;
-        a.tiles = slb_bspsplit_tiles(it->bspstab.h, v.n);
         a.am = am;
         a.linesum = g->linesum;
-        a.tab_dev = it->bspstab_dev;
-        a.tab = it->bspstab;
+        if (rf_split) {
+            a.use_rf = 1;
+            a.rf = it->bsprf;
+            a.tab_dev = it->bsprf_dev;
+            a.tiles = slb_bspsplit_tiles_rf(it->bsprf.ndoubles, v.n);
+        } else {
+            a.tiles = slb_bspsplit_tiles(it->bspstab.h, v.n);
+            a.tab_dev = it->bspstab_dev;
+            a.tab = it->bspstab;
+        }
         int lrc = slb_bspsplit_launch(a, it->tab, c->sm_count, c->stream);
         if (lrc != 0) return fail(lrc < 0 ? SLB_E_UNSUPPORTED : SLB_E_CUDA, "slb_sweep: split B-spline launch failed (%d)", lrc);
         c->launches++;
@@ -761,6 +769,7 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         }
         if (imp) a.im = *imp;
         a.linesum = g->linesum;
+        a.stagger = (int)env_ll("SLB_BSPLINE_STAGGER", 0);
         if (use_rf) {
             a.use_rf = 1;
             a.rf = it->bsprf;

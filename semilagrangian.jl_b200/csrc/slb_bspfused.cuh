@@ -57,6 +57,8 @@ struct BspFusedArgs {
     double* linesum;   // strided variant, optional: per-line sums of the outputs
     const double* tab_dev;
     BspFusedTab tab;
+    int stagger;       // cycles by which consecutive warps of a block delay their first tile (0: none): de-phases the
+                       // load / compute cycles of the warps, which otherwise stay in lockstep
     int use_rf;        // 1: the solve is the constant-coefficient recursive-filter cascade (slb_bsprf.cuh);
     BspRfTab rf;       //    tab_dev then holds its table (poles, gain, start-up responses)
 };
@@ -113,6 +115,10 @@ k_bspline_fused(const __grid_constant__ BspFusedArgs fa, const __grid_constant__
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
     double* col = tile + lane;
     const long long ntiles = (fa.nlines + 31) / 32;
+    if (fa.stagger > 0 && wid > 0) {
+        const long long t0 = clock64(), wait = (long long)fa.stagger * wid;
+        while (clock64() - t0 < wait) __nanosleep(200);
+    }
 
     for (long long t = (long long)blockIdx.x * fa.warps + wid; t < ntiles; t += (long long)gridDim.x * fa.warps) {
     const long long line0 = t * 32;

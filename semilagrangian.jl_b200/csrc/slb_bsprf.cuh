@@ -187,6 +187,38 @@ __host__ __device__ __forceinline__ void bsprf_init(const BspRfTab& t, const dou
     }
 }
 
+// Same with periodic indexing: x[(r0 + dir * r) mod n] -- start-up of a cascade that begins in the middle
+// of the line (the state before ANY row m is sum_r G_k[r] x[(m-1-r) mod n], which is what lets several
+// threads work on segments of one line independently).  Four partial sums: the loop is a latency chain.
+template <int H>
+__host__ __device__ __forceinline__ void bsprf_init_wrap(const BspRfTab& t, const double* tab, const double* x, int pitch, int n,
+                                                         int r0, int dir, double (&s)[H])
+{
+    r0 = r0 < 0 ? r0 + n : (r0 >= n ? r0 - n : r0);
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const double* G = tab + t.oG[k];
+        const int K = t.K[k];
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        int idx = r0;
+        int r = 0;
+        for (; r + 3 < K; r += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = fma(G[r + q], x[(long long)idx * pitch], a[q]);
+                idx += dir;
+                idx = idx < 0 ? idx + n : (idx >= n ? idx - n : idx);
+            }
+        }
+        for (; r < K; ++r) {
+            a[0] = fma(G[r], x[(long long)idx * pitch], a[0]);
+            idx += dir;
+            idx = idx < 0 ? idx + n : (idx >= n ? idx - n : idx);
+        }
+        s[k] = (a[0] + a[1]) + (a[2] + a[3]);
+    }
+}
+
 // One pass of the cascade over the line, rows i0, i0 + dir, ... (n rows), in place.  Rows are handled
 // in groups of 8 whose inputs are fetched one group ahead; within a group the h stages of consecutive
 // rows overlap (row r+1 stage k only waits for row r stage k and row r+1 stage k-1), so the chain is one

@@ -40,6 +40,7 @@
 
 #include "../../include/slb200.h"
 #include "slb_sweep.cuh"
+#include "slb_bsprf.cuh"
 
 struct BspSplitHost {
     int h, n, Na;
@@ -273,13 +274,17 @@ struct BspSplitArgs {
     double* linesum;    // optional: per-line sums of the outputs
     const double* tab_dev;
     BspSplitTab tab;
+    int use_rf;         // 1: each warp runs the recursive-filter cascade (slb_bsprf.cuh) on its half of the rows,
+    BspRfTab rf;        //    started from the periodic look-back sums; tab_dev then holds the RF table
 };
 
+int slb_bspsplit_tiles_rf(int ndoubles, int n);
 int slb_bspsplit_launch(const BspSplitArgs& a, const CoefTab& ct, int sm_count, cudaStream_t stream);
 int slb_bspsplit_tiles(int h, int n);   // tiles per block that fit the shared memory next to the tables; 0: unsupported
 
 #ifdef SLB_BSPS_IMPL
-#define SLB_BSPS_MAXTILES 6
+#define SLB_BSPS_MAXTILES 6      // LU form: 163 registers x 384 threads
+#define SLB_BSPS_MAXTILES_RF 7   // recursive-filter form: lighter threads, smaller tables
 
 __device__ __forceinline__ void bsps_cp_async8(unsigned smem_dst, const void* gsrc)
 {
@@ -309,8 +314,8 @@ __device__ __forceinline__ void bsps_ldrec(double (&dst)[NV], const double* src)
 #endif
 }
 
-template <int H>
-__global__ void __launch_bounds__(64 * SLB_BSPS_MAXTILES, 1)
+template <int H, bool RF>
+__global__ void __launch_bounds__(RF ? 64 * SLB_BSPS_MAXTILES_RF : 64 * SLB_BSPS_MAXTILES, 1)
 k_bspline_split(const __grid_constant__ BspSplitArgs fa, const __grid_constant__ CoefTab ct)
 {
     constexpr int P1 = 2 * H + 2;  // order + 1 stencil points, order = 2h + 1
@@ -318,19 +323,20 @@ k_bspline_split(const __grid_constant__ BspSplitArgs fa, const __grid_constant__
     constexpr int PITCH = 32;
     constexpr int FR = bsps_FR(H), BR = bsps_BR(H);
     extern __shared__ __align__(16) double bsm[];
-    __shared__ double lsx[SLB_BSPS_MAXTILES][32];
+    __shared__ double lsx[SLB_BSPS_MAXTILES_RF][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ts = wid >> 1;  // tile slot of this warp pair
     const int s = wid & 1;    // which half of the line this warp owns
     const int n = fa.n, Na = fa.tab.Na, nh = n >> 1;
     // ---- factor tables: one copy per block ------------------------------------------------------
+    const int ntab = RF ? fa.rf.ndoubles : fa.tab.ndoubles;
     double* tabs = bsm;
-    for (int i = threadIdx.x; i < fa.tab.ndoubles; i += blockDim.x) tabs[i] = __ldg(fa.tab_dev + i);
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) tabs[i] = __ldg(fa.tab_dev + i);
     __syncthreads();
     const double* tF = tabs;
     const double* tB = tabs + fa.tab.o_bwd;
     const double* tS = tabs + fa.tab.o_S;
-    double* tile = bsm + ((fa.tab.ndoubles + 1) & ~1) + (size_t)ts * n * PITCH;
+    double* tile = bsm + ((ntab + 1) & ~1) + (size_t)ts * n * PITCH;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(tile);
     double* col = tile + lane;                   // this lane's line: element k at col[k * PITCH]
     double* colh = col + (size_t)s * nh * PITCH;  // its own half: local row i at colh[i * PITCH]
@@ -371,10 +377,32 @@ k_bspline_split(const __grid_constant__ BspSplitArgs fa, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < P1; ++j) w[j] = fma(tt, w[j], ct.c[j * SLB_NCMAX + k]);
         }
+        if (RF) {  // the cascade returns C A^{-1} u: the gain goes into the stencil weights
+            const double invC = tabs[H];
+#pragma unroll
+            for (int j = 0; j < P1; ++j) w[j] *= invC;
+        }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
+    if (RF) {
+        // ---- 2'. recursive-filter cascade on this warp's rows [s n/2, (s+1) n/2) (slb_bsprf.cuh).  The state
+        // of the cascade before any row m is a short periodic look-back sum, so the two halves of a line
+        // are independent; the barriers only order the in-place updates against the look-back reads.
+        double z[H], st[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) z[k] = tabs[k];
+        const int m0 = s * nh;
+        BSPS_PAIR_SYNC();  // every row of the line has arrived
+        bsprf_init_wrap<H>(fa.rf, tabs, col, PITCH, n, m0 - 1, -1, st);
+        BSPS_PAIR_SYNC();  // all causal start-up sums are done: the inputs may be overwritten
+        bsprf_pass<H>(z, st, col, PITCH, nh, m0, +1);
+        BSPS_PAIR_SYNC();  // causal output complete
+        bsprf_init_wrap<H>(fa.rf, tabs, col, PITCH, n, m0 + nh, +1, st);
+        BSPS_PAIR_SYNC();
+        bsprf_pass<H>(z, st, col, PITCH, nh, m0 + nh - 1, -1);
+    } else {
     // ---- 2. forward substitution on the own half; border sums --------------------------------------
     double x2[B];
     {
@@ -515,6 +543,7 @@ k_bspline_split(const __grid_constant__ BspSplitArgs fa, const __grid_constant__
         }
 #undef BSPS_BWD_ROW
     }
+    }  // !RF
     BSPS_PAIR_SYNC();  // the whole line is solved
 
     // ---- 4. stencil: this warp produces outputs [s n/2, (s+1) n/2) from the whole line --------------

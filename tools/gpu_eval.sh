@@ -63,7 +63,7 @@ PY
         done
       done ;;
     ncusplit)
-      timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_bspline_split -s 3 -c 1 \
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k_bspline_fused} -s 3 -c 1 \
         -f -o "$OUT/prof_split" python tools/prof_step.py --steps 1 --interp bspline_fft --order 11 > "$OUT/ncusplit.log" 2>&1
       echo "ncusplit rc=$?"; tail -3 "$OUT/ncusplit.log"; ls -la "$OUT" ;;
     configs)
