@@ -719,7 +719,10 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
         return slb_grid_swap(g);
     }
     const bool use_rf = bs && it->bsprf_dev && env_ll("SLB_BSPLINE_RF", 1) != 0;
-    const bool rf_split = use_rf && dim > 0 && !omp && !imp && slb_bspsplit_tiles_rf(it->bsprf.ndoubles, v.n) > 0;
+    // two warps per line pay off while the look-back start-up of a half line is short (measured at 128^4: order 3
+    // 0.94 -> 0.80 ms, order 5 1.05 -> 0.98 ms, order 11 1.55 -> 1.92 ms): orders 3 and 5 only
+    const bool rf_split = use_rf && dim > 0 && !omp && !imp && it->bsprf.h <= (int)env_ll("SLB_BSPLINE_RFSPLIT_HMAX", 2) &&
+                          slb_bspsplit_tiles_rf(it->bsprf.ndoubles, v.n) > 0;
     if (bs && (rf_split || (!use_rf && it->bspstab_dev)) && dim > 0 && !omp && !imp && !(flags & SLB_SWEEP_EXACT) &&
         env_ll("SLB_BSPLINE_FUSED", 1) != 0 && env_ll("SLB_BSPLINE_SPLIT", 1) != 0) {
         // strided dims: pre-solve + stencil in one pass with two warps per tile of lines (slb_bspsplit.cuh)
