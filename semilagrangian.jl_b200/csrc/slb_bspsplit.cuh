@@ -295,23 +295,12 @@ template <int NV>
 __device__ __forceinline__ void bsps_ldrec(double (&dst)[NV], const double* src)
 {
     static_assert(NV % 2 == 0, "records are whole 16-byte words");
-#ifdef SLB_BSPS_EXPERIMENT_HALF_TABLES  // timing experiment only (wrong results): half the table traffic
-#pragma unroll
-    for (int q = 0; q < NV / 2; q += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(src + q);
-        dst[q] = v.x;
-        dst[q + 1] = v.y;
-        dst[q + NV / 2] = v.y;
-        dst[q + 1 + NV / 2] = v.x;
-    }
-#else
 #pragma unroll
     for (int q = 0; q < NV; q += 2) {
         const double2 v = *reinterpret_cast<const double2*>(src + q);
         dst[q] = v.x;
         dst[q + 1] = v.y;
     }
-#endif
 }
 
 template <int H, bool RF>

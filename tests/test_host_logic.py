@@ -196,3 +196,23 @@ def test_driver_level_oracle_kats():
     # reference convention (src/poisson.jl:8,139-144): E_hat = (i k / |k|^2) rho_hat  ->  E = -(A/k) sin(kx)
     assert np.max(np.abs(E + 0.2 * np.sin(0.5 * mx.points) * (pv.rho.max() / 0.1))) < 1e-8
     assert abs(R.compute_ee(advd) - mx.step * np.sum(E**2)) < 1e-15
+
+
+def test_inside_edge_is_rejected_by_advection_and_accepted_by_the_types():
+    """InsideEdge exists at the kernel seam only: the reference's advection! has no method for it
+    (src/advection.jl:627-631 passes one weight vector, src/interpolation.jl:250-256 wants one per offset)."""
+    import slb200 as S
+
+    it = S.Lagrange(7, edge=S.InsideEdge)
+    assert it.edge == S.InsideEdge and S.Lagrange(7).edge == S.CircEdge
+    with pytest.raises(ValueError):
+        S.Lagrange(7, edge=3)
+    m = S.UniformMesh(0.0, 1.0, 16)
+    with pytest.raises(ValueError):
+        S.Advection((m, m), [it, it], 0.1, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)])
+    # the time-algorithm arguments of Advection (src/advection.jl:96-97)
+    adv = S.Advection((m, m), [S.Lagrange(3)] * 2, 0.1, [([1, 2], 2, 1, False)], tab_coef=S.nosplit(0.1), timealg=S.ABTimeAlg_ip)
+    assert adv.ordalg == 4 and len(adv.abcoef) == 5
+    assert S.Advection((m, m), [S.Lagrange(3)] * 2, 0.1, [([1, 2], 2, 1, False)], tab_coef=S.nosplit(0.1)).ordalg == 0
+    with pytest.raises(ValueError):
+        S.Advection((m, m), [S.Lagrange(3)] * 2, 0.1, [([1, 2], 2, 1, False)], timealg=9)
