@@ -125,6 +125,8 @@ end
 # -- the device-side replacement of getalpha(parext, advd, indext) (src/advection.jl:221-224).
 const PENDING = IdDict{Any,Any}()   # stage held back for pair fusion, per B200AdvectionData
 
+# slb_sweep flags (include/slb200.h): 1 = SLB_SWEEP_EXACT (the reference's operation order, bitwise),
+# 2 = SLB_SWEEP_INSIDE_EDGE (Lagrange(order; edge = InsideEdge) at the kernel seam, src/interpolation.jl:250-286)
 sweep_now(self, s) = check(ccall((:slb_sweep, LIB), Cint,
     (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Cdouble, Cint, Cint),
     self.grid, s.dim, self.interps[s.dim+1], s.tab, s.len, s.strides, s.scale, s.ondev, 0))
