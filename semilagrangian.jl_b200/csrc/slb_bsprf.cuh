@@ -164,8 +164,7 @@ static void bsprf_fill(BspRfTab* tab, std::vector<double>& v, const BspRfHost& h
     tab->ndoubles = (int)v.size();
 }
 
-// Start-up states of the cascade: s_k = sum_{r < K_k} G_k[r] x[r0 + dir * r] (four partial sums: the loop is
-// a latency chain, 108 terms long for the slowest stage of order 11).
+// Start-up states of the cascade: s_k = sum_{r < K_k} G_k[r] x[r0 + dir * r] (two partial sums).
 template <int H>
 __host__ __device__ __forceinline__ void bsprf_init(const BspRfTab& t, const double* tab, const double* x, int pitch, int r0,
                                                     int dir, double (&s)[H])
@@ -176,18 +175,15 @@ __host__ __device__ __forceinline__ void bsprf_init(const BspRfTab& t, const dou
         const int K = t.K[k];
         const double* p = x + (long long)r0 * pitch;
         const int st = dir * pitch;
-        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        double a0 = 0.0, a1 = 0.0;
         int r = 0;
-        for (; r + 3 < K; r += 4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) a[q] = fma(G[r + q], p[q * st], a[q]);
-            p += 4 * st;
+        for (; r + 1 < K; r += 2) {
+            a0 = fma(G[r], p[0], a0);
+            a1 = fma(G[r + 1], p[st], a1);
+            p += 2 * st;
         }
-        for (; r < K; ++r) {
-            a[0] = fma(G[r], p[0], a[0]);
-            p += st;
-        }
-        s[k] = (a[0] + a[1]) + (a[2] + a[3]);
+        if (r < K) a0 = fma(G[r], p[0], a0);
+        s[k] = a0 + a1;
     }
 }
 
