@@ -224,3 +224,51 @@ class RotationVar2d:
 
 def getrotationvar2d(adv):
     return RotationVar2d(adv)
+
+
+# ---------------------------------------------------------------------------------------
+# surface quasi-geostrophic provider -- src/quasigeostrophic.jl:1-135 (single unsplit 2-D state)
+# ---------------------------------------------------------------------------------------
+class GeoVar:
+    """GeoConst + GeoVar (src/quasigeostrophic.jl:6-74): u = real(ifft(coefrsqk .* fft(b))) with
+    coefrsqk[1] = i k_y / |k|, coefrsqk[2] = -i k_x / |k| (zero mode 0); bufcur = dt * (u_1, u_2)."""
+
+    def __init__(self, adv, odg_b=1e-3):
+        if adv.N != 2:
+            raise ValueError("the number of dimension must be 2")
+        self.odg_b = float(odg_b)
+        kx, ky = R.vec_k_fft(adv.t_mesh[0])[:, None], R.vec_k_fft(adv.t_mesh[1])[None, :]
+        k = np.sqrt(kx**2 + ky**2)       # sqrt(sum(tp .^ 2)): kx^2 + ky^2 summed left to right
+        with np.errstate(divide="ignore"):
+            v = np.where(k == 0, 0.0, 1.0 / k)
+        self.coef_imag = (np.asfortranarray(v * ky), np.asfortranarray(-(v * kx)))   # imaginary parts (:37-42)
+
+    def initdata(self, advd):
+        """initdata! -- src/quasigeostrophic.jl:79-104"""
+        mx, my = advd.adv.t_mesh
+        lx, ly = mx.stop - mx.start, my.stop - my.start
+        x, y = mx.points, my.points
+        ee = 4
+        sig = lx / 15
+
+        def anticyclone(cx, cy):
+            return np.exp(-ee * (x - cx) ** 2 / (2 * sig**2))[:, None] * np.exp(-((y - cy) ** 2) / (2 * sig**2))[None, :]
+
+        d = anticyclone(lx / 4, ly / 4)
+        d = d + anticyclone(3 * lx / 4, ly / 4)
+        d = d - anticyclone(lx / 4, 3 * ly / 4)
+        d = d - anticyclone(3 * lx / 4, 3 * ly / 4)
+        advd.data[...] = d * self.odg_b
+
+    def initcoef(self, advd):
+        """initcoef! -- src/quasigeostrophic.jl:109-121"""
+        dt = advd.getcur_t()
+        buf = np.fft.fft2(advd.data)
+        if advd.bufcur is None:
+            advd.bufcur = np.zeros(advd.adv.sizeall + (2,), order="F")
+        for x in range(2):
+            advd.bufcur[:, :, x] = dt * np.real(np.fft.ifft2((1j * self.coef_imag[x]) * buf))
+
+
+def getgeovar(adv, **kw):
+    return GeoVar(adv, **kw)

@@ -20,4 +20,5 @@ from .unsplit2d import (NoTimeAlg, ABTimeAlg_ip, ABTimeAlg_new, ABTimeAlg_init, 
                         autointerp, interpbufc, abcoef)
 from .rotation import RotationVar, getrotationvar
 from .translation import TranslationVar, gettranslationvar
+from .quasigeostrophic import GeoVar, getgeovar
 from .interpolate import interpolate, interpolate_lines, interpolate_nd, sol

@@ -203,10 +203,12 @@ class FakeLib:
 
     # -- Vlasov-Poisson pieces (numpy restatement, 1-D space only) -----------------------------
     def slb_poisson_create(self, ctx, nsp, ext, fctv, out):
-        assert nsp == 1
-        n = int(ext[0])
+        assert nsp in (1, 2)
+        shape = tuple(int(ext[d]) for d in range(nsp))
+        n = int(np.prod(shape))
         pid = self._new_id()
-        self.plans[pid] = {"n": n, "mult": np.array(_arr(fctv[0], n), copy=True)}
+        self.plans[pid] = {"n": n, "shape": shape, "mult": np.array(_arr(fctv[0], n), copy=True),
+                           "mults": [np.array(_arr(fctv[x], n), copy=True).reshape(shape, order="F") for x in range(nsp)]}
         _set(out, pid)
         return 0
 
@@ -236,6 +238,12 @@ class FakeLib:
 
     def slb_poisson_solve(self, plan, rho, E):
         pl = self.plans[_addr(plan)]
+        if len(pl["shape"]) == 2:  # E_x = real(ifft2(i m_x fft2(rho)))
+            self.calls.append("poisson_solve_2d")
+            buf = np.fft.fft2(np.array(_arr(rho, pl["n"]), copy=True).reshape(pl["shape"], order="F"))
+            for x in range(2):
+                _arr(E[x], pl["n"])[:] = np.real(np.fft.ifft2((1j * pl["mults"][x]) * buf)).reshape(-1, order="F")
+            return 0
         self._solve(pl, np.array(_arr(rho, pl["n"]), copy=True), E)
         return 0
 

@@ -289,3 +289,26 @@ def test_split_states_reject_time_algorithms():
     advd = S.AdvectionData(adv, np.zeros((16, 16)), S.gettranslationvar((1.0, 1.0)))
     with pytest.raises(NotImplementedError):
         S.advection(advd)
+
+
+@pytest.mark.parametrize("alg,ordalg", [("NoTimeAlg", 0), ("ABTimeAlg_ip", 2), ("ABTimeAlg_ip", 3)])
+def test_quasigeostrophic_matches_oracle(alg, ordalg):
+    """test/test_quasigeostrophic.jl:25-96: the SQG provider (velocity = spectral multiplier of the advected
+    field, on the library's DFT kernels) with the unsplit driver, 10 steps on 128 x 128, against the oracle"""
+    import slb200 as S
+    from test_oracle_unsplit2d import sqg_run
+
+    g = sqg_run(S, S.getgeovar, 10, getattr(S, alg), ordalg)
+    o = sqg_run(R, U.getgeovar, 10, getattr(R, alg), ordalg, nthreads=4)
+    assert abs(g.time_cur - o.time_cur) <= 1e-9
+    assert relerr(g.getdata(), o.data) <= 1e-10
+
+
+def test_quasigeostrophic_order_on_device():
+    """test/test_quasigeostrophic.jl:146-161, :189 (test_orderno, ABTimeAlg_ip 2)"""
+    import slb200 as S
+    from test_oracle_unsplit2d import sqg_run
+
+    d4, d1, d2 = (sqg_run(S, S.getgeovar, n, S.ABTimeAlg_ip, 2).getdata() for n in (40, 10, 20))
+    ret1, ret2 = np.linalg.norm(d4 - d1), np.linalg.norm(d4 - d2)
+    assert ret1 * 1.2 / ret2 > 2**2, (ret1, ret2)

@@ -78,3 +78,16 @@ def test_pool_recycles_storage(fake):
     v = S.DeviceField.view(ctx, 8, 8, 2, b.ptr)
     v.free()  # a view never returns storage it does not own
     assert not S.DeviceField._pool.get((id(ctx), 128))
+
+
+@pytest.mark.parametrize("alg,ordalg", [("NoTimeAlg", 0), ("ABTimeAlg_ip", 2), ("ABTimeAlg_ip", 3)])
+def test_quasigeostrophic_driver_sequencing(fake, alg, ordalg):
+    """the SQG provider (slb200/quasigeostrophic.py) against the oracle's, through the test double"""
+    import slb200 as S
+    from test_oracle_unsplit2d import sqg_run
+
+    g = sqg_run(S, S.getgeovar, 6, getattr(S, alg), ordalg, sz=(32, 48))
+    o = sqg_run(R, U.getgeovar, 6, getattr(R, alg), ordalg, sz=(32, 48))
+    assert relerr(g.getdata(), o.data) <= 1e-11
+    assert relerr(g.bufcur.to_host(), o.bufcur) <= 1e-9
+    assert "poisson_solve_2d" in fake.calls

@@ -296,3 +296,28 @@ def test_rotation2d_abtimealg_converges():
     # in its asymptotic regime; 80 / 160 steps show the order cleanly
     r1, r2 = run(80, 2), run(160, 2)
     assert r2 < (r1 * 1.1) / 4 and r1 < 0.1, (r1, r2)
+
+
+def sqg_run(M, getgv, nbdt, timealg, ordalg, sz=(128, 128), t_max=10000.0, **kw):
+    """test/test_quasigeostrophic.jl:25-96 (test_quasigeostrophic, nosplit): returns the final data"""
+    mx, my = M.UniformMesh(0.0, 1e6, sz[0]), M.UniformMesh(0.0, 1e6, sz[1])
+    dt = t_max / nbdt
+    adv = M.Advection((mx, my), [M.Lagrange(9), M.Lagrange(9)], dt, [([1, 2], 2, 1, False)], tab_coef=M.nosplit(dt), timealg=timealg,
+                      ordalg=ordalg, **kw)
+    pv = getgv(adv)
+    advd = M.AdvectionData(adv, np.zeros(sz, order="F"), pv)
+    pv.initdata(advd)
+    borne_t = t_max - adv.dt_base / 2
+    while advd.time_cur < borne_t:
+        while M.advection(advd):
+            pass
+    return advd
+
+
+@pytest.mark.parametrize("timealg,ordalg", [(R.NoTimeAlg, 0), (R.ABTimeAlg_ip, 2), (R.ABTimeAlg_ip, 3)])
+def test_quasigeostrophic_order(timealg, ordalg):
+    """test/test_quasigeostrophic.jl:146-161, :188-190 (test_orderno): halving dt divides the distance to the
+    4x finer run by 2^ord (Float64 here, Double64 there)"""
+    d4, d1, d2 = (np.array(sqg_run(R, U.getgeovar, n, timealg, ordalg, nthreads=4).data) for n in (40, 10, 20))
+    ret1, ret2 = np.linalg.norm(d4 - d1), np.linalg.norm(d4 - d2)
+    assert ret1 * 1.2 / ret2 > 2 ** (ordalg if ordalg else 1), (ret1, ret2)
