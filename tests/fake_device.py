@@ -201,6 +201,42 @@ class FakeLib:
         _arr(out, n)[:] = acc
         return 0
 
+    # -- the sweep itself, through the oracle's C line algorithms (dry-runs of GPU test code only) ----------
+    def slb_sweep(self, g, dim, h, alpha, alpha_len, strides, scale, on_device, flags):
+        from oracle import clib
+
+        self.calls.append("sweep")
+        gr, it = self._g(g), self.interps[_addr(h)]
+        ext, nd = gr["ext"], len(gr["ext"])
+        n = ext[dim]
+        if it["kind"] in (1, 2) and it["n"] != n:
+            return -1
+        L = clib.lib()
+        oh = L.orc_interp_create(it["kind"], it["order"], n, it["coef"].ctypes.data_as(dp), it["nc"],
+                                 it["nodes"].ctypes.data_as(dp) if it["nodes"] is not None else None)
+        tab = scale * np.array(_arr(alpha, alpha_len), copy=True)
+        data = _arr(gr["front"], gr["numel"])
+        if flags & 2:  # InsideEdge: line by line
+            a = data.reshape(ext, order="F")
+            mv = np.moveaxis(a, dim, 0)
+            other = [e for d, e in enumerate(ext) if d != dim]
+            ostr = [int(strides[d]) for d in range(nd) if d != dim]
+            for idx in np.ndindex(*other):
+                al = float(tab[sum(i * s_ for i, s_ in zip(idx, ostr))])
+                line = np.ascontiguousarray(mv[(slice(None),) + idx])
+                out = np.empty(n)
+                rc = L.orc_interpolate_inside(out.ctypes.data_as(dp), line.ctypes.data_as(dp), n, int(np.floor(al)), al - np.floor(al),
+                                              it["coef"].ctypes.data_as(dp), it["order"], it["nc"])
+                if rc != 0:
+                    return -1
+                mv[(slice(None),) + idx] = out
+            return 0
+        scratch = np.empty(gr["numel"])
+        rc = L.orc_sweep(data.ctypes.data_as(dp), scratch.ctypes.data_as(dp), nd, clib.lp(ext), dim, oh, tab.ctypes.data_as(dp),
+                         clib.lp([int(strides[d]) for d in range(nd)]), 1)
+        L.orc_interp_destroy(oh)
+        return rc
+
     # -- Vlasov-Poisson pieces (numpy restatement, 1-D space only) -----------------------------
     def slb_poisson_create(self, ctx, nsp, ext, fctv, out):
         assert nsp in (1, 2)
