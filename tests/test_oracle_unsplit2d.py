@@ -321,3 +321,38 @@ def test_quasigeostrophic_order(timealg, ordalg):
     d4, d1, d2 = (np.array(sqg_run(R, U.getgeovar, n, timealg, ordalg, nthreads=4).data) for n in (40, 10, 20))
     ret1, ret2 = np.linalg.norm(d4 - d1), np.linalg.norm(d4 - d2)
     assert ret1 * 1.2 / ret2 > 2 ** (ordalg if ordalg else 1), (ret1, ret2)
+
+
+def test_poisson_3d3v_consistency():
+    """test/test_poisson.jl:38-108 (test_poisson, 3D3V, Lagrange 3, random data): after initcoef! at the first
+    velocity state, rho equals the direct charge integral, every E component the direct spectral formula
+    (src/util_poisson.jl:84-119) and compute_ee / compute_ke their definitions"""
+    ms = [R.UniformMesh(a, b, n) for a, b, n in ((-1, 3, 8), (-10, 6, 4), (-3, 5, 16), (-3, 1, 4), (-9, 7, 8), (1, 5, 4))]
+    interp = [R.Lagrange(3) for _ in range(6)]
+    adv = R.Advection(tuple(ms), interp, 1 / 80, [([1, 2, 3, 4, 5, 6], 3, 1, False), ([4, 5, 6, 1, 2, 3], 3, 2, False)])
+    tab = np.asfortranarray(np.random.default_rng(3).random(adv.sizeall))
+    pv = R.getpoissonvar(adv)
+    advd = R.AdvectionData(adv, tab, pv)
+    assert np.array_equal(pv.v_square, R.dotprod([m.points for m in ms[3:]]) ** 2)
+    dv = ms[3].step * ms[4].step * ms[5].step
+    dsp = ms[0].step * ms[1].step * ms[2].step
+    ke_ref = dsp * dv * float(np.sum(pv.v_square * np.sum(tab, axis=(0, 1, 2))))
+    assert abs(R.compute_ke(advd) - ke_ref) <= 1e-13 * abs(ke_ref)
+    advd.state_gen = 2
+    pv.compute_charge(advd)      # what initcoef! does first at a velocity state that contains dim Nsp+1
+    pv.compute_elfield()
+    rho = dv * np.sum(tab, axis=(3, 4, 5))
+    rho = rho - rho.sum() / rho.size
+    assert np.max(np.abs(pv.rho - rho)) <= 1e-12 * np.max(np.abs(rho))
+    ks = np.meshgrid(*[R.vec_k_fft(m) for m in ms[:3]], indexing="ij")
+    k2 = ks[0] ** 2 + ks[1] ** 2 + ks[2] ** 2
+    k2[0, 0, 0] = 1.0
+    rk = np.fft.fftn(rho)
+    ee = 0.0
+    for d in range(3):
+        mult = 1j * ks[d] / k2
+        mult[0, 0, 0] = 0.0
+        E = np.real(np.fft.ifftn(mult * rk))
+        assert np.max(np.abs(pv.t_elfield[d] - E)) <= 1e-12 * max(np.max(np.abs(E)), 1e-300)
+        ee += float(np.sum(E**2))
+    assert abs(R.compute_ee(advd) - dsp * ee) <= 1e-12 * dsp * ee
