@@ -2,7 +2,8 @@
     python tools/ncu_hotspots.py gpurun_out/<tag>/prof.ncu-rep > profiles/rN_ncu_hot_<tag>.txt   (runs without a GPU)"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+extra = sys.argv[2:]  # e.g. -k regex:k_sweep_fused -c 1
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO("\n".join(l for l in txt.splitlines() if l.startswith('"')))))
 hdr = rows[1]
 ia, isrc, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples")
