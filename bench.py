@@ -149,16 +149,18 @@ def run_reference(args):
             pass
         return R.compute_ee(advd)
 
-    for _ in range(args.warmup):
-        step()
+    warm = max(args.warmup, 3)  # same step count as the GPU arm, so that ee_after_timed is comparable
+    ee = None
+    for _ in range(warm):
+        ee = step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        ee = step()
     dt = time.perf_counter() - t0
     val = cells_per_step * args.steps / dt / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ee_after_timed": ee, "steps_done": warm + args.steps, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
@@ -179,9 +181,10 @@ def workload_config(args):
     }
 
 
-def cpu_baseline_sample(args):
-    """Bounded CPU sample for the `cpu_baseline` object of our own arm: Strang steps of the oracle on
-    the full grid for about 10 s on the box's cores."""
+def cpu_baseline_sample(args, steps_done):
+    """CPU leg of our own arm: the oracle runs the SAME steps as the GPU arm (warm-up + timed, capped at 30: about
+    10-40 s on the box's cores), recording the electric energy after every step.  Returns the `cpu_baseline`
+    object (timed over those steps) and the oracle's ee history for the parity object."""
     from oracle import refmodel as R
 
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -191,19 +194,121 @@ def cpu_baseline_sample(args):
     fill_product(f, vecs)
     advd = R.AdvectionData(adv, f, R.getpoissonvar(adv))
     del f
-    R.advection(advd)  # first-touch warm-up of the scratch array (one stage)
-    advd.state_gen = 1
-    nsteps = 0
+    nsteps = min(steps_done, 30)
+    hist = []
     t0 = time.perf_counter()
-    while nsteps < 12 and (nsteps == 0 or time.perf_counter() - t0 < 10.0):  # about 10 s of CPU work
+    for _ in range(nsteps):
         while R.advection(advd):
             pass
-        R.compute_ee(advd)
-        nsteps += 1
+        hist.append(R.compute_ee(advd))
     dt = time.perf_counter() - t0
-    return {"value": 6 * n**4 * nsteps / dt / 1e9, "unit": UNIT, "cores": ncores, "kind": "port",
-            "sample": f"{nsteps} full Strang steps (6 sweeps + field solves each) of the 2D2V {n}^4 workload, {dt:.1f} s, "
-                      f"oracle C/OpenMP port on {ncores} threads"}
+    cb = {"value": 6 * n**4 * nsteps / dt / 1e9, "unit": UNIT, "cores": ncores, "kind": "port",
+          "sample": f"{nsteps} full Strang steps (6 sweeps + field solves each) of the 2D2V {n}^4 workload from the same initial "
+                    f"condition as the GPU arm, {dt:.1f} s, oracle C/OpenMP port on {ncores} threads"}
+    return cb, hist
+
+
+def gpu_ee_history(S, args, nsteps):
+    """ee after each of the first nsteps Strang steps on a fresh device-resident grid (same initial condition)"""
+    n = args.size
+    adv, vecs = vp2d2v_setup(S, n, args.order, args.interp)
+    f = np.empty((n,) * 4, order="F")
+    fill_product(f, vecs)
+    advd = S.AdvectionData(adv, f, S.getpoissonvar(adv))
+    del f
+    hist = []
+    for _ in range(nsteps):
+        while S.advection(advd):
+            pass
+        hist.append(S.compute_ee(advd))
+    advd.close()
+    return hist
+
+
+# ------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (C1-C4), each timed and parity-checked in the same run
+# ------------------------------------------------------------------------------------------
+def _cfg_c1(M, **kw):
+    """C1: Vlasov-Poisson 1D1V Landau damping 128 x 256, Lagrange 9, Strang (examples/vlasov-poisson-1d1v.jl:24-45)"""
+    nx, nv = 128, 256
+    mx, mv = M.UniformMesh(0.0, 2 * math.pi / 0.5, nx), M.UniformMesh(-6.0, 6.0, nv)
+    adv = M.Advection((mx, mv), [M.Lagrange(9)] * 2, 0.1, [([2, 1], 1, 1, True), ([1, 2], 1, 2, True)], **kw)
+    f = M.dotprod((1 + 0.001 * np.cos(0.5 * mx.points), np.exp(-mv.points**2 / 2) / math.sqrt(2 * math.pi)))
+    return M.AdvectionData(adv, f, M.getpoissonvar(adv)), 3 * nx * nv
+
+
+def _cfg_c2(M, **kw):
+    """C2: 2-D rigid rotation 1024 x 1024, periodic B-spline order 5 (BSplineLU), magic splitting
+    (examples/run_rotation.jl shape, test/test_rotation.jl:43-62)"""
+    n = 1024
+    m1, m2 = M.UniformMesh(-5.0, 5.0, n), M.UniformMesh(-5.0, 5.0, n)
+    dt = 2 * math.pi / 100
+    adv = M.Advection((m1, m2), [M.BSplineLU(5, n), M.BSplineLU(5, n)], dt, [([1, 2], 1, 1, True), ([2, 1], 1, 2, True)],
+                      tab_coef=M.magicsplit(dt), **kw)
+    x, y = m1.points[:, None], m2.points[None, :]
+    return M.AdvectionData(adv, np.asfortranarray(np.exp(-13 * (x**2 + (y + 1.2) ** 2))), M.getrotationvar(adv)), 3 * n * n
+
+
+def _cfg_vp4(n, order, kind):
+    def build(M, **kw):
+        adv, vecs = vp2d2v_setup(M, n, order, kind, **kw)
+        f = np.empty((n,) * 4, order="F")
+        fill_product(f, vecs)
+        return M.AdvectionData(adv, f, M.getpoissonvar(adv)), 6 * n**4
+    return build
+
+
+def run_configs(S, ctx, args, peak, only=None):
+    """C1-C4 on this GPU: ms/step (CUDA events), Gcell/s per sweep, the HBM fraction of the per-sweep algorithmic
+    traffic (16 B per cell-update; C1/C2/C3 are cache-resident or launch-bound, flagged), and a
+    parity figure: the grid after `psteps` Strang steps against the oracle on the same inputs (max-abs relative)."""
+    from oracle import refmodel as R
+    from slb200 import _lib
+
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    e0, e1 = ctx.event(), ctx.event()
+    cases = [
+        ("C1_vp1d1v_128x256_L9_strang", _cfg_c1, 200, 10, "256 KB grid: launch-bound, cache-resident", True),
+        ("C2_rotation_1024x1024_bsplinelu5_magic", _cfg_c2, 50, 3, "8 MB grid: L2-resident", False),
+        ("C3_vp2d2v_64^4_L7_strang", _cfg_vp4(64, 7, "lagrange"), 30, 2, "134 MB grid: just above L2", True),
+        ("C4_vp2d2v_128^4_bsplinefft11_strang", _cfg_vp4(128, 11, "bspline_fft"), 5, 1, "2.15 GB grid: HBM-bound", True),
+    ]
+    out = {}
+    for name, build, nsteps, psteps, note, has_ee in cases:
+        if (args.size < 128 and name.startswith("C4")) or (only and not name.startswith(tuple(only))):
+            continue  # reduced-size smoke runs of bench.py skip the big case
+        try:
+            g, cells = build(S)
+            o, _ = build(R, nthreads=ncores)
+            for _ in range(psteps):
+                while S.advection(g):
+                    pass
+                while R.advection(o):
+                    pass
+            a, b = g.getdata(), o.data
+            par = {"steps": psteps, "f_rel_maxabs": float(np.max(np.abs(a - b)) / np.max(np.abs(b)))}
+            if has_ee:
+                ee_g, ee_o = S.compute_ee(g), R.compute_ee(o)
+                par["ee_rel"] = abs(ee_g - ee_o) / abs(ee_o)
+            del a, b, o
+            for _ in range(3):
+                while S.advection(g):
+                    pass
+            ctx.sync()
+            l0 = ctx.launch_count()
+            ctx.record(e0)
+            for _ in range(nsteps):
+                while S.advection(g):
+                    pass
+            ctx.record(e1)
+            ms = _lib.Context.elapsed_ms(e0, e1) / nsteps
+            nl = (ctx.launch_count() - l0) / nsteps
+            g.close()
+            out[name] = {"ms_per_step": ms, "Gcell_s": cells / ms / 1e6, "launches_per_step": nl,
+                         "hbm_frac_per_sweep_bytes": cells * BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peak, "parity": par, "note": note}
+        except Exception as exc:  # a side measurement must not take the headline down
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -261,6 +366,10 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0
     advd_nfused = advd.n_fused - nfused0
     clocks = sampler.stop()
+    # electric energy right after the timed steps (nothing has touched the grid since): the cross-check
+    # value every arm prints -- N = 1/2/4/8 and the oracle after the same number of steps must agree
+    steps_done = max(args.warmup, 3) + args.steps
+    ee_after_timed = S.compute_ee(advd)
     value = cells_per_step * args.steps / (ms_total * 1e-3) / 1e9
     # per-stage durations (include the field solve for the v1 stages)
     stage_ms = [_lib.Context.elapsed_ms(evs[j], evs[j + 1]) for j in range(i)]
@@ -297,23 +406,35 @@ def run_ours(args):
     pairs = (("k_sweep_fused/v1v2", vE(2), vE(3)),
              ("k_sweep_fused/x1x2", stage(0, tdev_v, n, [0, 0, 1, 0], sx), stage(1, tdev_v, n, [0, 0, 0, 1], sx)))
     for name, sa, sb in pairs:
+        if not S.sweep_pair(advd, sa, sb):  # not pair-fused for this interpolation kind (B-spline pre-solves): nothing launched
+            continue
         ms = timed(lambda: S.sweep_pair(advd, sa, sb))
         kern[name] = {"ms": ms, "GBps": n**4 * BYTES_PER_CELL / (ms * 1e-3) / 1e9, "Gcell_s": 2 * n**4 / (ms * 1e-3) / 1e9,
                       "cell_updates_per_cell": 2}
-    for name, sg in (("k_sweep_strided/v2", vE(3)), ("k_sweep_strided/v1", vE(2)),
-                     ("k_sweep_strided/x2", stage(1, tdev_v, n, [0, 0, 0, 1], sx)), ("k_sweep_contig/x1", stage(0, tdev_v, n, [0, 0, 1, 0], sx))):
+    singles = (("sweep/v2", vE(3)), ("sweep/v1", vE(2)), ("sweep/x2", stage(1, tdev_v, n, [0, 0, 0, 1], sx)),
+               ("sweep/x1", stage(0, tdev_v, n, [0, 0, 1, 0], sx)))
+    for name, sg in singles:
         ms = timed(lambda: S.sweep(advd, *sg[:6]))
         kern[name] = {"ms": ms, "GBps": n**4 * BYTES_PER_CELL / (ms * 1e-3) / 1e9, "Gcell_s": n**4 / (ms * 1e-3) / 1e9,
                       "cell_updates_per_cell": 1}
     ctx.free(tdev_E)
     ctx.free(tdev_v)
-    dom = "k_sweep_fused/v1v2"
+    fused_step = advd_nfused > 0
+    if fused_step and "k_sweep_fused/v1v2" in kern:
+        # the step runs as pair-fused passes: the v1v2 pass is 2 of its 3 big launches
+        dom = "k_sweep_fused/v1v2"
+        dom_note = ("one launch reads f once and writes it once (16 B per cell) and performs TWO sweeps (2 cell-updates per cell); "
+                    "in SURVEY.md 8(d)'s per-sweep unit (16 B per cell-update) that is twice the single-sweep roofline rate")
+        traffic, traffic_src = NCU_TRAFFIC.get(n), "profiles/r1_ncu_full_fused_L7_128_s4f.txt (ncu --set full, per launch)"
+    else:
+        # no pair fusion for this kind: the step is six single sweeps; the dominant kernel is the slowest of them
+        dom = max((k for k in kern if k.startswith("sweep/")), key=lambda k: kern[k]["ms"])
+        dom_note = "single sweep (pre-solve + stencil in one pass for the B-spline kinds): reads f once, writes it once, 16 B per cell-update"
+        traffic, traffic_src = None, None
     ach = kern[dom]["GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": ach / peak, "traffic": NCU_TRAFFIC.get(n), "traffic_source": "profiles/r1_ncu_full_fused_L7_128_s4f.txt (ncu --set full, per launch)",
-                "bytes_per_launch": n**4 * BYTES_PER_CELL,
-                "note": "one launch reads f once and writes it once (16 B per cell) and performs TWO sweeps (2 cell-updates per cell); "
-                        "in SURVEY.md 8(d)'s per-sweep unit (16 B per cell-update) that is twice the single-sweep roofline rate",
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "bytes_per_launch": n**4 * BYTES_PER_CELL, "note": dom_note,
                 "ms_per_launch": kern[dom]["ms"], "all_kernels": kern}
 
     # ---- e2e: host buffers in, host buffers out, every step --------------------------------------
@@ -399,12 +520,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
-                "steps": e2e_steps, "note": "every step: upload f from pinned host memory, full Strang step, read back f and ee; two independent "
-                                            "grids in flight on two streams, half a period apart, so that one grid's upload overlaps the other's "
-                                            "read-back (wall clock); PCIe-bound by construction: 2 x 2.15 GB per step"},
-        "e2e_serial": {"value": cells_per_step * ser_steps / wall_ser / 1e9, "unit": UNIT, "steps": ser_steps,
-                       "note": "one grid: upload, step, read back, nothing overlapped"},
+        "e2e": {"value": cells_per_step * ser_steps / wall_ser / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
+                "steps": ser_steps, "note": "ONE grid through the public API, nothing overlapped: every step uploads f from pinned host memory "
+                                            "(AdvectionData.upload), runs the full Strang step, reads back ee and f (getdata); wall clock; "
+                                            "PCIe-bound by construction: 2 x 2.15 GB per 2.7 ms step"},
+        "e2e_two_grids_pipelined": {"value": e2e_val, "unit": UNIT, "steps": e2e_steps,
+                                    "note": "two INDEPENDENT grids in flight on two streams, half a period apart, so that one grid's upload "
+                                            "overlaps the other's read-back (throughput of a batch of problems, not of one problem)"},
         "e2e_resident": {"value": cells_per_step * e2e_steps / wall_res / 1e9, "unit": UNIT,
                          "note": "f resident in HBM across steps (AdvectionData semantics), ee read back per step; wall clock"},
         "gpu_launches": int(launches),
@@ -414,13 +536,28 @@ def run_ours(args):
         "advection_call_ms": {f"dim{d}": float(np.mean(v)) for d, v in sorted(per_dim.items())},
         "advection_call_note": "device time between successive advection() calls: the first stage of a fused pair is only recorded "
                                "(dim2 = charge density + Poisson solve), the second runs both sweeps",
-        "last_ee": ee,
+        "ee_after_timed": ee_after_timed, "steps_done": steps_done,
     }
     if not args.no_cpu:
         try:
-            line["cpu_baseline"] = cpu_baseline_sample(args)
+            cb, hist_o = cpu_baseline_sample(args, steps_done)
+            line["cpu_baseline"] = cb
+            hist_g = gpu_ee_history(S, args, len(hist_o))
+            ho, hg = np.array(hist_o), np.array(hist_g)
+            line["parity"] = {
+                "what": "electric-energy history of the first %d Strang steps from the same initial condition: this GPU path vs the oracle "
+                        "(CPU restatement of the reference; itself pinned by the reference's KATs only -- parity unpinned at the ulp "
+                        "level, no Julia runtime here)" % len(hist_o),
+                "steps": len(hist_o), "ee_hist_rel_vs_oracle": float(np.max(np.abs(hg - ho)) / np.max(np.abs(ho))),
+                "ee_oracle_last": hist_o[-1], "ee_gpu_last": hist_g[-1],
+                "ee_after_timed_equals_fresh_run": (bool(hist_g[-1] == ee_after_timed) if len(hist_g) == steps_done else None),
+                "tolerance": 1e-10,
+            }
         except Exception as exc:  # the checker must never take the product down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    if not args.no_configs:
+        advd.close()
+        line["configs"] = run_configs(S, ctx, args, peak)
     print(json.dumps(line))
     return 0
 
@@ -435,6 +572,7 @@ def main():
     ap.add_argument("--order", type=int, default=7)
     ap.add_argument("--interp", default="lagrange", choices=["lagrange", "bspline_lu", "bspline_fft", "hermite"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1-C4 side measurements")
     ap.add_argument("--no-e2e", action="store_true", help="sharded runs: skip the host-buffer end-to-end leg (large grids)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU re-shard: peer stores fused into the sweep (p2p) or NCCL all-to-all")

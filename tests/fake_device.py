@@ -130,6 +130,7 @@ class FakeLib:
         return 0
 
     def slb_grid_set_linesum(self, g, p):
+        self._g(g)["linesum"] = _addr(p)
         return 0
 
     # -- interpolation objects -------------------------------------------------------------
@@ -235,6 +236,9 @@ class FakeLib:
         rc = L.orc_sweep(data.ctypes.data_as(dp), scratch.ctypes.data_as(dp), nd, clib.lp(ext), dim, oh, tab.ctypes.data_as(dp),
                          clib.lp([int(strides[d]) for d in range(nd)]), 1)
         L.orc_interp_destroy(oh)
+        if rc == 0 and gr.get("linesum"):  # per-line sums of the outputs (line index: the other dims, Fortran order)
+            ls = data.reshape(ext, order="F").sum(axis=dim).reshape(-1, order="F")
+            _arr(gr["linesum"], ls.size)[:] = ls
         return rc
 
     # -- Vlasov-Poisson pieces (numpy restatement, 1-D space only) -----------------------------
@@ -262,7 +266,46 @@ class FakeLib:
         r = dv * _arr(f, n * nv).reshape((n, nv), order="F").sum(axis=1)
         r = r - r.sum() / n
         _arr(rho, n)[:] = r
+        if len(pl["shape"]) == 2:
+            return self.slb_poisson_solve(plan, rho, E)
         self._solve(pl, r, E)
+        return 0
+
+    # -- pieces bench.py touches (dry-runs of its host logic on the CPU) ---------------------------
+    def slb_sweep_pair(self, *a):
+        return -4  # SLB_E_UNSUPPORTED: callers issue two sweeps
+
+    def slb_timer_start(self, ctx):
+        import time
+        self._t0 = time.perf_counter()
+        return 0
+
+    def slb_timer_stop(self, ctx, ms):
+        import time
+        _set(ms, 1e3 * (time.perf_counter() - self._t0))
+        return 0
+
+    def slb_event_create(self, ctx, out):
+        eid = self._new_id()
+        self.mem[("ev", eid)] = 0.0
+        _set(out, eid)
+        return 0
+
+    def slb_event_record(self, ctx, ev):
+        import time
+        self.mem[("ev", _addr(ev))] = time.perf_counter()
+        return 0
+
+    def slb_event_elapsed_ms(self, e0, e1, ms):
+        _set(ms, max(1e-6, 1e3 * (self.mem[("ev", _addr(e1))] - self.mem[("ev", _addr(e0))])))
+        return 0
+
+    def slb_host_alloc(self, nbytes, out):
+        _set(out, self._alloc(nbytes))
+        return 0
+
+    def slb_host_free(self, p):
+        self.mem.pop(_addr(p), None)
         return 0
 
     def slb_charge_density(self, g, nsp, dv, rho):

@@ -106,6 +106,54 @@ def test_vlasov_poisson_2d2v_steps(sz, kind, order, nsteps):
     assert np.allclose(eg, eo, rtol=1e-11, atol=0)
 
 
+@pytest.mark.parametrize("n,kind,order", [(64, "lagrange", 7), (128, "bspline_fft", 11)])
+def test_vlasov_poisson_2d2v_full_size_step(n, kind, order):
+    """C3 (2D2V 64^4, Lagrange 7) and C4 (2D2V 128^4, BSplineFFT 11) at their REAL sizes: one Strang step compared
+    with the oracle after every stage (<= 1e-12 relative max-abs per sweep, accumulated), then rho, E and ee.
+    The oracle runs on all host cores (OpenMP over lines = SimpleThreadsOpt); a 128^4 B-spline stage takes seconds."""
+    import os
+
+    import slb200 as S
+    from oracle import refmodel as R
+
+    ncores = len(os.sched_getaffinity(0))
+    sz = (n,) * 4
+
+    def build(M, **kw):
+        m1 = M.UniformMesh(0.0, 4 * math.pi, n)
+        m2 = M.UniformMesh(0.0, 4 * math.pi, n)
+        v1 = M.UniformMesh(-6.0, 6.0, n)
+        v2 = M.UniformMesh(-6.0, 6.0, n)
+        mk = {"lagrange": lambda: M.Lagrange(order), "bspline_fft": lambda: M.BSplineFFT(order, n)}[kind]
+        tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+        adv = M.Advection((m1, m2, v1, v2), [mk() for _ in sz], 0.1, tabst, **kw)
+        fsp = lambda x: 0.5 * np.cos(x / 2) + 1
+        fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+        f = M.dotprod((fsp(m1.points), fsp(m2.points), fv(v1.points), fv(v2.points)))
+        pv = M.getpoissonvar(adv)
+        return M.AdvectionData(adv, f, pv), pv
+
+    g, pv_g = build(S)
+    o, pv_o = build(R, nthreads=ncores)
+    buf = np.empty(sz, dtype=np.float64, order="F")
+    more, stage = True, 0
+    while more:
+        more = S.advection(g)
+        assert more == R.advection(o)
+        stage += 1
+        g.getdata(out=buf)
+        np.subtract(buf, o.data, out=buf)
+        err = float(np.max(np.abs(buf)) / np.max(np.abs(o.data)))
+        assert err <= 1e-12 * stage, (stage, err)
+    assert stage == 6
+    assert relerr(pv_g.rho, pv_o.rho) <= 1e-11
+    for eg, eo in zip(pv_g.t_elfield, pv_o.t_elfield):
+        assert relerr(eg, eo) <= 1e-11
+    ee_g, ee_o = S.compute_ee(g), R.compute_ee(o)
+    assert abs(ee_g - ee_o) <= 1e-11 * abs(ee_o)
+    g.close()
+
+
 def test_field_solve_pieces_random():
     """compute_charge! / compute_elfield! on random data (test/test_poisson.jl:38-108 shape)."""
     import slb200 as S
