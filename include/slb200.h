@@ -167,6 +167,64 @@ int slb_sweep_pair_ex(slb_grid* g, int dimA, const slb_interp* itA, const double
                       int alpha_on_device, int flags, int in_nblocks, int out_nblocks, double* const* out_block_bases,
                       int first_block);
 
+/* ---- pair passes on a HALO-SHARDED grid (replaces the MPI mode's replicate + broadcast of
+ * every sweep, src/mpiinterface.jl:17-38, src/advection.jl:116-123) -----------------------------------------
+ * A 2D2V grid f[x1,x2,v1,v2] is split over P ranks in slabs of c = n4 / P points along ONE dim (v2) for the whole
+ * step; every rank stores [low halo | slab | high halo] = c + 2 halo planes along that dim.  No transposes:
+ *   - a pass that does not sweep the sharded dim (x1 x2) runs on the slab view (SLB_HALO_PASSIVE);
+ *   - a pass whose SECOND sweep runs along the sharded dim (v1 v2) marches once over the c + 2 halo rows and
+ *     emits the slab's c rows (SLB_HALO_MARCH): shifts need floor(alpha) + order/2 + 1 <= halo and
+ *     order/2 - floor(alpha) <= halo, else bit 0 of the error word is set (slb_halo_error) -- for
+ *     Vlasov-Poisson velocity sweeps |alpha| = dt/dv |E| is about one cell.
+ * Either pass can also store the outputs that lie within `halo` of a slab boundary into the neighbours' halo
+ * planes (push_lo / push_hi: the address, in the rank below / above, of the array that corresponds to this
+ * grid's back buffer; NULL = no push): the halo exchange rides inside the pass as NVLink peer stores, there is no
+ * separate collective.  Callers order the ranks with slb_comm_* before the halos are read.
+ * Results are bit-identical to slb_sweep_pair on the unsharded grid.  Lagrange / Hermite kinds (B-spline
+ * pre-solves couple the whole line: they use the transposing driver, slb_sweep_pair_ex / slb_sweep_peer). */
+#define SLB_HALO_MARCH 1
+#define SLB_HALO_PASSIVE 2
+typedef struct slb_halo {
+    int mode;        /* SLB_HALO_MARCH: the grid's extent along dimB is c + 2 halo | SLB_HALO_PASSIVE: the grid is the slab */
+    int halo;        /* halo planes on either side */
+    int shard_dim;   /* SLB_HALO_PASSIVE: the sharded grid dim (not dimA, not dimB) */
+    double* push_lo; /* neighbour arrays (device pointers, possibly peer memory), or NULL */
+    double* push_hi;
+    int* err_flag;   /* device word for the shift-range check, or NULL: the context's (slb_halo_error) */
+} slb_halo;
+int slb_sweep_pair_halo(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA_tab, int64_t alphaA_len,
+                        const int64_t* alphaA_strides, double alphaA_scale, int dimB, const slb_interp* itB,
+                        const double* alphaB_tab, int64_t alphaB_len, const int64_t* alphaB_strides, double alphaB_scale,
+                        int alpha_on_device, int flags, const slb_halo* halo);
+/* reads and clears the context's error word (synchronises): bit 0 = a shift exceeded the halo */
+int slb_halo_error(slb_ctx* ctx, int* flags_out);
+
+/* ---- rank-to-rank plumbing without MPI / NCCL in the data path ------------------------------
+ * One process per GPU.  Every rank owns a small device "mailbox" (flags + nslot_doubles * nranks doubles) that
+ * its peers map (CUDA IPC across processes, plain peer access inside one process).  The host language only
+ * moves the opaque handles once at start-up (MPI.Allgather in Julia, any all-gather elsewhere); afterwards
+ * every exchange is a kernel on the context's stream: peer stores + a flag, no host synchronisation.
+ * Replaces MPI.Bcast / mpibroadcast (src/mpiinterface.jl:17-38) and the MPIOpt fields of Advection
+ * (src/advection.jl:116-123). */
+#define SLB_COMM_HANDLE_BYTES 128
+typedef struct slb_comm slb_comm;
+int slb_comm_create(slb_ctx* ctx, int rank, int nranks, int64_t nslot_doubles, slb_comm** out);
+void slb_comm_destroy(slb_comm* cm);
+int slb_comm_export(slb_comm* cm, void* handle128);                 /* this rank's mailbox handle */
+int slb_comm_connect(slb_comm* cm, const void* all_handles);        /* nranks * 128 bytes, rank order */
+/* any slb_malloc'ed buffer: export / map / unmap (same process: the pointer itself, peer access enabled) */
+int slb_comm_export_buffer(slb_comm* cm, void* dev, void* handle128);
+int slb_comm_open_buffer(slb_comm* cm, const void* handle128, void** dev_out);
+int slb_comm_close_buffer(slb_comm* cm, void* dev);
+/* stream-ordered barrier over all ranks (one small kernel: flag stores to every peer, spin on the own flags) */
+int slb_comm_barrier(slb_comm* cm);
+/* all-gather of n <= nslot_doubles doubles per rank: afterwards *slots_out (device pointer into this rank's
+ * mailbox) holds [nranks][n] contiguous, rank order, identical on every rank.  Doubles as a barrier: it returns
+ * (in stream order) only when every rank's contribution has arrived, i.e. every rank has reached this call.
+ * Charge-density slabs (transposing driver: the gathered array IS rho) and per-rank partial charge densities
+ * (halo driver: slb_poisson_solve_partial sums them in rank order) travel this way. */
+int slb_comm_allgather(slb_comm* cm, const double* local_dev, int64_t n, const double** slots_out);
+
 /* ---- sweeps fused with the multi-GPU re-shard -------------------------------- */
 /* A 2D2V grid sharded over P ranks alternates between two slab layouts; the all-to-all between
  * them (replacing mpibroadcast, src/mpiinterface.jl:17-38) moves contiguous blocks only when the
@@ -236,6 +294,12 @@ int slb_vp_field_solve(slb_poisson* p, const double* f_dev, int64_t nv_total, do
 /* same, starting from a charge density that is already reduced (e.g. all-gathered slabs of the
  * sharded driver); subtract_mean != 0 removes its mean first.  rho_dev is updated in place. */
 int slb_poisson_solve_raw(slb_poisson* p, double* rho_dev, int subtract_mean, double* const* E_dev);
+
+/* same as slb_poisson_solve_raw, from `nparts` partial charge densities stored [nparts][prod(extents)]
+ * (e.g. the slots of slb_comm_allgather): rho = scale * (part_0 + part_1 + ...) summed in that order, mean
+ * removed when subtract_mean != 0, then compute_elfield! -- all in the one cooperative kernel. */
+int slb_poisson_solve_partial(slb_poisson* p, const double* partial_dev, int nparts, double scale, int subtract_mean,
+                              double* rho_dev, double* const* E_dev);
 
 /* sum(x .^ 2) for compute_ee (src/util_poisson.jl:156-162); deterministic; synchronises */
 int slb_reduce_sumsq(slb_ctx* ctx, const double* dev, int64_t n, double* host_out);

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/slb200.h"
+#include "slb_internal.h"
 #include "slb_sweep.cuh"
 #include "slb_pair.cuh"
 #include "slb_bspline.cuh"
@@ -26,7 +27,7 @@
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...)
+int slb_fail(int code, const char* fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -36,39 +37,11 @@ static int fail(int code, const char* fmt, ...)
     g_err = buf;
     return code;
 }
-
-#define CUDA_TRY(expr)                                                                          \
-    do {                                                                                        \
-        cudaError_t e_ = (expr);                                                                \
-        if (e_ != cudaSuccess)                                                                  \
-            return fail(e_ == cudaErrorMemoryAllocation ? SLB_E_ALLOC : SLB_E_CUDA, "%s: %s",   \
-                        #expr, cudaGetErrorString(e_));                                         \
-    } while (0)
-
-#define LAUNCH_CHECK(ctx)                                                            \
-    do {                                                                             \
-        (ctx)->launches++;                                                           \
-        cudaError_t e_ = cudaGetLastError();                                         \
-        if (e_ != cudaSuccess) return fail(SLB_E_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
-    } while (0)
+#define fail slb_fail
 
 // ------------------------------------------------------------------------------------------
 // objects
 // ------------------------------------------------------------------------------------------
-struct slb_ctx {
-    int device;
-    cudaStream_t stream;
-    bool own_stream;
-    int64_t launches;
-    cudaEvent_t ev0, ev1;
-    double* red_partial;  // 1024 doubles
-    double* red_out;      // 8 doubles
-    double* host_out;     // pinned, 8 doubles
-    void* scratch;        // growable device scratch (alpha tables, partial sums)
-    size_t scratch_bytes;
-    int sm_count;
-};
-
 struct slb_grid {
     slb_ctx* ctx;
     int nd;
@@ -174,6 +147,8 @@ extern "C" int slb_ctx_create(int device_id, void* stream, slb_ctx** out)
     CUDA_TRY(cudaMalloc(&c->red_partial, 1024 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->red_out, 8 * sizeof(double)));
     CUDA_TRY(cudaMallocHost(&c->host_out, 8 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->err_word, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->err_word, 0, sizeof(int)));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device_id));
     *out = c;
     return SLB_OK;
@@ -189,6 +164,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* c)
     cudaFree(c->red_partial);
     cudaFree(c->red_out);
     cudaFreeHost(c->host_out);
+    cudaFree(c->err_word);
     if (c->scratch) cudaFree(c->scratch);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -918,7 +894,7 @@ static int check_alpha_table(const slb_grid* g, int dim, const double* tab, int6
 static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
                            const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
                            int64_t alenB, const int64_t* astrB, double scaleB, int on_device, int flags, int in_nblocks,
-                           int out_nblocks, double* const* out_bases, int first_block)
+                           int out_nblocks, double* const* out_bases, int first_block, const slb_halo* halo = nullptr)
 {
     if (!g || !itA || !itB) return fail(SLB_E_ARG, "slb_sweep_pair: NULL argument");
     slb_ctx* c = g->ctx;
@@ -931,6 +907,29 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     if (flags & SLB_SWEEP_INSIDE_EDGE) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: InsideEdge sweeps are not pair-fused");
     if (nd > 4) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: grids with more than 4 dims are not pair-fused");
     if (dimB == 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: the second sweep must not run along dim 0");
+    int mode = SLB_FUSED_PLAIN;
+    if (halo) {
+        if (in_nblocks > 1 || out_nblocks > 1 || out_bases || first_block) return fail(SLB_E_ARG, "slb_sweep_pair_halo: does not combine with block-major re-shards");
+        if (flags & SLB_SWEEP_EXACT) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair_halo: SLB_SWEEP_EXACT is not built for the halo-sharded passes");
+        if (halo->halo < 1) return fail(SLB_E_ARG, "slb_sweep_pair_halo: halo=%d must be positive", halo->halo);
+        if (halo->mode == SLB_HALO_MARCH) {
+            mode = SLB_FUSED_WIN;
+            if (dimA == 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair_halo: SLB_HALO_MARCH needs a first sweep along a dim > 0");
+            if (g->ext[dimB] - 2 * (int64_t)halo->halo < halo->halo)
+                return fail(SLB_E_ARG, "slb_sweep_pair_halo: a slab of %lld rows is shorter than the halo %d (halos reach the next neighbour only)",
+                            (long long)(g->ext[dimB] - 2 * (int64_t)halo->halo), halo->halo);
+            if (halo->halo < (itB->order + 1) / 2) return fail(SLB_E_ARG, "slb_sweep_pair_halo: halo=%d is narrower than half the stencil (order %d)", halo->halo, itB->order);
+        } else if (halo->mode == SLB_HALO_PASSIVE) {
+            mode = SLB_FUSED_PSH;
+            if (dimA != 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair_halo: SLB_HALO_PASSIVE is built for passes whose first sweep runs along dim 0");
+            if (halo->shard_dim < 0 || halo->shard_dim >= nd || halo->shard_dim == dimA || halo->shard_dim == dimB)
+                return fail(SLB_E_ARG, "slb_sweep_pair_halo: shard_dim must be a dim other than the two swept ones");
+            if (g->ext[halo->shard_dim] < 2 * (int64_t)halo->halo)
+                return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair_halo: a slab of %lld planes is shorter than two halos (%d each)",
+                            (long long)g->ext[halo->shard_dim], halo->halo);
+        } else
+            return fail(SLB_E_ARG, "slb_sweep_pair_halo: unknown mode %d", halo->mode);
+    }
     auto plain = [](const slb_interp* it) { return it->fast && it->kind != SLB_BSPLINE_LU && it->kind != SLB_BSPLINE_FFT; };
     if (!plain(itA) || !plain(itB) || itA->order != itB->order)
         return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: both stages need the same order (<= %d) and an identity pre-solve", SLB_P1MAX - 1);
@@ -979,10 +978,20 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
         if (!fa.oblk[q]) return fail(SLB_E_ARG, "slb_sweep_pair: out_block_bases[%d] is NULL", q);
     }
     fa.elo = fa.ehi = 1;
-    int npass = 0;
+    int npass = 0, pd[2] = {-1, -1};
     for (int q = 0; q < nd; ++q) {
         if (q == dimA || q == dimB) continue;
-        if (npass == 0) {
+        pd[npass++] = q;
+    }
+    // halo pushes along a passive dim: make it the FAST passive index, so that consecutive thread blocks belong to
+    // different slab planes and the boundary layers' NVLink stores are spread over the whole pass
+    if (mode == SLB_FUSED_PSH && npass == 2 && pd[1] == halo->shard_dim) {
+        pd[1] = pd[0];
+        pd[0] = halo->shard_dim;
+    }
+    for (int x = 0; x < npass; ++x) {
+        const int q = pd[x];
+        if (x == 0) {
             fa.elo = (unsigned)g->ext[q];
             fa.islo = is[q];
             fa.oslo = os[q];
@@ -997,7 +1006,6 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
             fa.aBhi = astrB[q];
             fa.lshi = lsstr[q];
         }
-        ++npass;
     }
     if (astrB[dimA] != 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: the second sweep's shift must not depend on the first sweep's dim");
     fa.lsc = lsstr[dimA];
@@ -1084,13 +1092,31 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     fa.ncA = itA->nc;
     fa.ncB = itB->nc;
     fa.linesum = g->linesum;
+    if (halo) {
+        if ((halo->push_lo == nullptr) != (halo->push_hi == nullptr)) return fail(SLB_E_ARG, "slb_sweep_pair_halo: push_lo and push_hi must both be set or both be NULL");
+        fa.win_h = halo->halo;
+        fa.err = halo->err_flag ? halo->err_flag : c->err_word;
+        if (mode == SLB_FUSED_WIN) {
+            fa.win_c = (int)nmarch - 2 * halo->halo;
+            if (halo->push_lo) fa.pushL = halo->push_lo + (int64_t)fa.win_c * os[dimB];
+            if (halo->push_hi) fa.pushR = halo->push_hi - (int64_t)fa.win_c * os[dimB];
+        } else {
+            const int sd = halo->shard_dim;
+            fa.win_c = (int)g->ext[sd];
+            fa.push_on_lo = (pd[0] == sd);
+            if (halo->push_lo) fa.pushL = halo->push_lo + (int64_t)fa.win_c * os[sd];
+            if (halo->push_hi) fa.pushR = halo->push_hi - (int64_t)fa.win_c * os[sd];
+        }
+    }
     const int64_t nblk = (int64_t)fa.ntile_c * ((np + gg - 1) / gg);
     if (nblk >= 0x7fffffffLL) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: too many blocks");
     const size_t smem = slb_fused_smem_bytes(fa.nrows_max, gg);
     if (smem > 200 * 1024) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit shared memory");
     const bool exact = (flags & SLB_SWEEP_EXACT) != 0;
-    int lrc = slb_fused_launch(fa, itA->tab, itB->tab, P1, exact, cc, (unsigned)nblk, (unsigned)(gg * ta / 2), smem, c->stream);
-    if (lrc < 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: no fused kernel for order %d, tile width %d", P1 - 1, gg);
+    if ((mode == SLB_FUSED_WIN && cc) || (mode == SLB_FUSED_PSH && !cc))
+        return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair_halo: this dim combination has no halo-sharded kernel");
+    int lrc = slb_fused_launch(fa, itA->tab, itB->tab, P1, exact, cc, mode, (unsigned)nblk, (unsigned)(gg * ta / 2), smem, c->stream);
+    if (lrc < 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: no fused kernel for order %d, tile width %d, mode %d", P1 - 1, gg, mode);
     if (lrc != 0) return fail(SLB_E_CUDA, "slb_sweep_pair: launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
     c->launches++;
     if (out_bases) return SLB_OK;  // the result left this grid (slb_sweep_peer's convention): roles unchanged
@@ -1112,6 +1138,28 @@ extern "C" int slb_sweep_pair_ex(slb_grid* g, int dimA, const slb_interp* itA, c
 {
     return sweep_pair_impl(g, dimA, itA, alphaA, alenA, astrA, scaleA, dimB, itB, alphaB, alenB, astrB, scaleB, on_device, flags,
                            in_nblocks, out_nblocks, out_block_bases, first_block);
+}
+
+extern "C" int slb_sweep_pair_halo(slb_grid* g, int dimA, const slb_interp* itA, const double* alphaA, int64_t alenA,
+                                   const int64_t* astrA, double scaleA, int dimB, const slb_interp* itB, const double* alphaB,
+                                   int64_t alenB, const int64_t* astrB, double scaleB, int alpha_on_device, int flags,
+                                   const slb_halo* halo)
+{
+    if (!halo) return fail(SLB_E_ARG, "slb_sweep_pair_halo: halo is NULL");
+    return sweep_pair_impl(g, dimA, itA, alphaA, alenA, astrA, scaleA, dimB, itB, alphaB, alenB, astrB, scaleB, alpha_on_device, flags,
+                           1, 1, nullptr, 0, halo);
+}
+
+extern "C" int slb_halo_error(slb_ctx* c, int* flags_out)
+{
+    if (!c || !flags_out) return fail(SLB_E_ARG, "slb_halo_error: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int* h = reinterpret_cast<int*>(c->host_out + 4);
+    CUDA_TRY(cudaMemcpyAsync(h, c->err_word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->err_word, 0, sizeof(int), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *flags_out = *h;
+    return SLB_OK;
 }
 
 extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)
@@ -1434,6 +1482,26 @@ extern "C" int slb_poisson_solve_raw(slb_poisson* p, double* rho_dev, int subtra
     if (rc != SLB_E_UNSUPPORTED) return rc;
     if (subtract_mean) {
         rc = slb_subtract_mean(p->ctx, rho_dev, p->ntot);
+        if (rc) return rc;
+    }
+    return slb_poisson_solve(p, rho_dev, E_dev);
+}
+
+extern "C" int slb_poisson_solve_partial(slb_poisson* p, const double* partial_dev, int nparts, double scale, int subtract_mean,
+                                         double* rho_dev, double* const* E_dev)
+{
+    if (!p || !partial_dev || !rho_dev || !E_dev || nparts < 1) return fail(SLB_E_ARG, "slb_poisson_solve_partial: bad argument");
+    for (int x = 0; x < p->nsp; ++x)
+        if (!E_dev[x]) return fail(SLB_E_ARG, "slb_poisson_solve_partial: E_dev[%d] is NULL", x);
+    slb_ctx* c = p->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = field_from_partial(p, partial_dev, nparts, scale, subtract_mean, rho_dev, E_dev);
+    if (rc != SLB_E_UNSUPPORTED) return rc;
+    // no cooperative launch: sum the parts with the charge kernel's second stage, then the separate DFT passes
+    k_charge_final<<<(unsigned)((p->ntot + 255) / 256), 256, 0, c->stream>>>(partial_dev, p->ntot, nparts, scale, rho_dev);
+    LAUNCH_CHECK(c);
+    if (subtract_mean) {
+        rc = slb_subtract_mean(c, rho_dev, p->ntot);
         if (rc) return rc;
     }
     return slb_poisson_solve(p, rho_dev, E_dev);

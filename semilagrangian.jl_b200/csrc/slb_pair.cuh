@@ -75,10 +75,29 @@ struct FusedArgs {
     int ncA, ncB;                // polynomial coefficients per weight
     double* linesum;             // optional: per (passive, cross) sum over the march dim of the outputs
     long long lslo, lshi, lsc;
+    // ---- halo-sharded grids (MODE != 0): one dim is split over the ranks in slabs of win_c
+    // points and every rank keeps win_h halo points of its two neighbours on either side of its slab.
+    // MODE 1 (SLB_FUSED_WIN): the MARCH dim is the sharded one.  The arrays hold nmarch = win_c + 2 win_h rows
+    //   [low halo | slab | high halo]; the march is not periodic: it runs once over those rows and emits the
+    //   win_c outputs of the slab (rows win_h .. win_h + win_c).  A shift whose stencil leaves the halo sets *err.
+    // MODE 2 (SLB_FUSED_PSH): a PASSIVE dim is the sharded one (the arrays are the slab, no halo rows involved
+    //   in the pass itself).
+    // In both modes the outputs that lie within win_h of a slab boundary are ALSO stored into the neighbour's
+    // halo (pushL / pushR != NULL): pushL is the address in the lower neighbour's output array that
+    // corresponds to this rank's output element 0 shifted by +win_c along the sharded dim, pushR the upper
+    // neighbour's shifted by -win_c, so that `own address - oblk[0] + push?` is the halo element.
+    int win_h, win_c;
+    int push_on_lo;              // MODE 2: the sharded passive index is plo (else phi)
+    double* pushL;
+    double* pushR;
+    int* err;
 };
+#define SLB_FUSED_PLAIN 0
+#define SLB_FUSED_WIN 1
+#define SLB_FUSED_PSH 2
 
 // host launcher (slb_pair.cu); returns cudaGetLastError() of the launch, or -1 when (P1, G) is not instantiated
-int slb_fused_launch(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, int P1, bool exact, bool cc,
+int slb_fused_launch(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, int P1, bool exact, bool cc, int mode,
                      unsigned nblocks, unsigned nthreads, size_t smem_bytes, cudaStream_t stream);
 bool slb_fused_supported(int P1, bool cc, int g);
 size_t slb_fused_smem_bytes(int nrows_max, int g);
@@ -154,7 +173,8 @@ __device__ __forceinline__ void fused_weights(const CoefTab& ct, int nc, double 
 
 // G > 0: passive points per tile fixed at compile time (CC = false); G == 0: run-time fa.g (CC = true)
 // W16: rows are fetched with 16-byte cp.async (pairs of doubles; the host checks alignment)
-template <int P1, bool EXACT, bool CC, int G, bool W16>
+// MODE: SLB_FUSED_PLAIN | SLB_FUSED_WIN (CC = false only) | SLB_FUSED_PSH (see FusedArgs)
+template <int P1, bool EXACT, bool CC, int G, bool W16, int MODE>
 __global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, (P1 <= 10 ? 2 : 1))  // orders <= 9: 128 registers, two blocks per SM
 k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ CoefTab ctA, const __grid_constant__ CoefTab ctB)
 {
@@ -198,11 +218,19 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         dA = fabs(fl) < 4.0e18 ? (long long)fl : (fl < 0 ? -4000000000000000000LL : 4000000000000000000LL);
         fused_weights<P1>(ctA, fa.ncA, t, w1);
     }
+    int lo = 0;  // MODE WIN: row (in the haloed array) of the next output this thread emits
     {
         const double alpha = fa.scaleB * __ldg(fa.tabB + (long long)plo * fa.aBlo + (long long)phi * fa.aBhi);
         double t;
         slb_split(alpha, nm, HALF, t, s0B);
         fused_weights<P1>(ctB, fa.ncB, t, w2);
+        if (MODE == SLB_FUSED_WIN) {
+            const double fl = floor(alpha);
+            const int di = fabs(fl) < 1.0e9 ? (int)fl : (fl < 0 ? -1000000000 : 1000000000);
+            lo = HALF - di;  // output row emitted at step P1 - 1: its stencil starts at input row 0
+            // the slab's outputs need input rows win_h + di - HALF .. win_h + win_c + di + HALF of [0, nmarch)
+            if (fa.win_h + di - HALF < 0 || di + HALF + 1 > fa.win_h) atomicOr(fa.err, 1);
+        }
     }
 
     // ---- staged row range: union over the tile's passive points --------------------------------
@@ -240,7 +268,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     constexpr int QS = CC ? 1 : (G > 0 ? G : 1);  // shared-memory stride between consecutive staged rows
     const int sread = CC ? p * fa.nrows_max + roff : roff * g + p;
 
-    const int nsteps = nm + P1 - 1;
+    const int nsteps = MODE == SLB_FUSED_WIN ? nm : nm + P1 - 1;
     const long long smel = fa.ism, scel = fa.isc, osmel = fa.osm, oscel = fa.osc;
     // march index of the outputs emitted at step P1-1, as (block, position in block)
     const int okc = fa.okc;
@@ -256,22 +284,67 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     // in the current output block (plain layout: until the periodic wrap)
     double* po = fa.oblk[oq] + othr + (long long)ol * osmel;
     int oleft = okc - ol;
+    if (MODE == SLB_FUSED_WIN) {  // no blocks, no wrap: row `lo` of the haloed output array (stores are predicated on the window)
+        oq = 0;
+        po = fa.oblk[0] + othr + (long long)lo * osmel;
+        oleft = 0x7fffffff;
+    }
     const bool st_pair = CC && W16 && act1;          // 16-byte store of both outputs
     const bool st_a = act0 && !st_pair, st_b = act1 && !st_pair;
+    // halo pushes: element offsets from this rank's output array to the neighbours' (see FusedArgs)
+    const long long pdL = (MODE != SLB_FUSED_PLAIN && fa.pushL) ? fa.pushL - fa.oblk[0] : 0;
+    const long long pdR = (MODE != SLB_FUSED_PLAIN && fa.pushR) ? fa.pushR - fa.oblk[0] : 0;
+    // MODE PSH: per-thread constants -- this thread's passive point lies in the lower or the upper boundary layer
+    // of the slab (the host guarantees win_c >= 2 win_h: never both), pd is the offset to that neighbour's halo
+    bool psh = false;
+    long long pd = 0;
+    if (MODE == SLB_FUSED_PSH && fa.pushL) {
+        const int ps = (int)(fa.push_on_lo ? plo : phi);
+        const bool toL = ps < fa.win_h, toR = ps >= fa.win_c - fa.win_h;
+        psh = toL || toR;
+        pd = toL ? pdL : pdR;
+    }
     double winA[P1], winB[P1];           // last order+1 values of T for the two cross outputs
 #pragma unroll
     for (int j = 0; j < P1; ++j) winA[j] = winB[j] = 0.0;
     double lsumA = 0.0, lsumB = 0.0;
 
     auto emit = [&](double accA, double accB) {
+        if (MODE == SLB_FUSED_WIN) {
+            // only the slab's rows are this rank's outputs; those within win_h of a slab boundary also go to the
+            // neighbour's halo rows (NVLink peer stores riding inside the pass)
+            const bool inw = (unsigned)(lo - fa.win_h) < (unsigned)fa.win_c;
+            lsumA += inw ? accA : 0.0;
+            lsumB += inw ? accB : 0.0;
+            fused_st(st_a && inw, po, accA);
+            fused_st(st_b && inw, po + oscel, accB);
+            if (fa.pushL) {
+                const bool pl = inw && lo < 2 * fa.win_h, pr = inw && lo >= fa.win_c;
+                fused_st(st_a && pl, po + pdL, accA);
+                fused_st(st_b && pl, po + pdL + oscel, accB);
+                fused_st(st_a && pr, po + pdR, accA);
+                fused_st(st_b && pr, po + pdR + oscel, accB);
+            }
+            ++lo;
+            po += osmel;
+            return;
+        }
         lsumA += accA;
         lsumB += accB;
         if (CC && W16) {  // neighbours in memory, 16-byte aligned: one store; the odd last column is rare
             fused_st_v2(st_pair, po, accA, accB);
             if (st_a) __stcs(po, accA);
+            if (MODE == SLB_FUSED_PSH) {
+                fused_st_v2(st_pair && psh, po + pd, accA, accB);
+                if (st_a && psh) __stcs(po + pd, accA);
+            }
         } else {
             fused_st(st_a, po, accA);
             fused_st(st_b, po + oscel, accB);
+            if (MODE == SLB_FUSED_PSH) {
+                fused_st(st_a && psh, po + pd, accA);
+                fused_st(st_b && psh, po + pd + oscel, accB);
+            }
         }
         po += osmel;
         if (--oleft == 0) {  // next output block (plain layout: wrap around the periodic line) -- rare
@@ -425,7 +498,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
                 const int k = k0 + r;
                 if (k < nsteps) {
                     const double* src = pdir + (long long)(b / fa.ikc) * fa.iblk + (long long)(b % fa.ikc) * smel;
-                    b = b + 1 == nm ? 0 : b + 1;
+                    b = (MODE != SLB_FUSED_WIN && b + 1 == nm) ? 0 : b + 1;
                     int rc = ac + s0A;
                     rc -= rc >= nc_ ? nc_ : 0;
                     double xa[P1 + 1];

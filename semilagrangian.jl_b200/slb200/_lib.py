@@ -12,6 +12,14 @@ c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
 c_void_pp = C.POINTER(C.c_void_p)
 
+class SlbHalo(C.Structure):
+    """struct slb_halo (include/slb200.h)"""
+    _fields_ = [("mode", C.c_int), ("halo", C.c_int), ("shard_dim", C.c_int), ("push_lo", C.c_void_p), ("push_hi", C.c_void_p),
+                ("err_flag", C.c_void_p)]
+
+
+SLB_HALO_MARCH, SLB_HALO_PASSIVE = 1, 2
+
 # every symbol include/slb200.h declares: (name, restype, argtypes)
 SIGNATURES = [
     ("slb_ctx_create", C.c_int, [C.c_int, C.c_void_p, c_void_pp]),
@@ -50,6 +58,20 @@ SIGNATURES = [
     ("slb_sweep_pair_ex", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int,
                                     C.c_int, C.c_int, c_void_pp, C.c_int]),
+    ("slb_sweep_pair_halo", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_int64_p, C.c_double, C.c_int, C.c_int,
+                                      C.POINTER(SlbHalo)]),
+    ("slb_halo_error", C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    ("slb_comm_create", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, c_void_pp]),
+    ("slb_comm_destroy", None, [C.c_void_p]),
+    ("slb_comm_export", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_comm_connect", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_comm_export_buffer", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("slb_comm_open_buffer", C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
+    ("slb_comm_close_buffer", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_comm_barrier", C.c_int, [C.c_void_p]),
+    ("slb_comm_allgather", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_void_pp]),
+    ("slb_poisson_solve_partial", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, c_void_pp]),
     ("slb_ipc_get_handle", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("slb_ipc_open_handle", C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     ("slb_ipc_close_handle", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,6 +1,12 @@
 import os
 import sys
 
+# tests/test_gpu_halo.py builds several ranks inside one process: their kernels wait for each other's flags, so
+# nothing may serialise them behind one another -- no lazy module loading in the middle of a step, one hardware
+# queue per stream.  Both are read when CUDA initialises, hence set before anything imports torch.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

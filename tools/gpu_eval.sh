@@ -37,7 +37,7 @@ for w in $WHAT; do
     bsp)
       for cfg in "bspline_fft 11" "bspline_lu 5" "bspline_lu 3"; do
         set -- $cfg
-        timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu --no-e2e 2>>"$OUT/bench_bsp.err" | tail -1 >> "$OUT/bench_bsp.jsonl"
+        timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu --no-configs 2>>"$OUT/bench_bsp.err" | tail -1 >> "$OUT/bench_bsp.jsonl"
       done
       python - <<PY
 import json
@@ -53,7 +53,7 @@ PY
       for split in ${BSPAB_MODES:-1 0}; do
         for cfg in "bspline_fft 11" "bspline_lu 5" "bspline_lu 3"; do
           set -- $cfg
-          SLB_BSPLINE_RF=$split timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu 2>>"$OUT/bench_bspab.err" | tail -1 > "$OUT/tmp.json"
+          SLB_BSPLINE_RF=$split timeout 300 python bench.py --steps 5 --warmup 3 --interp $1 --order $2 --no-cpu --no-configs 2>>"$OUT/bench_bspab.err" | tail -1 > "$OUT/tmp.json"
           python - <<PY
 import json
 d = json.load(open("$OUT/tmp.json")); k = d["roofline"]["all_kernels"]; c = d["config"]
