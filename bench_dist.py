@@ -87,15 +87,30 @@ def run_distributed(args, B):
     ctx.record(e1)
     torch.cuda.synchronize()
     dist.barrier()
+    # electric energy right after the timed steps: equal on every rank, across N = 1/2/4/8 and to the oracle's
+    ee_after_timed = sh.compute_ee()
+    steps_done = warm + args.steps
+    # where the step goes (outside the timed region): device time between successive advection() calls
+    nst = adv.nbstates
+    evs = [ctx.event() for _ in range(3 * nst + 1)]
+    ctx.record(evs[0])
+    dims = []
+    for k in range(3 * nst):
+        dims.append(sh.getst().perm[0] - 1)
+        sh.advection()
+        ctx.record(evs[k + 1])
+    torch.cuda.synchronize()
+    per_dim = {}
+    for k, dd in enumerate(dims):
+        per_dim.setdefault(dd, []).append(_lib.Context.elapsed_ms(evs[k], evs[k + 1]))
+    call_ms = {f"dim{dd}": float(np.mean(v)) for dd, v in sorted(per_dim.items())}
+    dist.barrier()
     ms = torch.tensor([_lib.Context.elapsed_ms(e0, e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = ctx.launch_count() - launches0
     nfused = sh.n_fused - nf0
     clocks = sampler.stop() if rank == 0 else None
-    # electric energy right after the timed steps: equal on every rank, across N = 1/2/4/8 and to the oracle's
-    ee_after_timed = sh.compute_ee()
-    steps_done = warm + args.steps
 
     # e2e: host slab in, host slab out, every step (pinned host memory)
     nbytes_local = n**4 * 8 // world
@@ -153,6 +168,9 @@ def run_distributed(args, B):
                          "unit": "GB/s", "frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_step_per_gpu": hbm_bytes},
             "nvlink": {"bytes_out_per_gpu_per_step": out_bytes, "peak_GBps": 770.0, "peak_source": "B200_PROFILING.md peer copy",
                        "bound_ms": out_bytes / 770e9 * 1e3, "frac_of_step": (out_bytes / 770e9 * 1e3) / ms_step, "note": link_note},
+            "advection_call_ms": call_ms,
+            "advection_call_note": "rank 0, device time between successive advection() calls: dim2 = charge density + mailbox all-gather + "
+                                   "Poisson solve (its sweep is deferred), dim3 = the v1v2 pass, dim1 = the x1x2 pass",
             "ee_after_timed": ee_after_timed, "steps_done": steps_done,
         }
         print(json.dumps(line))

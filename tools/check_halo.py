@@ -23,13 +23,14 @@ order = int(sys.argv[2]) if len(sys.argv) > 2 else 7
 nsteps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 ms = (S.UniformMesh(0.0, 4 * math.pi, n), S.UniformMesh(0.0, 4 * math.pi, n), S.UniformMesh(-6.0, 6.0, n), S.UniformMesh(-6.0, 6.0, n))
 tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
-adv = S.Advection(ms, [S.Lagrange(order)] * 4, 0.1, tabst)
+ctx1 = S.Context(local)   # ONE context (stream) for the single-GPU reference run: its provider and its grid must share it
+adv = S.Advection(ms, [S.Lagrange(order)] * 4, 0.1, tabst, ctx=ctx1)
 fsp = lambda x: 0.5 * np.cos(x / 2) + 1
 fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
 f = S.dotprod((fsp(ms[0].points), fsp(ms[1].points), fv(ms[2].points), fv(ms[3].points)))
 c = n // world
 sh = HaloShardedAdvectionData(adv, np.asfortranarray(f[:, :, :, rank * c:(rank + 1) * c]), rank, world, torch_allgather_bytes(dist), device=local)
-plain = S.AdvectionData(adv, f, S.getpoissonvar(adv), ctx=S.Context(local))
+plain = S.AdvectionData(adv, f, S.getpoissonvar(adv, ctx=ctx1), ctx=ctx1)
 worst = 0.0
 for step in range(nsteps):
     while S.advection(plain):
