@@ -19,6 +19,7 @@
 #include "slb_bspline.cuh"
 #include "slb_bspfused.cuh"
 #include "slb_bspsplit.cuh"
+#include "slb_bspseg.cuh"
 #include "slb_field.cuh"
 #include "slb_points.cuh"
 
@@ -67,6 +68,8 @@ struct slb_interp {
     BspRfTab bsprf;
     double* bspstab_dev;       // tables of the split-line fused sweep (two warps per tile, slb_bspsplit.cuh), or NULL
     BspSplitTab bspstab;
+    int seg_ok, wl_ok;         // segmented sweeps (slb_bspseg.cuh): block-per-tile / warp-per-line plans exist
+    BspSegTab segtab, wltab;
 };
 
 struct slb_poisson {
@@ -80,6 +83,9 @@ struct slb_poisson {
     double2* wx[2 * SLB_FIELD_MAXDIM];  // per-component work buffers of the one-kernel field solve
     double* red;                        // its block sums
     int coop_blocks;                    // cooperative grid size (0: cooperative launch unavailable)
+    int fft_ok;                         // power-of-two extents within the cluster FFT kernel's limits (k_field_fft)
+    int fft_log[2];
+    double* fft_mean;
 };
 
 static long long env_ll(const char* name, long long dflt)
@@ -419,6 +425,7 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
     memset(&it->bspstab, 0, sizeof(it->bspstab));
     it->bsprf_dev = nullptr;
     memset(&it->bsprf, 0, sizeof(it->bsprf));
+    it->seg_ok = it->wl_ok = 0;
     if (bs) {
         std::string msg;
         BsplineHost hb;
@@ -444,6 +451,8 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
             BspRfHost hr;
             std::string msg2;
             if (bsprf_factor(order, n, node_vals, &hr, msg2) == SLB_OK) {
+                it->seg_ok = slb_bspseg_plan(hr, false, &it->segtab) ? 1 : 0;
+                it->wl_ok = slb_bspseg_plan(hr, true, &it->wltab) ? 1 : 0;
                 std::vector<double> v;
                 bsprf_fill(&it->bsprf, v, hr);
                 if (slb_bspfused_warps_rf(it->bsprf.ndoubles, hb.n, true) > 0) {
@@ -693,6 +702,39 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
                                                        (flags & SLB_SWEEP_EXACT) ? 1 : 0);
         LAUNCH_CHECK(c);
         return slb_grid_swap(g);
+    }
+    if (bs && !(flags & SLB_SWEEP_EXACT) && (it->seg_ok || it->wl_ok) && env_ll("SLB_BSPLINE_SEG", 1) != 0) {
+        // segmented sweeps (slb_bspseg.cuh): S threads per line, line data in registers
+        const bool contig = v.inner == 1;
+        const bool wl = it->wl_ok && !omp && !imp && !g->linesum;
+        const bool sg = it->seg_ok && !(contig && (g->linesum || omp)) && !(imp && !contig);
+        if (wl || sg) {
+            BspSegArgs a;
+            memset(&a, 0, sizeof(a));
+            a.in = g->front;
+            a.out = g->back;
+            a.inner = v.inner;
+            a.nlines = v.inner * v.outer;
+            a.n = v.n;
+            a.nc = it->nc;
+            a.am = am;
+            if (omp)
+                a.om = *omp;
+            else {
+                a.om.kc = v.n;
+                a.om.bstride = (long long)v.n * v.inner;
+            }
+            if (imp) a.im = *imp;
+            a.linesum = g->linesum;
+            a.tab = sg ? it->segtab : it->wltab;
+            const int lrc = sg ? slb_bspseg_launch(a, it->tab, contig, c->stream) : slb_bspwline_launch(a, it->tab, c->stream);
+            if (lrc > 0) return fail(SLB_E_CUDA, "slb_sweep: segmented B-spline launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
+            if (lrc == 0) {
+                c->launches++;
+                return slb_grid_swap(g);
+            }
+            // lrc < 0: not instantiated for this shape: fall through to the thread-per-line kernels
+        }
     }
     const bool use_rf = bs && it->bsprf_dev && env_ll("SLB_BSPLINE_RF", 1) != 0;
     // two warps per line pay off while the look-back start-up of a half line is short (measured at 128^4: order 3
@@ -1315,6 +1357,7 @@ extern "C" void slb_poisson_destroy(slb_poisson* p)
     for (int d = 0; d < 2 * SLB_FIELD_MAXDIM; ++d)
         if (p->wx[d]) cudaFree(p->wx[d]);
     if (p->red) cudaFree(p->red);
+    if (p->fft_mean) cudaFree(p->fft_mean);
     delete p;
 }
 
@@ -1369,6 +1412,22 @@ extern "C" int slb_poisson_create(slb_ctx* c, int nsp, const int64_t* ext, const
             e = cudaMalloc(&p->red, (size_t)p->coop_blocks * sizeof(double));
         }
         cudaGetLastError();
+        // cluster FFT kernel: power-of-two extents, one or two space dims
+        auto lg = [](int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return (((int64_t)1 << l) == v) ? l : -1; };
+        const int la = lg(ext[0]), lb = nsp == 2 ? lg(ext[1]) : 0;
+        const int64_t lim = nsp == 2 ? SLB_FFT_NMAX : 4096;
+        if (nsp <= 2 && la >= 1 && lb >= 0 && ext[0] <= lim && (nsp == 1 || (ext[1] <= lim && lb >= 1))) {
+            const int nth = nsp == 2 ? SLB_FFT_THREADS : 32;
+            const int n2 = nsp == 2 ? (int)ext[1] : 1;
+            const size_t fsm = ((size_t)ext[0] + n2 + (size_t)2 * (nth / 32) * nmax) * sizeof(double2);
+            if (cudaFuncSetAttribute(k_field_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) == cudaSuccess &&
+                cudaMalloc(&p->fft_mean, sizeof(double)) == cudaSuccess) {
+                p->fft_ok = 1;
+                p->fft_log[0] = la;
+                p->fft_log[1] = lb;
+            }
+            cudaGetLastError();
+        }
     }
     if (e != cudaSuccess) {
         slb_poisson_destroy(p);
@@ -1442,6 +1501,47 @@ static int field_from_partial(slb_poisson* p, const double* partial, int nchunk,
                               double* const* E_dev)
 {
     slb_ctx* c = p->ctx;
+    if (p->fft_ok && env_ll("SLB_FIELD_FFT", 1) != 0) {
+        FieldFftArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.partial = partial;
+        fa.nchunk = nchunk;
+        fa.scale = scale;
+        fa.subtract_mean = subtract_mean;
+        fa.nsp = p->nsp;
+        fa.n1 = (int)p->ext[0];
+        fa.n2 = p->nsp == 2 ? (int)p->ext[1] : 1;
+        fa.l1 = p->fft_log[0];
+        fa.l2 = p->fft_log[1];
+        fa.tw1 = p->tw[0];
+        fa.tw2 = p->nsp == 2 ? p->tw[1] : p->tw[0];
+        for (int d = 0; d < p->nsp; ++d) {
+            fa.mult[d] = p->mult[d];
+            fa.E[d] = E_dev[d];
+            fa.wc[d] = p->wx[2 * d];
+        }
+        fa.rho = rho_dev;
+        fa.wa = p->wa;
+        fa.mean = p->fft_mean;
+        const int nth = p->nsp == 2 ? SLB_FFT_THREADS : 32;
+        const int nmax = fa.n1 > fa.n2 ? fa.n1 : fa.n2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(p->nsp == 2 ? SLB_FFT_CLUSTER : 1);
+        cfg.blockDim = dim3(nth);
+        cfg.dynamicSmemBytes = ((size_t)fa.n1 + fa.n2 + (size_t)2 * (nth / 32) * nmax) * sizeof(double2);
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cfg.gridDim.x;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_field_fft, fa));
+        c->launches++;
+        return SLB_OK;
+    }
     if (!p->coop_blocks) return SLB_E_UNSUPPORTED;
     FieldArgs fa;
     memset(&fa, 0, sizeof(fa));

@@ -371,3 +371,146 @@ __global__ void __launch_bounds__(128) k_field_solve(const __grid_constant__ Fie
         inner *= n;
     }
 }
+
+
+// ------------------------------------------------------------------------------------------
+// K5c: the same field solve for power-of-two space grids up to 256 points per dim, as radix-2 FFTs inside ONE
+// thread-block cluster (8 CTAs x 16 warps, one line per warp in shared memory) with two cluster barriers instead
+// of five grid barriers around O(n^2) line DFTs: ~10 us instead of ~50 us per solve at 128^2 -- two solves per
+// Strang step, which is 4 % of the step on one GPU and 15 % when the grid is sharded over eight.
+//   phase 0: rho = scale * sum_c partial[c]  (stored raw), forward FFT of every x1 line          -> wa
+//   phase 1: per x1 wavenumber: forward FFT along x2 (the spectrum, in shared memory; its (0,0) entry / N is the
+//            mean of src/util_poisson.jl:77), then per component the multiplier i k_x/|k|^2 (fctv_k,
+//            src/poisson.jl:7-15; its zero mode is 0, so the mean never reaches E) and the inverse FFT along x2 -> wc[x]
+//   phase 2: per component the inverse FFT of every x1 line, real part -> E_x; rho -= mean
+// One space dim (1D1V): a single warp does forward FFT, multiplier and inverse FFT of the one line.
+// ------------------------------------------------------------------------------------------
+#define SLB_FFT_CLUSTER 8
+#define SLB_FFT_THREADS 512
+#define SLB_FFT_NMAX 256
+struct FieldFftArgs {
+    const double* partial;   // [nchunk][n1*n2]
+    int nchunk;
+    double scale;
+    int subtract_mean;
+    int nsp, n1, n2, l1, l2;  // n2 = 1, l2 = 0 for one space dim
+    const double2* tw1;       // exp(-2 pi i m / n1)
+    const double2* tw2;
+    const double* mult[2];
+    double* rho;
+    double* E[2];
+    double2* wa;
+    double2* wc[2];
+    double* mean;             // one double of work space
+};
+
+// in-place radix-2 decimation-in-time FFT of a line held in shared memory in BIT-REVERSED order, by one warp;
+// tw = forward twiddles exp(-2 pi i m / n) in shared memory (conjugated for the inverse transform)
+template <bool INVERSE>
+__device__ __forceinline__ void field_warp_fft(double2* x, int n, int logn, const double2* tw, int lane)
+{
+    for (int s = 1; s <= logn; ++s) {
+        const int half = 1 << (s - 1);
+        __syncwarp();
+        for (int b = lane; b < (n >> 1); b += 32) {
+            const int k = b & (half - 1);
+            const int i0 = ((b >> (s - 1)) << s) + k;
+            const int i1 = i0 + half;
+            double2 w = tw[k << (logn - s)];
+            if (INVERSE) w.y = -w.y;
+            const double2 u = x[i0], v = x[i1];
+            const double tr = fma(v.x, w.x, -v.y * w.y), ti = fma(v.x, w.y, v.y * w.x);
+            x[i0] = make_double2(u.x + tr, u.y + ti);
+            x[i1] = make_double2(u.x - tr, u.y - ti);
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int field_brev(int i, int logn) { return logn ? (int)(__brev((unsigned)i) >> (32 - logn)) : 0; }
+
+__global__ void __launch_bounds__(SLB_FFT_THREADS) k_field_fft(const __grid_constant__ FieldFftArgs fa)
+{
+    namespace cg = cooperative_groups;
+    extern __shared__ double2 fsm2[];
+    const int n1 = fa.n1, n2 = fa.n2, l1 = fa.l1, l2 = fa.l2;
+    const int nmax = n1 > n2 ? n1 : n2;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double2* tw1 = fsm2;
+    double2* tw2 = fsm2 + n1;
+    double2* xa = fsm2 + n1 + n2 + (size_t)(2 * w) * nmax;  // two lines per warp
+    double2* xb = xa + nmax;
+    for (int j = threadIdx.x; j < n1; j += blockDim.x) tw1[j] = fa.tw1[j];
+    if (fa.nsp == 2)
+        for (int j = threadIdx.x; j < n2; j += blockDim.x) tw2[j] = fa.tw2[j];
+    __syncthreads();
+    const int gw = blockIdx.x * nw + w, W = gridDim.x * nw;
+    const long long ntot = (long long)n1 * n2;
+    // ---- phase 0 -------------------------------------------------------------------------------------------
+    for (int j = gw; j < n2; j += W) {
+        const long long base = (long long)n1 * j;
+        for (int a = lane; a < n1; a += 32) {
+            double s = 0.0;
+            for (int c = 0; c < fa.nchunk; ++c) s += fa.partial[(long long)c * ntot + base + a];
+            s *= fa.scale;
+            fa.rho[base + a] = s;
+            xa[field_brev(a, l1)] = make_double2(s, 0.0);
+        }
+        field_warp_fft<false>(xa, n1, l1, tw1, lane);
+        if (fa.nsp == 2) {
+            for (int k = lane; k < n1; k += 32) fa.wa[base + k] = xa[k];
+        } else {
+            // one space dim: multiplier and inverse transform right here
+            const double mean = fa.subtract_mean ? xa[0].x / (double)n1 : 0.0;
+            __syncwarp();
+            for (int k = lane; k < n1; k += 32) {
+                const double2 v = xa[k];
+                const double mm = fa.mult[0][k];
+                xb[field_brev(k, l1)] = make_double2(-v.y * mm, v.x * mm);
+            }
+            field_warp_fft<true>(xb, n1, l1, tw1, lane);
+            const double sc = 1.0 / (double)n1;
+            for (int a = lane; a < n1; a += 32) {
+                fa.E[0][a] = xb[a].x * sc;
+                fa.rho[a] -= mean;
+            }
+        }
+    }
+    if (fa.nsp != 2) return;
+    cg::this_cluster().sync();
+    // ---- phase 1: columns ------------------------------------------------------------------------------------
+    for (int k1 = gw; k1 < n1; k1 += W) {
+        for (int j = lane; j < n2; j += 32) xa[field_brev(j, l2)] = fa.wa[k1 + (long long)n1 * j];
+        field_warp_fft<false>(xa, n2, l2, tw2, lane);
+        if (k1 == 0 && lane == 0) *fa.mean = fa.subtract_mean ? xa[0].x / (double)ntot : 0.0;
+        const double sc = 1.0 / (double)n2;
+        for (int x = 0; x < 2; ++x) {
+            __syncwarp();
+            for (int k2 = lane; k2 < n2; k2 += 32) {
+                const double2 v = xa[k2];
+                const double mm = fa.mult[x][k1 + (long long)n1 * k2];
+                xb[field_brev(k2, l2)] = make_double2(-v.y * mm, v.x * mm);
+            }
+            field_warp_fft<true>(xb, n2, l2, tw2, lane);
+            for (int j = lane; j < n2; j += 32) {
+                const double2 v = xb[j];
+                fa.wc[x][k1 + (long long)n1 * j] = make_double2(v.x * sc, v.y * sc);
+            }
+        }
+    }
+    cg::this_cluster().sync();
+    // ---- phase 2: inverse x1 lines of both components; mean removal -------------------------------------------
+    const double mean = *fa.mean;
+    const double sc1 = 1.0 / (double)n1;
+    for (int t = gw; t < 2 * n2; t += W) {
+        const int x = t / n2, j = t - x * n2;
+        const long long base = (long long)n1 * j;
+        __syncwarp();
+        for (int k = lane; k < n1; k += 32) xa[field_brev(k, l1)] = fa.wc[x][base + k];
+        field_warp_fft<true>(xa, n1, l1, tw1, lane);
+        for (int a = lane; a < n1; a += 32) {
+            fa.E[x][base + a] = xa[a].x * sc1;
+            if (x == 0 && fa.subtract_mean) fa.rho[base + a] -= mean;
+        }
+    }
+}
