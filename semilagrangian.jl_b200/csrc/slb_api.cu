@@ -311,12 +311,12 @@ extern "C" int slb_grid_create(slb_ctx* c, int nd, const int64_t* ext, slb_grid*
     cudaError_t e = cudaMalloc(&g->front, g->numel * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&g->back, g->numel * sizeof(double));
     if (e != cudaSuccess) {
+        const long long nbytes = (long long)(g->numel * 8);
         if (g->front) cudaFree(g->front);
         delete g;
         *out = nullptr;
         cudaGetLastError();
-        return fail(SLB_E_ALLOC, "slb_grid_create: cudaMalloc of 2 x %lld bytes failed: %s",
-                    (long long)(g->numel * 8), cudaGetErrorString(e));
+        return fail(SLB_E_ALLOC, "slb_grid_create: cudaMalloc of 2 x %lld bytes failed: %s", nbytes, cudaGetErrorString(e));
     }
     g->owned = true;
     return SLB_OK;

@@ -405,26 +405,65 @@ struct FieldFftArgs {
 };
 
 // in-place radix-2 decimation-in-time FFT of a line held in shared memory in BIT-REVERSED order, by one warp;
-// tw = forward twiddles exp(-2 pi i m / n) in shared memory (conjugated for the inverse transform)
-template <bool INVERSE>
-__device__ __forceinline__ void field_warp_fft(double2* x, int n, int logn, const double2* tw, int lane)
+// tw = forward twiddles exp(-2 pi i m / n) in shared memory (conjugated for the inverse transform).
+// LOGN > 0: line length known at compile time -- stages and the n / 64 butterflies of a lane fully unrolled
+// (independent instruction streams, no loop or index bookkeeping); LOGN == 0: run-time length.
+template <bool INVERSE, int LOGN>
+__device__ __forceinline__ void field_warp_fft_t(double2* x, int n_rt, int logn_rt, const double2* tw, int lane)
 {
-    for (int s = 1; s <= logn; ++s) {
+    const int logn = LOGN > 0 ? LOGN : logn_rt;
+    const int n = LOGN > 0 ? (1 << LOGN) : n_rt;
+    constexpr int NBF = LOGN > 5 ? (1 << (LOGN - 6)) : 1;  // butterflies per lane and stage (compile-time form)
+#pragma unroll
+    for (int s = 1; s <= (LOGN > 0 ? LOGN : 30); ++s) {
+        if (LOGN == 0 && s > logn) break;
         const int half = 1 << (s - 1);
         __syncwarp();
-        for (int b = lane; b < (n >> 1); b += 32) {
-            const int k = b & (half - 1);
-            const int i0 = ((b >> (s - 1)) << s) + k;
-            const int i1 = i0 + half;
-            double2 w = tw[k << (logn - s)];
-            if (INVERSE) w.y = -w.y;
-            const double2 u = x[i0], v = x[i1];
-            const double tr = fma(v.x, w.x, -v.y * w.y), ti = fma(v.x, w.y, v.y * w.x);
-            x[i0] = make_double2(u.x + tr, u.y + ti);
-            x[i1] = make_double2(u.x - tr, u.y - ti);
+        if (LOGN > 5) {
+            double2 u[NBF], v[NBF], w[NBF];
+            int i0[NBF];
+#pragma unroll
+            for (int q = 0; q < NBF; ++q) {
+                const int b = lane + 32 * q;
+                const int k = b & (half - 1);
+                i0[q] = ((b >> (s - 1)) << s) + k;
+                w[q] = tw[k << (logn - s)];
+                u[q] = x[i0[q]];
+                v[q] = x[i0[q] + half];
+            }
+#pragma unroll
+            for (int q = 0; q < NBF; ++q) {
+                const double wy = INVERSE ? -w[q].y : w[q].y;
+                const double tr = fma(v[q].x, w[q].x, -v[q].y * wy), ti = fma(v[q].x, wy, v[q].y * w[q].x);
+                x[i0[q]] = make_double2(u[q].x + tr, u[q].y + ti);
+                x[i0[q] + half] = make_double2(u[q].x - tr, u[q].y - ti);
+            }
+        } else {
+            for (int b = lane; b < (n >> 1); b += 32) {
+                const int k = b & (half - 1);
+                const int i0 = ((b >> (s - 1)) << s) + k;
+                const int i1 = i0 + half;
+                double2 w = tw[k << (logn - s)];
+                if (INVERSE) w.y = -w.y;
+                const double2 u = x[i0], v = x[i1];
+                const double tr = fma(v.x, w.x, -v.y * w.y), ti = fma(v.x, w.y, v.y * w.x);
+                x[i0] = make_double2(u.x + tr, u.y + ti);
+                x[i1] = make_double2(u.x - tr, u.y - ti);
+            }
         }
     }
     __syncwarp();
+}
+
+template <bool INVERSE>
+__device__ __forceinline__ void field_warp_fft(double2* x, int n, int logn, const double2* tw, int lane)
+{
+    switch (logn) {  // block-uniform
+    case 6: field_warp_fft_t<INVERSE, 6>(x, n, logn, tw, lane); break;
+    case 7: field_warp_fft_t<INVERSE, 7>(x, n, logn, tw, lane); break;
+    case 8: field_warp_fft_t<INVERSE, 8>(x, n, logn, tw, lane); break;
+    default: field_warp_fft_t<INVERSE, 0>(x, n, logn, tw, lane); break;
+    }
 }
 
 __device__ __forceinline__ int field_brev(int i, int logn) { return logn ? (int)(__brev((unsigned)i) >> (32 - logn)) : 0; }

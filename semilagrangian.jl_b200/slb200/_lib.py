@@ -148,6 +148,7 @@ class Context:
     """One per process and GPU (slb_ctx)."""
 
     LEGACY_DEFAULT_STREAM = 1  # cudaStreamLegacy: adopt the default stream explicitly
+    _next_serial = 1
 
     def __init__(self, device=0, stream=None):
         """stream: None -> the library creates a private non-blocking stream; an integer
@@ -158,6 +159,11 @@ class Context:
         check(lib().slb_ctx_create(int(device), C.c_void_p(int(stream)) if stream is not None else None, C.byref(h)))
         self.h = h
         self.device = device
+        # caches elsewhere (interpolation handles, pooled device fields) are keyed by this serial number, never by
+        # id(ctx): ids are reused once a Context has been collected.  Cached handles register a release callback here.
+        self.serial = Context._next_serial
+        Context._next_serial += 1
+        self._on_close = []
 
     def sync(self):
         check(lib().slb_sync(self.h))
@@ -208,8 +214,17 @@ class Context:
         self.sync()
         return out
 
+    def on_close(self, fn):
+        self._on_close.append(fn)
+
     def close(self):
         if self.h:
+            for fn in reversed(self._on_close):
+                try:
+                    fn()
+                except Exception:
+                    pass
+            self._on_close = []
             lib().slb_ctx_destroy(self.h)
             self.h = None
 

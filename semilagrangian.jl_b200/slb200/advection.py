@@ -254,8 +254,7 @@ class AdvectionData:
             if fld is not None:
                 fld.free()
         self.bufcur, self.t_bufc = None, []
-        if hasattr(self.parext, "close"):
-            self.parext.close()
+        # the displacement provider is the caller's object (it may serve other AdvectionData): not closed here
 
     def __del__(self):
         try:

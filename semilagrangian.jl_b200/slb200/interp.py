@@ -216,7 +216,7 @@ class AbstractInterpolation:
 
     def handle(self, ctx, n):
         """device object for lines of length n (created lazily, cached per context)."""
-        key = (id(ctx), int(n) if self.kind in (BSPLINE_LU, BSPLINE_FFT) else 0)
+        key = (ctx.serial, int(n) if self.kind in (BSPLINE_LU, BSPLINE_FFT) else 0)
         h = self._handles.get(key)
         if h is None:
             if self.kind in (BSPLINE_LU, BSPLINE_FFT) and int(n) != self.n:
@@ -231,6 +231,12 @@ class AbstractInterpolation:
                 )
             )
             self._handles[key] = h
+
+            def release(key=key, h=h):  # the context is closing: its device objects go with it
+                if self._handles.pop(key, None) is not None:
+                    _lib.lib().slb_interp_destroy(h)
+
+            ctx.on_close(release)
         return h
 
     def getprecal(self, decf):

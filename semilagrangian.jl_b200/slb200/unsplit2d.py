@@ -56,7 +56,7 @@ class DeviceField:
         self.numel = self.n1 * self.n2 * self.ncomp
         self.owned = ptr is None
         if ptr is None:
-            free = DeviceField._pool.get((id(ctx), self.numel))
+            free = DeviceField._pool.get((ctx.serial, self.numel))
             ptr = free.pop() if free else ctx.malloc(self.numel * 8)
         self.ptr = ptr
 
@@ -104,7 +104,11 @@ class DeviceField:
     def free(self):
         """return the storage to the free list (stream-ordered reuse)"""
         if self.ptr is not None and self.owned:
-            DeviceField._pool.setdefault((id(self.ctx), self.numel), []).append(self.ptr)
+            key = (self.ctx.serial, self.numel)
+            if not any(k[0] == self.ctx.serial for k in DeviceField._pool):
+                ctx = self.ctx
+                ctx.on_close(lambda: DeviceField.release_pool(ctx))  # pooled blocks die with their context
+            DeviceField._pool.setdefault(key, []).append(self.ptr)
         self.ptr = None
 
     def __del__(self):
@@ -116,7 +120,7 @@ class DeviceField:
     @classmethod
     def release_pool(cls, ctx):
         """cudaFree every pooled block of a context"""
-        for key in [k for k in cls._pool if k[0] == id(ctx)]:
+        for key in [k for k in cls._pool if k[0] == ctx.serial]:
             for p in cls._pool.pop(key):
                 ctx.free(p)
 
