@@ -1416,7 +1416,7 @@ extern "C" int slb_poisson_create(slb_ctx* c, int nsp, const int64_t* ext, const
         auto lg = [](int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return (((int64_t)1 << l) == v) ? l : -1; };
         const int la = lg(ext[0]), lb = nsp == 2 ? lg(ext[1]) : 0;
         const int64_t lim = nsp == 2 ? SLB_FFT_NMAX : 4096;
-        if (nsp <= 2 && la >= 1 && lb >= 0 && ext[0] <= lim && (nsp == 1 || (ext[1] <= lim && lb >= 1))) {
+        if (nsp <= 2 && la >= 1 && lb >= 0 && ext[0] <= lim && (nsp == 1 || (ext[1] <= lim && lb >= 1 && coop))) {
             const int nth = nsp == 2 ? SLB_FFT_THREADS : 32;
             const int n2 = nsp == 2 ? (int)ext[1] : 1;
             const size_t fsm = ((size_t)ext[0] + n2 + (size_t)2 * (nth / 32) * nmax) * sizeof(double2);
@@ -1523,22 +1523,14 @@ static int field_from_partial(slb_poisson* p, const double* partial, int nchunk,
         fa.rho = rho_dev;
         fa.wa = p->wa;
         fa.mean = p->fft_mean;
-        const int nth = p->nsp == 2 ? SLB_FFT_THREADS : 32;
         const int nmax = fa.n1 > fa.n2 ? fa.n1 : fa.n2;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(p->nsp == 2 ? SLB_FFT_CLUSTER : 1);
-        cfg.blockDim = dim3(nth);
-        cfg.dynamicSmemBytes = ((size_t)fa.n1 + fa.n2 + (size_t)2 * (nth / 32) * nmax) * sizeof(double2);
-        cfg.stream = c->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cfg.gridDim.x;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_field_fft, fa));
+        const int nth = p->nsp == 2 ? SLB_FFT_THREADS : 32;
+        const size_t fsm = ((size_t)fa.n1 + fa.n2 + (size_t)2 * (nth / 32) * nmax) * sizeof(double2);
+        void* kargs[] = {&fa};
+        if (p->nsp == 2)
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_field_fft, dim3(SLB_FFT_BLOCKS), dim3(nth), kargs, fsm, c->stream));
+        else
+            k_field_fft<<<1, nth, fsm, c->stream>>>(fa);
         c->launches++;
         return SLB_OK;
     }

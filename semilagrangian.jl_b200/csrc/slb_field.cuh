@@ -374,10 +374,11 @@ __global__ void __launch_bounds__(128) k_field_solve(const __grid_constant__ Fie
 
 
 // ------------------------------------------------------------------------------------------
-// K5c: the same field solve for power-of-two space grids up to 256 points per dim, as radix-2 FFTs inside ONE
-// thread-block cluster (8 CTAs x 16 warps, one line per warp in shared memory) with two cluster barriers instead
-// of five grid barriers around O(n^2) line DFTs: ~10 us instead of ~50 us per solve at 128^2 -- two solves per
-// Strang step, which is 4 % of the step on one GPU and 15 % when the grid is sharded over eight.
+// K5c: the same field solve for power-of-two space grids up to 256 points per dim, as radix-2 FFTs: a small
+// cooperative grid (32 blocks x 8 warps, one line per warp in shared memory) with two grid barriers instead of five
+// around O(n^2) line DFTs.  (A first version ran inside one 8-block cluster: 96 transforms per SM made it
+// shared-memory-bandwidth bound, 35-41 us; the work is tiny but wants to be spread.)  Two solves per Strang step:
+// 4 % of the step on one GPU, 15 % when the grid is sharded over eight.
 //   phase 0: rho = scale * sum_c partial[c]  (stored raw), forward FFT of every x1 line          -> wa
 //   phase 1: per x1 wavenumber: forward FFT along x2 (the spectrum, in shared memory; its (0,0) entry / N is the
 //            mean of src/util_poisson.jl:77), then per component the multiplier i k_x/|k|^2 (fctv_k,
@@ -385,8 +386,8 @@ __global__ void __launch_bounds__(128) k_field_solve(const __grid_constant__ Fie
 //   phase 2: per component the inverse FFT of every x1 line, real part -> E_x; rho -= mean
 // One space dim (1D1V): a single warp does forward FFT, multiplier and inverse FFT of the one line.
 // ------------------------------------------------------------------------------------------
-#define SLB_FFT_CLUSTER 8
-#define SLB_FFT_THREADS 512
+#define SLB_FFT_BLOCKS 32     // cooperative grid: 32 blocks x 8 warps = one line per warp in the widest phase at 128^2
+#define SLB_FFT_THREADS 256
 #define SLB_FFT_NMAX 256
 struct FieldFftArgs {
     const double* partial;   // [nchunk][n1*n2]
@@ -404,19 +405,24 @@ struct FieldFftArgs {
     double* mean;             // one double of work space
 };
 
-// in-place radix-2 decimation-in-time FFT of a line held in shared memory in BIT-REVERSED order, by one warp;
-// tw = forward twiddles exp(-2 pi i m / n) in shared memory (conjugated for the inverse transform).
-// LOGN > 0: line length known at compile time -- stages and the n / 64 butterflies of a lane fully unrolled
-// (independent instruction streams, no loop or index bookkeeping); LOGN == 0: run-time length.
+// In-place radix-2 FFTs of a line held in shared memory, by one warp, without any bit-reversal pass:
+//   forward  = decimation in frequency : natural order in  -> BIT-REVERSED order out   (stages n/2 ... 1)
+//   inverse  = decimation in time      : bit-reversed in   -> natural order out        (stages 1 ... n/2)
+// so the spectrum simply stays in bit-reversed order between the two (the multiplier is looked up at the reversed
+// index).  Twiddles come from a per-stage table tws[half + k] = exp(-2 pi i k / (2 half)), k < half, so that the
+// lanes of a stage read consecutive entries (a stride-n/m walk through one table is an 8-way bank conflict; that
+// and the bit-reversed scatter were half of all shared-memory wavefronts of the first version of this kernel).
+// LOGN > 5: line length known at compile time, the n / 64 butterflies of a lane unrolled.
 template <bool INVERSE, int LOGN>
-__device__ __forceinline__ void field_warp_fft_t(double2* x, int n_rt, int logn_rt, const double2* tw, int lane)
+__device__ __forceinline__ void field_warp_fft_t(double2* x, int n_rt, int logn_rt, const double2* tws, int lane)
 {
     const int logn = LOGN > 0 ? LOGN : logn_rt;
     const int n = LOGN > 0 ? (1 << LOGN) : n_rt;
     constexpr int NBF = LOGN > 5 ? (1 << (LOGN - 6)) : 1;  // butterflies per lane and stage (compile-time form)
 #pragma unroll
-    for (int s = 1; s <= (LOGN > 0 ? LOGN : 30); ++s) {
-        if (LOGN == 0 && s > logn) break;
+    for (int st = 1; st <= (LOGN > 0 ? LOGN : 30); ++st) {
+        if (LOGN == 0 && st > logn) break;
+        const int s = INVERSE ? st : logn + 1 - st;
         const int half = 1 << (s - 1);
         __syncwarp();
         if (LOGN > 5) {
@@ -427,28 +433,38 @@ __device__ __forceinline__ void field_warp_fft_t(double2* x, int n_rt, int logn_
                 const int b = lane + 32 * q;
                 const int k = b & (half - 1);
                 i0[q] = ((b >> (s - 1)) << s) + k;
-                w[q] = tw[k << (logn - s)];
+                w[q] = tws[half + k];
                 u[q] = x[i0[q]];
                 v[q] = x[i0[q] + half];
             }
 #pragma unroll
             for (int q = 0; q < NBF; ++q) {
-                const double wy = INVERSE ? -w[q].y : w[q].y;
-                const double tr = fma(v[q].x, w[q].x, -v[q].y * wy), ti = fma(v[q].x, wy, v[q].y * w[q].x);
-                x[i0[q]] = make_double2(u[q].x + tr, u[q].y + ti);
-                x[i0[q] + half] = make_double2(u[q].x - tr, u[q].y - ti);
+                if (INVERSE) {
+                    const double tr = fma(v[q].x, w[q].x, v[q].y * w[q].y), ti = fma(v[q].y, w[q].x, -v[q].x * w[q].y);  // conj(w) v
+                    x[i0[q]] = make_double2(u[q].x + tr, u[q].y + ti);
+                    x[i0[q] + half] = make_double2(u[q].x - tr, u[q].y - ti);
+                } else {
+                    const double dr = u[q].x - v[q].x, di = u[q].y - v[q].y;
+                    x[i0[q]] = make_double2(u[q].x + v[q].x, u[q].y + v[q].y);
+                    x[i0[q] + half] = make_double2(fma(dr, w[q].x, -di * w[q].y), fma(dr, w[q].y, di * w[q].x));
+                }
             }
         } else {
             for (int b = lane; b < (n >> 1); b += 32) {
                 const int k = b & (half - 1);
                 const int i0 = ((b >> (s - 1)) << s) + k;
                 const int i1 = i0 + half;
-                double2 w = tw[k << (logn - s)];
-                if (INVERSE) w.y = -w.y;
+                const double2 w = tws[half + k];
                 const double2 u = x[i0], v = x[i1];
-                const double tr = fma(v.x, w.x, -v.y * w.y), ti = fma(v.x, w.y, v.y * w.x);
-                x[i0] = make_double2(u.x + tr, u.y + ti);
-                x[i1] = make_double2(u.x - tr, u.y - ti);
+                if (INVERSE) {
+                    const double tr = fma(v.x, w.x, v.y * w.y), ti = fma(v.y, w.x, -v.x * w.y);
+                    x[i0] = make_double2(u.x + tr, u.y + ti);
+                    x[i1] = make_double2(u.x - tr, u.y - ti);
+                } else {
+                    const double dr = u.x - v.x, di = u.y - v.y;
+                    x[i0] = make_double2(u.x + v.x, u.y + v.y);
+                    x[i1] = make_double2(fma(dr, w.x, -di * w.y), fma(dr, w.y, di * w.x));
+                }
             }
         }
     }
@@ -456,17 +472,30 @@ __device__ __forceinline__ void field_warp_fft_t(double2* x, int n_rt, int logn_
 }
 
 template <bool INVERSE>
-__device__ __forceinline__ void field_warp_fft(double2* x, int n, int logn, const double2* tw, int lane)
+__device__ __forceinline__ void field_warp_fft(double2* x, int n, int logn, const double2* tws, int lane)
 {
     switch (logn) {  // block-uniform
-    case 6: field_warp_fft_t<INVERSE, 6>(x, n, logn, tw, lane); break;
-    case 7: field_warp_fft_t<INVERSE, 7>(x, n, logn, tw, lane); break;
-    case 8: field_warp_fft_t<INVERSE, 8>(x, n, logn, tw, lane); break;
-    default: field_warp_fft_t<INVERSE, 0>(x, n, logn, tw, lane); break;
+    case 6: field_warp_fft_t<INVERSE, 6>(x, n, logn, tws, lane); break;
+    case 7: field_warp_fft_t<INVERSE, 7>(x, n, logn, tws, lane); break;
+    case 8: field_warp_fft_t<INVERSE, 8>(x, n, logn, tws, lane); break;
+    default: field_warp_fft_t<INVERSE, 0>(x, n, logn, tws, lane); break;
     }
 }
 
 __device__ __forceinline__ int field_brev(int i, int logn) { return logn ? (int)(__brev((unsigned)i) >> (32 - logn)) : 0; }
+
+// per-stage twiddle table of a dim from its forward twiddles tw[m] = exp(-2 pi i m / n)
+__device__ __forceinline__ void field_fill_tws(double2* tws, const double2* __restrict__ tw, int n)
+{
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        if (q == 0) {
+            tws[0] = make_double2(1.0, 0.0);
+        } else {
+            const int half = 1 << (31 - __clz(q)), k = q - half;  // q = half + k
+            tws[q] = tw[k * (n / (2 * half))];
+        }
+    }
+}
 
 __global__ void __launch_bounds__(SLB_FFT_THREADS) k_field_fft(const __grid_constant__ FieldFftArgs fa)
 {
@@ -479,13 +508,12 @@ __global__ void __launch_bounds__(SLB_FFT_THREADS) k_field_fft(const __grid_cons
     double2* tw2 = fsm2 + n1;
     double2* xa = fsm2 + n1 + n2 + (size_t)(2 * w) * nmax;  // two lines per warp
     double2* xb = xa + nmax;
-    for (int j = threadIdx.x; j < n1; j += blockDim.x) tw1[j] = fa.tw1[j];
-    if (fa.nsp == 2)
-        for (int j = threadIdx.x; j < n2; j += blockDim.x) tw2[j] = fa.tw2[j];
+    field_fill_tws(tw1, fa.tw1, n1);
+    if (fa.nsp == 2) field_fill_tws(tw2, fa.tw2, n2);
     __syncthreads();
     const int gw = blockIdx.x * nw + w, W = gridDim.x * nw;
     const long long ntot = (long long)n1 * n2;
-    // ---- phase 0 -------------------------------------------------------------------------------------------
+    // ---- phase 0: rho, forward transform of the x1 lines (spectrum index in bit-reversed position) -----------------
     for (int j = gw; j < n2; j += W) {
         const long long base = (long long)n1 * j;
         for (int a = lane; a < n1; a += 32) {
@@ -493,19 +521,19 @@ __global__ void __launch_bounds__(SLB_FFT_THREADS) k_field_fft(const __grid_cons
             for (int c = 0; c < fa.nchunk; ++c) s += fa.partial[(long long)c * ntot + base + a];
             s *= fa.scale;
             fa.rho[base + a] = s;
-            xa[field_brev(a, l1)] = make_double2(s, 0.0);
+            xa[a] = make_double2(s, 0.0);
         }
         field_warp_fft<false>(xa, n1, l1, tw1, lane);
         if (fa.nsp == 2) {
-            for (int k = lane; k < n1; k += 32) fa.wa[base + k] = xa[k];
+            for (int p = lane; p < n1; p += 32) fa.wa[base + p] = xa[p];
         } else {
             // one space dim: multiplier and inverse transform right here
             const double mean = fa.subtract_mean ? xa[0].x / (double)n1 : 0.0;
             __syncwarp();
-            for (int k = lane; k < n1; k += 32) {
-                const double2 v = xa[k];
-                const double mm = fa.mult[0][k];
-                xb[field_brev(k, l1)] = make_double2(-v.y * mm, v.x * mm);
+            for (int p = lane; p < n1; p += 32) {
+                const double2 v = xa[p];
+                const double mm = fa.mult[0][field_brev(p, l1)];
+                xb[p] = make_double2(-v.y * mm, v.x * mm);
             }
             field_warp_fft<true>(xb, n1, l1, tw1, lane);
             const double sc = 1.0 / (double)n1;
@@ -516,36 +544,37 @@ __global__ void __launch_bounds__(SLB_FFT_THREADS) k_field_fft(const __grid_cons
         }
     }
     if (fa.nsp != 2) return;
-    cg::this_cluster().sync();
-    // ---- phase 1: columns ------------------------------------------------------------------------------------
-    for (int k1 = gw; k1 < n1; k1 += W) {
-        for (int j = lane; j < n2; j += 32) xa[field_brev(j, l2)] = fa.wa[k1 + (long long)n1 * j];
+    cg::this_grid().sync();
+    // ---- phase 1: columns (position p1 holds wavenumber k1 = brev(p1)) -----------------------------------------------
+    for (int p1 = gw; p1 < n1; p1 += W) {
+        const int k1 = field_brev(p1, l1);
+        for (int j = lane; j < n2; j += 32) xa[j] = fa.wa[p1 + (long long)n1 * j];
         field_warp_fft<false>(xa, n2, l2, tw2, lane);
-        if (k1 == 0 && lane == 0) *fa.mean = fa.subtract_mean ? xa[0].x / (double)ntot : 0.0;
+        if (p1 == 0 && lane == 0) *fa.mean = fa.subtract_mean ? xa[0].x / (double)ntot : 0.0;
         const double sc = 1.0 / (double)n2;
         for (int x = 0; x < 2; ++x) {
             __syncwarp();
-            for (int k2 = lane; k2 < n2; k2 += 32) {
-                const double2 v = xa[k2];
-                const double mm = fa.mult[x][k1 + (long long)n1 * k2];
-                xb[field_brev(k2, l2)] = make_double2(-v.y * mm, v.x * mm);
+            for (int p2 = lane; p2 < n2; p2 += 32) {
+                const double2 v = xa[p2];
+                const double mm = fa.mult[x][k1 + (long long)n1 * field_brev(p2, l2)];
+                xb[p2] = make_double2(-v.y * mm, v.x * mm);
             }
             field_warp_fft<true>(xb, n2, l2, tw2, lane);
             for (int j = lane; j < n2; j += 32) {
                 const double2 v = xb[j];
-                fa.wc[x][k1 + (long long)n1 * j] = make_double2(v.x * sc, v.y * sc);
+                fa.wc[x][p1 + (long long)n1 * j] = make_double2(v.x * sc, v.y * sc);
             }
         }
     }
-    cg::this_cluster().sync();
-    // ---- phase 2: inverse x1 lines of both components; mean removal -------------------------------------------
+    cg::this_grid().sync();
+    // ---- phase 2: inverse x1 lines of both components (input already in bit-reversed order); mean removal ------------
     const double mean = *fa.mean;
     const double sc1 = 1.0 / (double)n1;
     for (int t = gw; t < 2 * n2; t += W) {
         const int x = t / n2, j = t - x * n2;
         const long long base = (long long)n1 * j;
         __syncwarp();
-        for (int k = lane; k < n1; k += 32) xa[field_brev(k, l1)] = fa.wc[x][base + k];
+        for (int p = lane; p < n1; p += 32) xa[p] = fa.wc[x][base + p];
         field_warp_fft<true>(xa, n1, l1, tw1, lane);
         for (int a = lane; a < n1; a += 32) {
             fa.E[x][base + a] = xa[a].x * sc1;

@@ -356,6 +356,41 @@ class HaloShardedAdvectionData:
         self.ctx = None
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# pure layout conventions (numpy) -- pinned by world_size-2 gloo tests on CPU (tests/test_sharded_cpu.py) and used
+# by the GPU tests to check what the kernels pushed
+# ---------------------------------------------------------------------------------------------------------------
+def slab_with_halos(global_arr, rank, nranks, H):
+    """rank's [low halo | slab | high halo] view of a periodic global array, sharded along its LAST dim"""
+    n = global_arr.shape[-1]
+    c = n // nranks
+    idx = [(rank * c - H + j) % n for j in range(c + 2 * H)]
+    return np.asfortranarray(global_arr[..., idx])
+
+
+def halo_destinations(rank, nranks, c, H):
+    """where a rank's boundary planes go: [(source rows, destination rank, destination rows)] in haloed row numbers.
+    Rows [H, 2H) (the slab's first H planes) fill the lower neighbour's HIGH halo, rows [c, c + H) (its last H
+    planes) the upper neighbour's LOW halo -- what slb_sweep_pair_halo's push_lo / push_hi stores implement."""
+    lo, hi = (rank - 1) % nranks, (rank + 1) % nranks
+    return [((H, 2 * H), lo, (H + c, 2 * H + c)), ((c, c + H), hi, (0, H))]
+
+
+def exchange_halos_reference(local_haloed, rank, nranks, H, dist, torch, group=None):
+    """host-side (CPU tensors, any backend) restatement of the halo exchange: fills the halo planes of
+    `local_haloed` ([..., c + 2H], slab already in place) from the neighbours' boundary planes"""
+    c = local_haloed.shape[-1] - 2 * H
+    mine = [np.ascontiguousarray(local_haloed[..., a:b]) for (a, b), _, _ in halo_destinations(rank, nranks, c, H)]
+    payload = torch.from_numpy(np.stack(mine))
+    allp = [torch.empty_like(payload) for _ in range(nranks)]
+    dist.all_gather(allp, payload, group=group)
+    for src in range(nranks):
+        for k, (_, dst, (a, b)) in enumerate(halo_destinations(src, nranks, c, H)):
+            if dst == rank:
+                local_haloed[..., a:b] = allp[src][k].numpy()
+    return local_haloed
+
+
 def torch_allgather_bytes(dist, group=None):
     """`allgather_bytes` over an initialised torch.distributed group (any backend: the handles are a few hundred
     bytes, exchanged once).  A Julia host passes MPI.Allgather instead."""
