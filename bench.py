@@ -303,9 +303,28 @@ def run_configs(S, ctx, args, peak, only=None):
             ctx.record(e1)
             ms = _lib.Context.elapsed_ms(e0, e1) / nsteps
             nl = (ctx.launch_count() - l0) / nsteps
+            extra = {}
+            if name.startswith("C1") and hasattr(S, "StepGraph"):
+                # launch-bound: whole steps recorded once and replayed as one CUDA-graph launch per two steps, with the
+                # electric energy of every step still reduced on the device (the example's loop reads it per step)
+                sg = S.StepGraph(g, nsteps=2)
+                for _ in range(3):
+                    sg.launch()
+                ctx.sync()
+                ctx.record(e0)
+                for _ in range(nsteps // 2):
+                    sg.launch()
+                ctx.record(e1)
+                extra["ms_per_step_graph"] = _lib.Context.elapsed_ms(e0, e1) / (nsteps // 2 * 2)
+                t0 = time.perf_counter()
+                for _ in range(nsteps // 2):
+                    sg.launch()
+                    sg.energies()
+                extra["ms_per_step_graph_ee_readback_wall"] = (time.perf_counter() - t0) * 1e3 / (nsteps // 2 * 2)
+                sg.close()
             g.close()
             out[name] = {"ms_per_step": ms, "Gcell_s": cells / ms / 1e6, "launches_per_step": nl,
-                         "hbm_frac_per_sweep_bytes": cells * BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peak, "parity": par, "note": note}
+                         "hbm_frac_per_sweep_bytes": cells * BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peak, "parity": par, "note": note, **extra}
         except Exception as exc:  # a side measurement must not take the headline down
             out[name] = {"error": f"{type(exc).__name__}: {exc}"}
     return out

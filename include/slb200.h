@@ -72,6 +72,19 @@ int64_t slb_launch_count(const slb_ctx* ctx);
 int slb_timer_start(slb_ctx* ctx);
 int slb_timer_stop(slb_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */
 
+/* ---- whole time steps as one launch (CUDA graph) ----------------------------------------------------------
+ * Small grids (the 1D1V example, 128 x 256: 256 KB, examples/vlasov-poisson-1d1v.jl:60-64) are bound by launch
+ * latency, not by HBM.  Between slb_capture_begin and slb_capture_end the calls of this library on the context's
+ * stream are RECORDED instead of executed; slb_graph_launch replays them as one launch.  The recorded sequence must
+ * consist of kernel launches on device-resident tables (no host alpha tables, no allocation, no call that returns a
+ * host scalar), and it must leave every grid's front/back roles as it found them (an even number of sweeps per grid),
+ * so that a replay continues where the last one ended.  slb_launch_count keeps counting the replayed kernels. */
+typedef struct slb_graph slb_graph;
+int slb_capture_begin(slb_ctx* ctx);
+int slb_capture_end(slb_ctx* ctx, slb_graph** out);
+int slb_graph_launch(slb_graph* g);
+void slb_graph_destroy(slb_graph* g);
+
 /* extra CUDA events on the context's stream (per-kernel timing inside bench.py) */
 int slb_event_create(slb_ctx* ctx, void** ev_out);
 int slb_event_record(slb_ctx* ctx, void* ev);
@@ -303,6 +316,8 @@ int slb_poisson_solve_partial(slb_poisson* p, const double* partial_dev, int npa
 
 /* sum(x .^ 2) for compute_ee (src/util_poisson.jl:156-162); deterministic; synchronises */
 int slb_reduce_sumsq(slb_ctx* ctx, const double* dev, int64_t n, double* host_out);
+/* same without synchronising: out_dev[0] = scale * sum(x .^ 2), a device location (usable inside a capture) */
+int slb_reduce_sumsq_async(slb_ctx* ctx, const double* dev, int64_t n, double scale, double* out_dev);
 /* sum(x) (deterministic; synchronises) */
 int slb_reduce_sum(slb_ctx* ctx, const double* dev, int64_t n, double* host_out);
 /* compute_ke (src/util_poisson.jl:41-53): (dsp*dv) * sum(v_square .* sum_sp f); v_square_dev

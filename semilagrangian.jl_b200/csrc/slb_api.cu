@@ -522,6 +522,17 @@ static void launch_strided(slb_ctx* c, const double* in, double* out, const View
                            const slb_interp* it, const OutMap& om, bool exact, double* linesum)
 {
     long long nlines = v.inner * v.outer;
+    if (nlines < 32768 && v.n <= 256 && v.n >= 32 && om.kc >= v.n && om.npeer == 0 && env_ll("SLB_SWEEP_CHUNK", 1) != 0) {
+        // few lines: cut them into chunks of 16 outputs so that the sweep fills more than a handful of warps
+        constexpr int CH = 16;
+        dim3 blk(32, (unsigned)((v.n + CH - 1) / CH));
+        unsigned nb = (unsigned)((nlines + 31) / 32);
+        if (exact)
+            k_sweep_strided_chunk<P1, true, CH><<<nb, blk, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, linesum);
+        else
+            k_sweep_strided_chunk<P1, false, CH><<<nb, blk, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, linesum);
+        return;
+    }
     unsigned blocks = (unsigned)((nlines + 127) / 128);
     if (exact)
         k_sweep_strided<P1, true><<<blocks, 128, 0, c->stream>>>(in, out, v.inner, v.n, nlines, am, it->tab, it->nc, om, linesum);
@@ -1250,6 +1261,79 @@ static int reduce_to_host(slb_ctx* c, const double* dev, int64_t n, int mode, do
 }
 
 extern "C" int slb_reduce_sumsq(slb_ctx* c, const double* dev, int64_t n, double* host_out) { return reduce_to_host(c, dev, n, 1, host_out); }
+
+extern "C" int slb_reduce_sumsq_async(slb_ctx* c, const double* dev, int64_t n, double scale, double* out_dev)
+{
+    if (!c || !dev || !out_dev || n < 1) return fail(SLB_E_ARG, "slb_reduce_sumsq_async: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return reduce_to_dev(c, dev, n, 1, scale, out_dev);
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA graphs: whole time steps of small grids as one launch
+// ------------------------------------------------------------------------------------------
+struct slb_graph {
+    slb_ctx* ctx;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    int64_t launches;  // kernels recorded in the graph (added to the context's count at every replay)
+};
+
+extern "C" int slb_capture_begin(slb_ctx* c)
+{
+    if (!c) return fail(SLB_E_ARG, "slb_capture_begin: ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->capture_launches0 = c->launches;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    return SLB_OK;
+}
+
+extern "C" int slb_capture_end(slb_ctx* c, slb_graph** out)
+{
+    if (!c || !out) return fail(SLB_E_ARG, "slb_capture_end: NULL argument");
+    *out = nullptr;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        return fail(SLB_E_CUDA, "slb_capture_end: the captured sequence is not replayable (%s): it must consist of kernel launches on "
+                                "device-resident tables only -- no allocation, host table or synchronising call", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t x = nullptr;
+    e = cudaGraphInstantiate(&x, g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        cudaGetLastError();
+        return fail(SLB_E_CUDA, "slb_capture_end: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    slb_graph* gr = new slb_graph();
+    gr->ctx = c;
+    gr->graph = g;
+    gr->exec = x;
+    gr->launches = c->launches - c->capture_launches0;
+    c->launches = c->capture_launches0;  // nothing ran yet
+    *out = gr;
+    return SLB_OK;
+}
+
+extern "C" int slb_graph_launch(slb_graph* g)
+{
+    if (!g) return fail(SLB_E_ARG, "slb_graph_launch: graph is NULL");
+    CUDA_TRY(cudaSetDevice(g->ctx->device));
+    CUDA_TRY(cudaGraphLaunch(g->exec, g->ctx->stream));
+    g->ctx->launches += g->launches;
+    return SLB_OK;
+}
+
+extern "C" void slb_graph_destroy(slb_graph* g)
+{
+    if (!g) return;
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaGraphExecDestroy(g->exec);
+    cudaGraphDestroy(g->graph);
+    delete g;
+}
 extern "C" int slb_reduce_sum(slb_ctx* c, const double* dev, int64_t n, double* host_out) { return reduce_to_host(c, dev, n, 0, host_out); }
 
 extern "C" int slb_subtract_mean(slb_ctx* c, double* dev, int64_t n)

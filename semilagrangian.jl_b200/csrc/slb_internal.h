@@ -17,6 +17,7 @@ struct slb_ctx {
     void* scratch;        // growable device scratch (alpha tables, partial sums)
     size_t scratch_bytes;
     int sm_count;
+    int64_t capture_launches0;  // launch counter when a stream capture began
     int* err_word;        // device word: bit 0 = a shift exceeded the halo of a sharded pass (slb_halo_error)
 };
 

@@ -239,6 +239,76 @@ k_sweep_strided(const double* __restrict__ in, double* __restrict__ out, long lo
 }
 
 // ------------------------------------------------------------------------------------------
+// K1 strided, FEW lines (small 2-D grids: the 1D1V example has 128 lines of 256 points): one thread per line leaves
+// a B200 with a single block of 128 threads marching 256 rows one after the other (37 us per sweep, 70 % of a
+// 128 x 256 Vlasov-Poisson step).  A Lagrange / Hermite stencil has no recurrence, so the line is cut into chunks of
+// CH outputs: block = 32 neighbouring lines x NCH chunks, every thread loads its CH + order inputs at once and
+// evaluates CH outputs from registers.  Same operation order per output as k_sweep_strided (bit-identical results);
+// the line sums are reduced over the chunks through shared memory in a fixed order.
+// ------------------------------------------------------------------------------------------
+template <int P1, bool EXACT, int CH>
+__global__ void __launch_bounds__(512)
+k_sweep_strided_chunk(const double* __restrict__ in, double* __restrict__ out, long long inner, int n, long long nlines,
+                      AlphaMap am, CoefTab ct, int nc, double* __restrict__ linesum)
+{
+    __shared__ double lsb[16][33];
+    const int lane = threadIdx.x, ch = threadIdx.y, nch = blockDim.y;  // nch <= 16
+    const long long gid = (long long)blockIdx.x * 32 + lane;
+    const bool active = gid < nlines;
+    const long long gc = active ? gid : nlines - 1;
+    const long long b = gc / inner, a = gc - b * inner;
+    const double alpha = am.scale * __ldg(am.tab + slb_alpha_off(am, (unsigned)a, (unsigned)b));
+    double t;
+    int s0;
+    slb_split(alpha, n, (P1 - 1) / 2, t, s0);
+    double w[P1];
+#pragma unroll
+    for (int j = 0; j < P1; ++j) w[j] = ct.c[j * SLB_NCMAX + nc - 1];
+    for (int k = nc - 2; k >= 0; --k) {
+#pragma unroll
+        for (int j = 0; j < P1; ++j) w[j] = fma(t, w[j], ct.c[j * SLB_NCMAX + k]);
+    }
+    const int i0 = ch * CH;                 // first output of this chunk
+    const int cnt = n - i0 < CH ? n - i0 : CH;
+    const double* pin = in + (b * n) * inner + a;
+    double x[CH + P1 - 1];
+    int kk = (s0 + i0) % n;
+#pragma unroll
+    for (int j = 0; j < CH + P1 - 1; ++j) {
+        x[j] = (j < cnt + P1 - 1) ? __ldg(pin + (long long)kk * inner) : 0.0;
+        kk = kk + 1 == n ? 0 : kk + 1;
+    }
+    double* po = out + (b * n) * inner + a + (long long)i0 * inner;
+    double lsum = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        double acc;
+        if (EXACT) {
+            acc = __dmul_rn(x[j], w[0]);
+#pragma unroll
+            for (int q = 1; q < P1; ++q) acc = __dadd_rn(acc, __dmul_rn(x[j + q], w[q]));
+        } else {
+            acc = x[j] * w[0];
+#pragma unroll
+            for (int q = 1; q < P1; ++q) acc = fma(x[j + q], w[q], acc);
+        }
+        if (j < cnt) {
+            lsum += acc;
+            if (active) po[(long long)j * inner] = acc;
+        }
+    }
+    if (linesum) {
+        lsb[ch][lane] = lsum;
+        __syncthreads();
+        if (ch == 0 && active) {
+            double sacc = lsb[0][lane];
+            for (int q = 1; q < nch; ++q) sacc += lsb[q][lane];
+            linesum[gid] = sacc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K1 contiguous: warp per line segment
 // ------------------------------------------------------------------------------------------
 template <int R>

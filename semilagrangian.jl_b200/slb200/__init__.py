@@ -13,7 +13,8 @@ from .interp import (AbstractInterpolation, Lagrange, BSplineLU, BSplineFFT, Her
 from .splitting import (nosplit, standardsplit, strangsplit, magicsplit, triplejumpsplit, order6split,
                         hamsplit_3_11)
 from .advection import (Advection, AdvectionData, AbstractExtDataAdv, StateAdv, advection, getdata, sizeall,
-                        sweep, sweep_pair, modone, invperm)
+                        sweep, sweep_pair, modone, invperm, StepGraph)
+from .sharded import HaloShardedAdvectionData, HaloUnsupported, local_group
 from .poisson import (PoissonVar, getpoissonvar, compute_ee, compute_ke, getenergy, getenergyall, dotprod,
                       StdPoisson, StdPoisson2d)
 from .unsplit2d import (NoTimeAlg, ABTimeAlg_ip, ABTimeAlg_new, ABTimeAlg_init, DeviceField, interpolate_points,

@@ -87,6 +87,11 @@ SIGNATURES = [
     ("slb_vp_field_solve", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, c_void_pp]),
     ("slb_poisson_solve_raw", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_void_pp]),
     ("slb_reduce_sumsq", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
+    ("slb_reduce_sumsq_async", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
+    ("slb_capture_begin", C.c_int, [C.c_void_p]),
+    ("slb_capture_end", C.c_int, [C.c_void_p, c_void_pp]),
+    ("slb_graph_launch", C.c_int, [C.c_void_p]),
+    ("slb_graph_destroy", None, [C.c_void_p]),
     ("slb_reduce_sum", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
     ("slb_kinetic_energy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, c_double_p]),
     ("slb_interp2d_points", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

@@ -431,3 +431,83 @@ def advection(advd):
                 return advd.nextstate()
     _sweep_now(advd, *cur)
     return advd.nextstate()
+
+
+class StepGraph:
+    """`nsteps` whole time steps of `advd` recorded ONCE (slb_capture_begin / _end) and replayed with one launch
+    each (CUDA graph): for grids so small that a step is bound by launch latency, not by HBM -- the 1D1V example
+    (128 x 256, examples/vlasov-poisson-1d1v.jl:60-64) issues 7 kernels for 256 KB of data.  The loop semantics stay
+    the reference's: `launch()` advances `nsteps` steps, `energies()` returns the electric energy after each of them
+    (compute_ee, src/util_poisson.jl:156-162, reduced on the device inside the graph).
+
+    The recorded steps must leave the grid's front/back roles as they found them: use an even `nsteps` when a step
+    has an odd number of passes.  Displacement providers must keep their tables on the device (the Poisson, rotation
+    and translation providers do)."""
+
+    def __init__(self, advd, nsteps=2):
+        L = _lib.lib()
+        adv, ctx, pv = advd.adv, advd.ctx, advd.parext
+        if advd.state_gen != 1:
+            raise ValueError("StepGraph records whole time steps: build it between two steps")
+        advd.flush()
+        self.advd, self.nsteps = advd, int(nsteps)
+        # everything a step would allocate or upload lazily happens now, not inside the recording
+        for d, it in enumerate(adv.t_interp):
+            it.handle(ctx, adv.sizeall[d])
+            advd.points_dev(d)
+        if advd._linesum is None and adv.N > 1:
+            advd._linesum = ctx.malloc(int(np.prod(adv.sizeall)) // min(adv.sizeall[1:]) * 8)
+        self.E = list(getattr(pv, "E_dev", []))
+        if hasattr(pv, "field_solve"):
+            pv.field_solve(advd)  # sizes the scratch; the field of the current f (every step recomputes it anyway)
+        self.nE = len(self.E)
+        self.ee_dev = ctx.malloc(max(1, self.nsteps * max(1, self.nE)) * 8)
+        dx = 1.0
+        for m in adv.t_mesh[: getattr(pv, "Nsp", 0)]:
+            dx *= m.step
+        ctx.sync()
+        front0, t0, nf0 = L.slb_grid_front(advd.grid), advd.time_cur, advd.n_fused
+        _lib.check(L.slb_capture_begin(ctx.h))
+        h = C.c_void_p()
+        try:
+            for s in range(self.nsteps):
+                while advection(advd):
+                    pass
+                for d, e in enumerate(self.E):
+                    _lib.check(L.slb_reduce_sumsq_async(ctx.h, e, pv.nsp_tot, dx, C.c_void_p(self.ee_dev.value + 8 * (s * self.nE + d))))
+        finally:
+            rc = L.slb_capture_end(ctx.h, C.byref(h))
+        _lib.check(rc)
+        self.h = h
+        self.fused_per_launch = advd.n_fused - nf0
+        advd.time_cur, advd.n_fused = t0, nf0  # nothing has run yet
+        if L.slb_grid_front(advd.grid) != front0:
+            L.slb_graph_destroy(self.h)
+            self.h = None
+            raise ValueError(f"{self.nsteps} step(s) swap the grid's buffers an odd number of times: record an even number of steps")
+
+    def launch(self):
+        """advance nsteps time steps (asynchronous)"""
+        _lib.check(_lib.lib().slb_graph_launch(self.h))
+        for _ in range(self.nsteps):  # the same additions as nextstate!, src/advection.jl:364
+            self.advd.time_cur += self.advd.adv.dt_base
+        self.advd.n_fused += self.fused_per_launch
+
+    def energies(self):
+        """electric energy after each of the last launch's steps (synchronises)"""
+        if not self.nE:
+            return []
+        v = self.advd.ctx.to_host(self.ee_dev, self.nsteps * self.nE).reshape(self.nsteps, self.nE)
+        return [float(sum(row)) for row in v]   # dx * sum_d sum(E_d .^ 2), components added left to right
+
+    def close(self):
+        if self.h:
+            _lib.lib().slb_graph_destroy(self.h)
+            self.h = None
+            self.advd.ctx.free(self.ee_dev)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

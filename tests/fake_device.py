@@ -300,6 +300,25 @@ class FakeLib:
         _set(ms, max(1e-6, 1e3 * (self.mem[("ev", _addr(e1))] - self.mem[("ev", _addr(e0))])))
         return 0
 
+    # CUDA-graph entry points: the double executes eagerly, so a "recording" has already run once and a replay is
+    # a no-op -- enough to dry-run bench.py's control flow, not to check graph semantics (GPU test does that)
+    def slb_capture_begin(self, ctx):
+        return 0
+
+    def slb_capture_end(self, ctx, out):
+        _set(out, self._new_id())
+        return 0
+
+    def slb_graph_launch(self, g):
+        return 0
+
+    def slb_graph_destroy(self, g):
+        return None
+
+    def slb_reduce_sumsq_async(self, ctx, p, n, scale, out):
+        _arr(out, 1)[0] = scale * float(np.sum(_arr(p, n) ** 2))
+        return 0
+
     def slb_host_alloc(self, nbytes, out):
         _set(out, self._alloc(nbytes))
         return 0

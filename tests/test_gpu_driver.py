@@ -289,3 +289,30 @@ def test_full_size_properties_128_4():
         g.close()
         g = DeviceGrid(f)
     g.close()
+
+
+def test_step_graph_replays_whole_steps_bitwise():
+    """CUDA-graph replay of whole Strang steps (C1 shape, 1D1V 128 x 256 Lagrange 9): the same kernels in the same
+    order, so the data and the electric-energy history equal the step-by-step driver bit for bit."""
+    import slb200 as S
+
+    _, a, _ = _landau_1d1v(S, 128, 256, lambda n: S.Lagrange(9))
+    _, b, _ = _landau_1d1v(S, 128, 256, lambda n: S.Lagrange(9))
+    el_a = _run(S, a, 6, S.advection)
+    g = S.StepGraph(b, nsteps=2)
+    el_b = []
+    for _ in range(3):
+        g.launch()
+        el_b += g.energies()
+    assert b.time_cur == a.time_cur
+    assert np.array_equal(np.array(el_b), el_a)
+    assert np.array_equal(a.getdata(), b.getdata())
+    # the driver can continue step by step after graph replays
+    assert S.advection(b) is True
+    with pytest.raises(ValueError):   # mid-step
+        S.StepGraph(b, nsteps=2)
+    while S.advection(b):
+        pass
+    with pytest.raises(ValueError):   # three passes per step: an odd number of steps leaves the buffers swapped
+        S.StepGraph(b, nsteps=1)
+    g.close()
