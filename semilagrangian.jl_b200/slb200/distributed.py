@@ -15,7 +15,11 @@ A Strang step  v1 v2 | x1 x2 | v1 v2  needs two exchanges.  Neither needs a pack
   A -> B : the x2 sweep writes its output block-major along x2 (SLB_RESHARD_OUT_BLOCKED), so
            each destination's block is contiguous; the received blocks concatenate along v2
            into the standard layout-B slab.
-rho slabs are all-gathered (n1*n2/P doubles per rank) and the Poisson solve is replicated.
+rho slabs are all-gathered (n1*n2/P doubles per rank) and the Poisson solve is replicated.  With
+exchange = "p2p" nothing in the data path goes through torch.distributed / NCCL: the re-shards are peer stores
+inside the passes, the barriers and the rho all-gather are the library's mailbox collectives (slb_comm_*).
+Lagrange / Hermite runs do not need this driver any more: slb200/sharded.py keeps ONE slab layout and exchanges
+halo planes only.  This one remains for the B-spline kinds, whose pre-solve couples whole lines.
 
 The pure index bookkeeping (block-major packing, slab ranges, split sizes) is kept free of CUDA
 so that world_size-2 gloo tests on CPU cover it (tests/test_distributed_cpu.py).
@@ -187,11 +191,24 @@ class ShardedAdvectionData:
                     row.append(q.value)
                     self._opened.append(q)
                 self.peer.append(row)
-            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+            # barrier and rho all-gather of the data path: the library's own mailbox collectives (slb_comm_*, peer
+            # stores + flags on the driver's stream) -- torch.distributed only carried the handles above
+            hc = C.c_void_p()
+            _lib.check(L.slb_comm_create(self.ctx.h, self.rank, self.P, n1 * n2 // self.P, C.byref(hc)))
+            self.comm = hc
+            hb = C.create_string_buffer(128)
+            _lib.check(L.slb_comm_export(self.comm, hb))
+            allm = [None] * self.P
+            dist.all_gather_object(allm, hb.raw, group=group)
+            blob = b"".join(allm)
+            _lib.check(L.slb_comm_connect(self.comm, C.create_string_buffer(blob, len(blob))))
         else:
             self.nbuf = 2
             self.bufs = [torch.empty(self.nloc, dtype=torch.float64, device=self.device) for _ in range(2)]
             self.ptr = [b.data_ptr() for b in self.bufs]
+        if self.exchange != "p2p":
+            self.comm = None
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.cur = 0  # index of the buffer holding f
         self.layout = LAYOUT_B
         self.since_barrier = 99  # sweeps since the last cross-rank barrier
@@ -249,7 +266,10 @@ class ShardedAdvectionData:
 
     def _barrier(self):
         """stream-ordered cross-rank barrier (called under the driver's stream)"""
-        self.dist.all_reduce(self._flag, group=self.group)
+        if self.comm is not None:
+            _lib.check(_lib.lib().slb_comm_barrier(self.comm))
+        else:
+            self.dist.all_reduce(self._flag, group=self.group)
         self.since_barrier = 0
         self.n_barriers += 1
 
@@ -294,11 +314,19 @@ class ShardedAdvectionData:
             _lib.check(L.slb_charge_density_from(self.ctx.h, C.c_void_p(self.linesum.data_ptr()), n1 * n2 // self.P, nv_rest, dv, rl, 0))
         else:
             _lib.check(L.slb_charge_density_raw(self._grid(LAYOUT_B), 2, dv, rl))
+        arr = (C.c_void_p * 2)(*[e.data_ptr() for e in self.E])
+        if self.comm is not None and self.P > 1:
+            # the slabs of rho land side by side in this rank's mailbox: the gathered array IS rho (x2 is the slowest
+            # space dim); the solve reads it from there and leaves the mean-free rho in self.rho
+            slots = C.c_void_p()
+            _lib.check(L.slb_comm_allgather(self.comm, rl, n1 * n2 // self.P, C.byref(slots)))
+            _lib.check(L.slb_poisson_solve_partial(self.plan, slots, 1, 1.0, 1, C.c_void_p(self.rho.data_ptr()), arr))
+            self.has_field = True
+            return
         if self.P > 1:
             self.dist.all_gather_into_tensor(self.rho, self.rho_local, group=self.group)
         else:
             self.rho.copy_(self.rho_local)
-        arr = (C.c_void_p * 2)(*[e.data_ptr() for e in self.E])
         _lib.check(L.slb_poisson_solve_raw(self.plan, C.c_void_p(self.rho.data_ptr()), 1, arr))  # mean removal + all DFT passes: one kernel
         self.has_field = True
 
@@ -540,6 +568,9 @@ class ShardedAdvectionData:
             L.slb_poisson_destroy(self.plan)
             self.plan = None
         if self.exchange == "p2p" and self._raw:
+            if self.comm is not None:
+                L.slb_comm_destroy(self.comm)
+                self.comm = None
             if self.P > 1:
                 self.dist.barrier(group=self.group)
             for q in self._opened:
