@@ -35,7 +35,8 @@ def run_distributed(args, B):
     lo, hi = slab(n, world, rank)
     a, b, c, d = vecs
     mode = os.environ.get("SLB_SHARD", "halo")
-    max_shift = float(os.environ.get("SLB_MAX_SHIFT", "1.0"))
+    max_shift = os.environ.get("SLB_MAX_SHIFT", "auto")   # cells; "auto": from the initial field, with a 1.5x margin
+    max_shift = max_shift if max_shift == "auto" else float(max_shift)
     sh = None
     if mode == "halo":
         try:
@@ -145,7 +146,8 @@ def run_distributed(args, B):
             plane = n**3 * 8
             out_bytes = 2 * 2 * H * plane     # two pushing passes per step, H planes to either neighbour
             hbm_bytes = (2 * (cs + 2 * H) + cs) * plane + 3 * cs * plane + cs * plane  # reads of 2 v passes + x pass, 3 writes, 1 rho pass
-            par = f"v2 slabs of {cs} planes + {H} halo planes per side over {world} GPUs, no transposes: halo planes pushed as peer stores inside the passes"
+            par = (f"v2 slabs of {cs} planes + {H} halo planes per side (velocity shifts below {sh.max_shift:.2f} cells) over {world} GPUs, "
+                   "no transposes: halo planes pushed as peer stores inside the passes")
             link_note = "halo planes ride inside the x1x2 pass and the step's last v1v2 pass as NVLink peer stores; rho: one 131 KB mailbox all-gather per field solve"
             kern = "whole step per rank: 3 fused passes (v passes read c + 2H rows) + 1 rho pass"
         else:

@@ -38,7 +38,9 @@ mutable struct B200Context
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:slb_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, r))
         c = new(r[])
-        finalizer(x -> ccall((:slb_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), c)
+        # finalizers run in no particular order: objects that live on this context destroy their device parts only
+        # while h is still set (see B200AdvectionData), and the context clears h when it goes
+        finalizer(x -> (ccall((:slb_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), c)
         return c
     end
 end
@@ -95,7 +97,12 @@ mutable struct B200AdvectionData{T,N}
         interps = [interp_handle(ctx, adv.t_interp[d], ext[d]) for d = 1:N]
         pts = [todevice(ctx, collect(points(adv.t_mesh[d]))) for d = 1:N]
         self = new{T,N}(adv, ctx, 1, time_init, g[], interps, pts, parext)
-        finalizer(x -> ccall((:slb_grid_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.grid), self)
+        finalizer(self) do x          # grid, interpolation handles and mesh nodes go together, before their context
+            x.ctx.h == C_NULL && return
+            ccall((:slb_grid_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.grid)
+            foreach(h -> ccall((:slb_interp_destroy, LIB), Cvoid, (Ptr{Cvoid},), h), x.interps)
+            foreach(p -> ccall((:slb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, p), x.points_dev)
+        end
         return self
     end
 end
@@ -175,6 +182,10 @@ function advection!(self::B200AdvectionData{T,N}) where {T,N}     # src/advectio
     tab, len, strides, scale, ondev = alphatable(self.parext, self)
     cur = (dim = st.perm[1] - 1, tab = tab, len = len, strides = strides, scale = scale, ondev = ondev)
     prev = pop!(PENDING, self, nothing)
+    if prev !== nothing && prev.ondev != cur.ondev   # one table on the host, one on the device: not one call
+        sweep_now(self, prev); sweep_now(self, cur)
+        return nextstate!(self)
+    end
     if prev !== nothing
         # two stages in one pass over HBM; bit-identical to two slb_sweep calls
         rc = ccall((:slb_sweep_pair, LIB), Cint,

@@ -16,6 +16,16 @@ f[x1,x2,v1,v2] is split ONCE, in slabs of c = n4/P points along v2, and stays th
                  rank order inside the one-kernel Poisson solve, which is replicated.  That all-gather is the
                  step's only synchronisation: it also orders the halo pushes against the passes that read them.
 
+Why the all-gather suffices as the only synchronisation (passes of a step: V1 reads halos, X pushes, V2 reads halos
+and pushes; buffers rotate B0 -> B1 -> B2 -> B0, pass k reads B[k % 3] and writes / pushes into B[(k + 1) % 3]):
+  * read-after-write: the halos V1(s+1) reads were pushed by the neighbours' V2(s); the all-gather before V1(s+1)
+    completes only when every rank's contribution has arrived, and a rank sends it after its own V2(s) (stream order).
+    Same for V2(s) and the neighbours' X(s), with the mid-step all-gather.
+  * write-after-read: X(s) pushes into the neighbours' B2, last read by their V2(s-1): finished before they contributed
+    to the all-gather that precedes V1(s).  V2(s) pushes into the neighbours' B0, last read by their V1(s): finished
+    before they contributed to the mid-step all-gather that precedes V2(s).  With two buffers the second case would race.
+  * the mailbox slots alternate between two sets: a rank can be one all-gather ahead of a peer, never two.
+
 H = order/2 + 1 + (ceil(max_shift) - 1): velocity shifts alpha = dt/dv E with |alpha| < max_shift cells.  A shift
 outside the halo raises on the next compute_ee()/getdata_local().  Per exchange a rank sends 2 H planes instead
 of (P-1)/P of its slab (the transposing driver, slb200/distributed.py), and the sends overlap the pass.
@@ -48,12 +58,30 @@ def halo_width(order, max_shift):
     return order // 2 + 1 + max(0, int(math.ceil(max_shift)) - 1)
 
 
+def estimate_max_shift(adv, rho, margin=1.5):
+    """Largest velocity shift |dt/dv E| (in cells) the first steps will see, from the initial charge density
+    (host-side numpy restatement of compute_elfield!, src/poisson.jl:139-144), times a safety margin: sizes the
+    halo before any device buffer exists.  The passes still check every shift against the halo at run time."""
+    from .poisson import _get_fctv_k_imag
+
+    rho = np.asarray(rho, dtype=np.float64)
+    rho = rho - rho.mean()
+    spec = np.fft.fft2(rho)
+    # time coefficients of the velocity stages only (Strang: dt/2 for v, dt for x)
+    dtmax = max(abs(adv.getcur_t(k)) for k in range(1, adv.nbstates + 1) if adv.getst(k).perm[0] > 2)
+    amax = 0.0
+    for x, m in enumerate(_get_fctv_k_imag(adv)):
+        e = np.real(np.fft.ifft2(1j * m * spec))
+        amax = max(amax, dtmax / adv.t_mesh[2 + x].step * float(np.max(np.abs(e))))
+    return max(1.0, margin * amax)
+
+
 class HaloShardedAdvectionData:
     """Sharded counterpart of AdvectionData + PoissonVar for the 4 const-shift states of
     examples/vlasov-poisson-2d2v.jl (v1, v2, x1, x2).  `data_local`: this rank's slab
     f[:, :, :, rank*c : (rank+1)*c] (numpy, any order)."""
 
-    def __init__(self, adv, data_local, rank, nranks, allgather_bytes=None, device=None, max_shift=1.0, _defer_connect=False):
+    def __init__(self, adv, data_local, rank, nranks, allgather_bytes=None, device=None, max_shift="auto", _defer_connect=False):
         if adv.N != 4:
             raise HaloUnsupported("the sharded driver covers 2D2V grids (N = 4)")
         for st in adv.states:
@@ -71,7 +99,18 @@ class HaloShardedAdvectionData:
         if n4 % self.P:
             raise HaloUnsupported(f"n4={n4} must be divisible by the number of ranks {self.P}")
         self.c = n4 // self.P
-        self.H = halo_width(its[3].order, max_shift)
+        if allgather_bytes is None and not _defer_connect:
+            if self.P != 1:
+                raise ValueError("allgather_bytes is required for more than one rank")
+            allgather_bytes = lambda b: [b]
+        if isinstance(max_shift, str):
+            if max_shift != "auto" or allgather_bytes is None:
+                raise ValueError("max_shift must be a number of cells, or 'auto' (which needs allgather_bytes)")
+            part = np.ascontiguousarray(np.asarray(data_local, dtype=np.float64).sum(axis=(2, 3))) * (adv.t_mesh[2].step * adv.t_mesh[3].step)
+            rho = sum(np.frombuffer(b, dtype=np.float64).reshape(n1, n2) for b in allgather_bytes(part.tobytes()))
+            max_shift = estimate_max_shift(adv, rho)
+        self.max_shift = float(max_shift)
+        self.H = halo_width(its[3].order, self.max_shift)
         if self.c < 2 * self.H:
             raise HaloUnsupported(f"slab of {self.c} planes is shorter than two halos of {self.H}")
         if tuple(data_local.shape) != (n1, n2, n3, self.c):
@@ -120,10 +159,6 @@ class HaloShardedAdvectionData:
         _lib.check(L.slb_charge_density_raw(self._grid(False, 0, 1), 2, 1.0, self.rho_part))
         self.ctx.sync()
         if not _defer_connect:
-            if allgather_bytes is None:
-                if self.P != 1:
-                    raise ValueError("allgather_bytes is required for more than one rank")
-                allgather_bytes = lambda b: [b]
             self._connect(allgather_bytes(self._export()))
 
     # ---- bootstrap: opaque handle bytes, carried once by the host language ----------------------------------
@@ -401,11 +436,13 @@ def torch_allgather_bytes(dist, group=None):
     return fn
 
 
-def local_group(adv, data, nranks, devices=None, max_shift=1.0):
+def local_group(adv, data, nranks, devices=None, max_shift="auto"):
     """P ranks inside ONE process (tests; also a single host thread driving several GPUs): returns the list of
     rank objects, wired to each other directly.  `data`: the full array [n1, n2, n3, n4]."""
     n4 = adv.sizeall[3]
     c = n4 // nranks
+    if isinstance(max_shift, str):
+        max_shift = estimate_max_shift(adv, np.asarray(data).sum(axis=(2, 3)) * (adv.t_mesh[2].step * adv.t_mesh[3].step))
     ranks = [HaloShardedAdvectionData(adv, np.asfortranarray(data[:, :, :, r * c:(r + 1) * c]), r, nranks,
                                       device=None if devices is None else devices[r], max_shift=max_shift, _defer_connect=True)
              for r in range(nranks)]
