@@ -89,6 +89,9 @@ void slb_graph_destroy(slb_graph* g);
 int slb_event_create(slb_ctx* ctx, void** ev_out);
 int slb_event_record(slb_ctx* ctx, void* ev);
 int slb_event_elapsed_ms(void* ev_start, void* ev_stop, float* elapsed_ms); /* waits for ev_stop */
+/* everything enqueued on ctx's stream after this call waits for `ev` (recorded on ANOTHER context's stream of the
+ * same device): lets a host layer run uploads and read-backs on their own streams next to the sweeps */
+int slb_stream_wait_event(slb_ctx* ctx, void* ev);
 int slb_event_destroy(void* ev);
 
 /* raw device / pinned-host buffers (E fields, rho, shift tables) */

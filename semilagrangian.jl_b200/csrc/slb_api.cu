@@ -218,6 +218,13 @@ extern "C" int slb_event_record(slb_ctx* c, void* ev)
     return SLB_OK;
 }
 
+extern "C" int slb_stream_wait_event(slb_ctx* c, void* ev)
+{
+    if (!c || !ev) return fail(SLB_E_ARG, "slb_stream_wait_event: NULL argument");
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, (cudaEvent_t)ev, 0));
+    return SLB_OK;
+}
+
 extern "C" int slb_event_elapsed_ms(void* e0, void* e1, float* ms)
 {
     if (!e0 || !e1 || !ms) return fail(SLB_E_ARG, "slb_event_elapsed_ms: NULL argument");

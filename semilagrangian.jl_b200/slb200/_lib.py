@@ -32,6 +32,7 @@ SIGNATURES = [
     ("slb_timer_stop", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("slb_event_create", C.c_int, [C.c_void_p, c_void_pp]),
     ("slb_event_record", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_stream_wait_event", C.c_int, [C.c_void_p, C.c_void_p]),
     ("slb_event_elapsed_ms", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     ("slb_event_destroy", C.c_int, [C.c_void_p]),
     ("slb_malloc", C.c_int, [C.c_void_p, C.c_int64, c_void_pp]),
@@ -191,6 +192,10 @@ class Context:
 
     def record(self, ev):
         check(lib().slb_event_record(self.h, ev))
+
+    def wait_event(self, ev):
+        """work enqueued on this context's stream from now on waits for `ev` (recorded on another context)"""
+        check(lib().slb_stream_wait_event(self.h, ev))
 
     @staticmethod
     def elapsed_ms(e0, e1):

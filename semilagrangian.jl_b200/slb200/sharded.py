@@ -436,7 +436,7 @@ def torch_allgather_bytes(dist, group=None):
     return fn
 
 
-def local_group(adv, data, nranks, devices=None, max_shift="auto"):
+def local_group(adv, data, nranks, devices=None, max_shift="auto", host_sync=False):
     """P ranks inside ONE process (tests; also a single host thread driving several GPUs): returns the list of
     rank objects, wired to each other directly.  `data`: the full array [n1, n2, n3, n4]."""
     n4 = adv.sizeall[3]
@@ -453,5 +453,8 @@ def local_group(adv, data, nranks, devices=None, max_shift="auto"):
     for s in ranks:
         s._connect(blobs, barrier=False)
     for s in ranks:
-        s.sync_ranks()
+        if host_sync:   # under a profiler that serialises kernel launches, ranks cannot wait for each other on the device
+            s.ctx.sync()
+        else:
+            s.sync_ranks()
     return ranks

@@ -296,6 +296,9 @@ class FakeLib:
         self.mem[("ev", _addr(ev))] = time.perf_counter()
         return 0
 
+    def slb_stream_wait_event(self, ctx, ev):
+        return 0
+
     def slb_event_elapsed_ms(self, e0, e1, ms):
         _set(ms, max(1e-6, 1e3 * (self.mem[("ev", _addr(e1))] - self.mem[("ev", _addr(e0))])))
         return 0
