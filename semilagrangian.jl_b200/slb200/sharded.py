@@ -358,6 +358,38 @@ class HaloShardedAdvectionData:
                                              C.c_void_p(self.ptr[self.cur] + 8 * self.H * self.plane), self.plane * self.c * 8))
         self.ctx.sync()
 
+    # ---- streamed host I/O: uploads and read-backs on their own streams (bench.py's end-to-end leg) ---------------
+    def stream_io_begin(self):
+        """contexts (streams) and events for read-backs and uploads that run next to the passes"""
+        if getattr(self, "_io", None) is None:
+            up, down = _lib.Context(self.ctx.device), _lib.Context(self.ctx.device)
+            self._io = {"up": up, "down": down, "ev_step": self.ctx.event(), "ev_up": up.event(), "ev_down": down.event()}
+            up.record(self._io["ev_up"])
+            down.record(self._io["ev_down"])
+        return self._io
+
+    def stream_io_exchange(self, host_out_flat, host_in_flat):
+        """after a step: read this rank's slab back into host_out_flat and, at the same time, upload host_in_flat as
+        the next step's slab into the free buffer of the rotation (PCIe is full duplex); the next step's passes wait
+        for both.  Every rank calls it; the new slab's halo planes go to the neighbours and the ranks synchronise."""
+        io, L = self.stream_io_begin(), _lib.lib()
+        nb, off = self.plane * self.c * 8, 8 * self.H * self.plane
+        self.ctx.record(io["ev_step"])
+        nxt = (self.cur + 1) % NBUF     # not read by anybody any more: pushes into it ended with the last all-gather
+        io["down"].wait_event(io["ev_step"])
+        _lib.check(L.slb_memcpy_d2h(io["down"].h, host_out_flat.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr[self.cur] + off), nb))
+        io["down"].record(io["ev_down"])
+        io["up"].wait_event(io["ev_step"])
+        _lib.check(L.slb_memcpy_h2d(io["up"].h, C.c_void_p(self.ptr[nxt] + off), host_in_flat.ctypes.data_as(C.c_void_p), nb))
+        io["up"].record(io["ev_up"])
+        self.ctx.wait_event(io["ev_up"])
+        self.ctx.wait_event(io["ev_down"])
+        self.cur = nxt
+        self._pending = None
+        self.linesum_valid = False
+        self._push_initial_halos()
+        self.sync_ranks()
+
     def sync_ranks(self):
         _lib.check(_lib.lib().slb_comm_barrier(self.comm))
 

@@ -184,4 +184,42 @@ def test_halo_driver_refuses_what_it_does_not_cover():
         HaloShardedAdvectionData(adv, np.zeros((16, 8, 8, 16)), 0, 1)
     adv = S.Advection(ms, [S.Lagrange(7)] * 4, 0.1, tabst)
     with pytest.raises(HaloUnsupported):   # slab of 4 planes, halo of 4
-        HaloShardedAdvectionData(adv, np.zeros((16, 8, 8, 4)), 0, 4)
+        HaloShardedAdvectionData(adv, np.zeros((16, 8, 8, 4)), 0, 4, allgather_bytes=lambda b: [b] * 4, max_shift=1.0)
+
+
+def test_streamed_io_exchange_between_steps():
+    """read-back of a step's result overlapped with the upload of the next step's input (the end-to-end leg of
+    bench.py): the downloaded slabs are the step's result, and the next step starts from the uploaded data."""
+    import slb200 as S
+    from slb200 import _lib
+    from slb200.sharded import local_group
+
+    sz = (32, 8, 16, 32)
+    adv, f = _adv(S, sz, 7)
+    plain = S.AdvectionData(adv, f, S.getpoissonvar(adv))
+    while S.advection(plain):
+        pass
+    want = plain.getdata()
+    ranks = local_group(adv, f, 2)
+    c = ranks[0].c
+    outs, ins = [], []
+    for s in ranks:
+        o, _p = _lib.pinned_empty((s.plane * c,))
+        i, _q = _lib.pinned_empty((s.plane * c,))
+        i[:] = np.asfortranarray(f[..., s.rank * c:(s.rank + 1) * c]).reshape(-1, order="F")
+        outs.append(o)
+        ins.append(i)
+    for rep in range(2):   # both repetitions start from f: the second one from the uploaded copy
+        more = True
+        while more:
+            more = [s.advection() for s in ranks][0]
+        for s, o, i in zip(ranks, outs, ins):
+            s.stream_io_exchange(o, i)
+        for s in ranks:
+            s.ctx.sync()
+            s._io["down"].sync()
+        got = np.concatenate([o.reshape((sz[0], sz[1], sz[2], c), order="F") for o in outs], axis=3)
+        assert relerr(got, want) <= 1e-13, rep
+    for s in ranks:
+        s.check()
+        s.close()
