@@ -194,8 +194,10 @@ int slb_sweep_pair_ex(slb_grid* g, int dimA, const slb_interp* itA, const double
  *     Vlasov-Poisson velocity sweeps |alpha| = dt/dv |E| is about one cell.
  * Either pass can also store the outputs that lie within `halo` of a slab boundary into the neighbours' halo
  * planes (push_lo / push_hi: the address, in the rank below / above, of the array that corresponds to this
- * grid's back buffer; NULL = no push): the halo exchange rides inside the pass as NVLink peer stores, there is no
- * separate collective.  Callers order the ranks with slb_comm_* before the halos are read.
+ * grid's back buffer; NULL = that side is not pushed by this pass): the halo exchange rides inside the pass as NVLink
+ * peer stores, there is no separate collective.  Callers order the ranks with slb_comm_* before the halos are read.
+ * (A pass whose NVLink time exceeds its HBM time can push one side itself and leave the other to a copy on a second
+ * stream that overlaps the field solve: slb_memcpy_d2d + slb_comm_signal / slb_comm_wait.)
  * Results are bit-identical to slb_sweep_pair on the unsharded grid.  Lagrange / Hermite kinds (B-spline
  * pre-solves couple the whole line: they use the transposing driver, slb_sweep_pair_ex / slb_sweep_peer). */
 #define SLB_HALO_MARCH 1
@@ -240,6 +242,13 @@ int slb_comm_barrier(slb_comm* cm);
  * Charge-density slabs (transposing driver: the gathered array IS rho) and per-rank partial charge densities
  * (halo driver: slb_poisson_solve_partial sums them in rank order) travel this way. */
 int slb_comm_allgather(slb_comm* cm, const double* local_dev, int64_t n, const double** slots_out);
+
+/* point-to-point ordering between two ranks (4 independent slots per pair): slb_comm_signal raises a flag in `peer`'s
+ * mailbox once everything enqueued before it on the stream of `on_ctx` (NULL: the comm's own context; e.g. a second
+ * context used as a copy stream for halo planes) is complete; slb_comm_wait holds the stream until the matching
+ * signal of `peer` has arrived.  Signals and waits of a (pair, slot) must match one to one. */
+int slb_comm_signal(slb_comm* cm, slb_ctx* on_ctx, int peer, int slot);
+int slb_comm_wait(slb_comm* cm, slb_ctx* on_ctx, int peer, int slot);
 
 /* ---- sweeps fused with the multi-GPU re-shard -------------------------------- */
 /* A 2D2V grid sharded over P ranks alternates between two slab layouts; the all-to-all between

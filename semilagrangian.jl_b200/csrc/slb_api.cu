@@ -1153,7 +1153,6 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     fa.ncB = itB->nc;
     fa.linesum = g->linesum;
     if (halo) {
-        if ((halo->push_lo == nullptr) != (halo->push_hi == nullptr)) return fail(SLB_E_ARG, "slb_sweep_pair_halo: push_lo and push_hi must both be set or both be NULL");
         fa.win_h = halo->halo;
         fa.err = halo->err_flag ? halo->err_flag : c->err_word;
         if (mode == SLB_FUSED_WIN) {

@@ -32,10 +32,12 @@ struct CommHandle {  // 128 bytes on the wire
 };
 static_assert(sizeof(CommHandle) == SLB_COMM_HANDLE_BYTES, "handle size");
 
+#define SLB_COMM_NSIG 4
 struct CommDev {  // kernel argument
     int rank, P;
     ull* bar[SLB_COMM_MAXP];     // bar[q]: the barrier flags in rank q's mailbox (bar[rank]: own)
     ull* gat[SLB_COMM_MAXP];     // all-gather flags
+    ull* sig[SLB_COMM_MAXP];     // point-to-point signals: [SLB_COMM_NSIG][MAXP]
     double* slots[SLB_COMM_MAXP];
 };
 
@@ -53,11 +55,12 @@ struct slb_comm {
     CommDev dev;
     bool connected;
     ull epoch_bar, epoch_gat;
+    ull sent[SLB_COMM_MAXP][SLB_COMM_NSIG], awaited[SLB_COMM_MAXP][SLB_COMM_NSIG];
     std::vector<Opened> opened;
 };
 
-// mailbox layout: [bar flags: MAXP ull][gather flags: MAXP ull][pad to 256 B][slots: 2 x P x nslot doubles]
-static const size_t kFlagBytes = 256;
+// mailbox layout: [bar flags: MAXP ull][gather flags: MAXP ull][signal flags: NSIG x MAXP ull][slots: 2 x P x nslot doubles]
+static const size_t kFlagBytes = (2 + SLB_COMM_NSIG) * SLB_COMM_MAXP * sizeof(ull);
 
 // ------------------------------------------------------------------------------------------------------------
 // kernels
@@ -83,6 +86,18 @@ __global__ void k_comm_barrier(const __grid_constant__ CommDev cd, ull epoch)
         comm_store_flag(cd.bar[q] + cd.rank, epoch);
         while (comm_load_flag(cd.bar[cd.rank] + q) < epoch) {
         }
+    }
+}
+
+// point-to-point: "what this rank enqueued before on that stream (a halo copy into your memory) is complete"
+__global__ void k_comm_signal(ull* flag, ull epoch)
+{
+    __threadfence_system();
+    comm_store_flag(flag, epoch);
+}
+__global__ void k_comm_wait(const ull* flag, ull epoch)
+{
+    while (comm_load_flag(flag) < epoch) {
     }
 }
 
@@ -198,6 +213,8 @@ extern "C" int slb_comm_create(slb_ctx* c, int rank, int nranks, int64_t nslot, 
     cm->nslot = nslot;
     cm->connected = false;
     cm->epoch_bar = cm->epoch_gat = 0;
+    memset(cm->sent, 0, sizeof(cm->sent));
+    memset(cm->awaited, 0, sizeof(cm->awaited));
     cm->mbox_bytes = kFlagBytes + (size_t)2 * nranks * nslot * sizeof(double);
     if (cm->mbox_bytes < ((size_t)4 << 20)) cm->mbox_bytes = (size_t)4 << 20;  // its own allocation, not a sub-allocated block
     cm->mbox = nullptr;
@@ -226,6 +243,7 @@ static void wire(slb_comm* cm, int q, char* mbox)
 {
     cm->dev.bar[q] = reinterpret_cast<ull*>(mbox);
     cm->dev.gat[q] = reinterpret_cast<ull*>(mbox) + SLB_COMM_MAXP;
+    cm->dev.sig[q] = reinterpret_cast<ull*>(mbox) + 2 * SLB_COMM_MAXP;
     cm->dev.slots[q] = reinterpret_cast<double*>(mbox + kFlagBytes);
 }
 
@@ -314,5 +332,29 @@ extern "C" int slb_comm_allgather(slb_comm* cm, const double* local_dev, int64_t
     k_comm_allgather<<<cm->P, 1024, 0, c->stream>>>(cm->dev, local_dev, n, slot_off, epoch);
     LAUNCH_CHECK(c);
     *slots_out = cm->dev.slots[cm->rank] + slot_off;
+    return SLB_OK;
+}
+
+extern "C" int slb_comm_signal(slb_comm* cm, slb_ctx* on, int peer, int slot)
+{
+    if (!cm || !cm->connected) return slb_fail(SLB_E_ARG, "slb_comm_signal: comm missing or not connected");
+    if (peer < 0 || peer >= cm->P || slot < 0 || slot >= SLB_COMM_NSIG) return slb_fail(SLB_E_ARG, "slb_comm_signal: peer / slot out of range");
+    slb_ctx* c = on ? on : cm->ctx;
+    if (c->device != cm->ctx->device) return slb_fail(SLB_E_ARG, "slb_comm_signal: the stream's context lives on another device");
+    CUDA_TRY(cudaSetDevice(c->device));
+    k_comm_signal<<<1, 1, 0, c->stream>>>(cm->dev.sig[peer] + slot * SLB_COMM_MAXP + cm->rank, ++cm->sent[peer][slot]);
+    LAUNCH_CHECK(c);
+    return SLB_OK;
+}
+
+extern "C" int slb_comm_wait(slb_comm* cm, slb_ctx* on, int peer, int slot)
+{
+    if (!cm || !cm->connected) return slb_fail(SLB_E_ARG, "slb_comm_wait: comm missing or not connected");
+    if (peer < 0 || peer >= cm->P || slot < 0 || slot >= SLB_COMM_NSIG) return slb_fail(SLB_E_ARG, "slb_comm_wait: peer / slot out of range");
+    slb_ctx* c = on ? on : cm->ctx;
+    if (c->device != cm->ctx->device) return slb_fail(SLB_E_ARG, "slb_comm_wait: the stream's context lives on another device");
+    CUDA_TRY(cudaSetDevice(c->device));
+    k_comm_wait<<<1, 1, 0, c->stream>>>(cm->dev.sig[cm->rank] + slot * SLB_COMM_MAXP + peer, ++cm->awaited[peer][slot]);
+    LAUNCH_CHECK(c);
     return SLB_OK;
 }

@@ -298,9 +298,9 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     // of the slab (the host guarantees win_c >= 2 win_h: never both), pd is the offset to that neighbour's halo
     bool psh = false;
     long long pd = 0;
-    if (MODE == SLB_FUSED_PSH && fa.pushL) {
+    if (MODE == SLB_FUSED_PSH) {
         const int ps = (int)(fa.push_on_lo ? plo : phi);
-        const bool toL = ps < fa.win_h, toR = ps >= fa.win_c - fa.win_h;
+        const bool toL = fa.pushL != nullptr && ps < fa.win_h, toR = fa.pushR != nullptr && ps >= fa.win_c - fa.win_h;
         psh = toL || toR;
         pd = toL ? pdL : pdR;
     }
@@ -319,9 +319,12 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
             fused_st(st_a && inw, po, accA);
             fused_st(st_b && inw, po + oscel, accB);
             if (fa.pushL) {
-                const bool pl = inw && lo < 2 * fa.win_h, pr = inw && lo >= fa.win_c;
+                const bool pl = inw && lo < 2 * fa.win_h;
                 fused_st(st_a && pl, po + pdL, accA);
                 fused_st(st_b && pl, po + pdL + oscel, accB);
+            }
+            if (fa.pushR) {
+                const bool pr = inw && lo >= fa.win_c;
                 fused_st(st_a && pr, po + pdR, accA);
                 fused_st(st_b && pr, po + pdR + oscel, accB);
             }

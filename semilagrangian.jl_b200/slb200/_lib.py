@@ -71,6 +71,8 @@ SIGNATURES = [
     ("slb_comm_open_buffer", C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     ("slb_comm_close_buffer", C.c_int, [C.c_void_p, C.c_void_p]),
     ("slb_comm_barrier", C.c_int, [C.c_void_p]),
+    ("slb_comm_signal", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    ("slb_comm_wait", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     ("slb_comm_allgather", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_void_pp]),
     ("slb_poisson_solve_partial", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, c_void_pp]),
     ("slb_ipc_get_handle", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -152,6 +152,18 @@ class HaloShardedAdvectionData:
         self.points = [self.ctx.to_device(m.points) for m in adv.t_mesh]
         self.linesum = self.ctx.malloc(self.plane * 8)
         self.left = self.right = None
+        # split pushes: a pushing pass stores the boundary planes of its LOW side into the lower neighbour itself; the
+        # HIGH side travels as a peer copy on a second stream while the main stream does the field solve that follows
+        # (the pass is NVLink-bound when slabs are thin: 8 GPUs at 128^4 send half as many bytes as they write).
+        import os as _os
+
+        sp = _os.environ.get("SLB_HALO_SPLIT_PUSH", "auto")
+        self.split_push = (self.c <= 4 * self.H) if sp == "auto" else sp not in ("0", "")
+        self.side = _lib.Context(device)
+        self.ev_pass = self.ctx.event()
+        self.ev_copy = self.side.event()
+        self.side.record(self.ev_copy)
+        self._await_copy = False
         # every allocation happens here, before the first cross-rank kernel: cudaMalloc / cudaFree synchronise the
         # device, which must not happen while another in-process rank's kernel waits for this rank's flag
         for d in range(4):
@@ -312,13 +324,20 @@ class HaloShardedAdvectionData:
             tB, lB, sB, scB = C.c_void_p(self.points[3].value + 8 * self.rank * self.c), self.c, [0, 0, 0, 1], -dtB / adv.t_mesh[1].step
         g = self._grid(vpass, self.cur, out)
         off = 0 if vpass else 8 * self.H * self.plane
+        split = push and self.split_push
         hl = _lib.SlbHalo()
         hl.mode = _lib.SLB_HALO_MARCH if vpass else _lib.SLB_HALO_PASSIVE
         hl.halo = self.H
         hl.shard_dim = 3
         hl.push_lo = (self.left[out] + off) if push else None
-        hl.push_hi = (self.right[out] + off) if push else None
+        hl.push_hi = (self.right[out] + off) if (push and not split) else None
         hl.err_flag = None
+        if vpass:
+            # the LOW halo rows of this pass's input were copied by the lower neighbour's second stream: hold the pass
+            # until its signal has arrived (every rank pushed, so every rank waits: signals and waits match one to one)
+            self._consume_copy()
+        if split:
+            self.ctx.wait_event(self.ev_copy)  # the previous copy out of this rotation's buffers is long over; make it formal
         want_ls = vpass and self.use_linesum and nxt == 2
         self.linesum_valid = False
         if want_ls:
@@ -329,12 +348,28 @@ class HaloShardedAdvectionData:
             _lib.check(L.slb_sweep_pair_halo(g, dA, hA, tA, lA, _lib.i64(sA), float(scA), dB, hB, tB, lB, _lib.i64(sB), float(scB), 1, 0,
                                              C.byref(hl)))
             _lib.check(L.slb_grid_swap(g))  # keep the handle's orientation; the driver tracks `cur`
+            if split:
+                # rows [c, c + H) of the output (haloed row numbers) -> the upper neighbour's low halo rows [0, H),
+                # as a peer copy on the second stream, then its signal; overlaps the field solve on the main stream
+                self.ctx.record(self.ev_pass)
+                self.side.wait_event(self.ev_pass)
+                _lib.check(L.slb_memcpy_d2d(self.side.h, C.c_void_p(self.right[out]), C.c_void_p(self.ptr[out] + 8 * self.plane * self.c),
+                                            8 * self.H * self.plane))
+                _lib.check(L.slb_comm_signal(self.comm, self.side.h, (self.rank + 1) % self.P, 0))
+                self.side.record(self.ev_copy)
+                self._await_copy = True
         finally:
             if want_ls:
                 _lib.check(L.slb_grid_set_linesum(g, None))
         self.linesum_valid = want_ls
         self.cur = out
         self.n_fused += 1
+
+    def _consume_copy(self):
+        """enqueue the wait for the lower neighbour's halo copy, if one is outstanding"""
+        if self._await_copy:
+            _lib.check(_lib.lib().slb_comm_wait(self.comm, None, (self.rank - 1) % self.P, 0))
+            self._await_copy = False
 
     # ---- data access --------------------------------------------------------------------------------------------
     def getdata_local(self):
@@ -348,6 +383,7 @@ class HaloShardedAdvectionData:
         """replace this rank's slab (flat Fortran order, e.g. pinned memory) and re-send its halo planes; every
         rank must call it, followed by sync_ranks()"""
         self._pending = None
+        self._consume_copy()
         _lib.check(_lib.lib().slb_memcpy_h2d(self.ctx.h, C.c_void_p(self.ptr[self.cur] + 8 * self.H * self.plane),
                                              host_flat.ctypes.data_as(C.c_void_p), self.plane * self.c * 8))
         self._push_initial_halos()
@@ -374,6 +410,7 @@ class HaloShardedAdvectionData:
         for both.  Every rank calls it; the new slab's halo planes go to the neighbours and the ranks synchronise."""
         io, L = self.stream_io_begin(), _lib.lib()
         nb, off = self.plane * self.c * 8, 8 * self.H * self.plane
+        self._consume_copy()
         self.ctx.record(io["ev_step"])
         nxt = (self.cur + 1) % NBUF     # not read by anybody any more: pushes into it ended with the last all-gather
         io["down"].wait_event(io["ev_step"])
@@ -406,6 +443,7 @@ class HaloShardedAdvectionData:
         L = _lib.lib()
         if self.ctx is None:
             return
+        self.side.sync()
         self.ctx.sync()
         for g in self._grids.values():
             L.slb_grid_destroy(g)
@@ -419,6 +457,7 @@ class HaloShardedAdvectionData:
         for p in self._raw + [self.rho_part, self.rho_dev, self.linesum] + self.E_dev + self.points:
             self.ctx.free(p)
         self._raw = []
+        self.side.close()
         self.ctx.close()
         self.ctx = None
 

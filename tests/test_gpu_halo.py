@@ -84,7 +84,8 @@ def test_halo_passes_bitwise_equal_unsharded(P, order, sz):
                 s.points = [None, None, tv1, tv2]
                 s._pass(0, -adv.t_mesh[0].step, 1, -adv.t_mesh[1].step, 2)
                 s.points = s.points_saved
-        for s in ranks:   # order the pushes of this pass against the next pass (the driver's all-gather does it)
+        for s in ranks:   # order the pushes of this pass against the next pass (the driver's all-gather does it; the half
+            s._consume_copy()   # that travels on the second stream is awaited by the next v pass -- here, explicitly)
             s.sync_ranks()
 
     run("v", 0)
@@ -115,10 +116,15 @@ def test_halo_passes_bitwise_equal_unsharded(P, order, sz):
         s.close()
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
 @pytest.mark.parametrize("P,order,sz,nsteps", [(2, 7, (32, 16, 16, 32), 3), (4, 7, (32, 8, 16, 32), 2), (1, 5, (32, 8, 16, 16), 2),
                                                 (4, 9, (16, 16, 20, 40), 2)])
-def test_halo_sharded_steps_match_single_grid_and_oracle(P, order, sz, nsteps):
+def test_halo_sharded_steps_match_single_grid_and_oracle(P, order, sz, nsteps, split, monkeypatch):
+    """split = "1": a pushing pass sends its low-side planes itself and leaves the high side to a peer copy on a second
+    stream (signalled to the neighbour, awaited before its next v pass); "0": both sides inside the pass."""
     import slb200 as S
+
+    monkeypatch.setenv("SLB_HALO_SPLIT_PUSH", split)
     from oracle import refmodel as R
     from slb200.sharded import local_group
 

@@ -14,7 +14,14 @@ import test_gpu_halo as T
 cases = [(8, 7, (64, 64, 64, 64)), (4, 7, (64, 64, 64, 64)), (8, 7, (32, 8, 16, 64)), (8, 7, (64, 8, 16, 64)), (4, 7, (64, 8, 16, 32)),
          (2, 7, (64, 8, 16, 32)), (8, 7, (128, 4, 16, 128))]
 for P, order, sz in cases:
-    for name, fn, extra in (("passes", T.test_halo_passes_bitwise_equal_unsharded, ()), ("steps", T.test_halo_sharded_steps_match_single_grid_and_oracle, (2,))):
+    class _Env:   # stands in for pytest's monkeypatch
+        @staticmethod
+        def setenv(k, v):
+            os.environ[k] = v
+
+    for name, fn, extra in (("passes", T.test_halo_passes_bitwise_equal_unsharded, ()),
+                            ("steps/split", T.test_halo_sharded_steps_match_single_grid_and_oracle, (2, "1", _Env)),
+                            ("steps/in-pass", T.test_halo_sharded_steps_match_single_grid_and_oracle, (2, "0", _Env))):
         try:
             fn(P, order, sz, *extra)
             print(f"P={P} order={order} sz={sz} {name}: OK", flush=True)
