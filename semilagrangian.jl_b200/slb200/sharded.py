@@ -152,13 +152,15 @@ class HaloShardedAdvectionData:
         self.points = [self.ctx.to_device(m.points) for m in adv.t_mesh]
         self.linesum = self.ctx.malloc(self.plane * 8)
         self.left = self.right = None
-        # split pushes: a pushing pass stores the boundary planes of its LOW side into the lower neighbour itself; the
-        # HIGH side travels as a peer copy on a second stream while the main stream does the field solve that follows
-        # (the pass is NVLink-bound when slabs are thin: 8 GPUs at 128^4 send half as many bytes as they write).
+        # split pushes (SLB_HALO_SPLIT_PUSH=1, off by default): a pushing pass stores the boundary planes of its LOW side
+        # into the lower neighbour itself; the HIGH side travels as a peer copy on a second stream while the main stream
+        # does the field solve that follows.  Measured on 8 GPUs at 128^4 (thin slabs, NVLink-bound passes): the x pass
+        # drops from 0.223 to 0.156 ms, but the copy does not hide behind the latency-bound field-solve chain (0.093 ->
+        # 0.147 ms) and the next v pass waits for it (0.193 -> 0.217): 0.771 -> 0.827 ms per step
+        # (profiles/r2_bench_8gpu_halo_splitpush_experiment.json).  Kept for larger grids / other link ratios.
         import os as _os
 
-        sp = _os.environ.get("SLB_HALO_SPLIT_PUSH", "auto")
-        self.split_push = (self.c <= 4 * self.H) if sp == "auto" else sp not in ("0", "")
+        self.split_push = _os.environ.get("SLB_HALO_SPLIT_PUSH", "0") not in ("0", "")
         self.side = _lib.Context(device)
         self.ev_pass = self.ctx.event()
         self.ev_copy = self.side.event()
