@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = M * S;
     double* zps = ssm;                       // [H][4 + NQ]  z_k^1 .. z_k^4 | z_k^(4b), b < NB
-    double* czs = zps + H * (4 + NQ);        // [H][S]   z_k^(M m) / (1 - z_k^n)
-    double* Lbuf = czs + H * S;              // [2][S][32]
+    double* czs = zps + H * (4 + NQ);        // [H][S]   z_k^(M m) / (1 - z_k^n), zero beyond the kept terms
+    double* zpl = czs + H * S;               // [H][M]   z_k^(j+1) (orders 9, 11: one chain per segment, see below)
+    double* Lbuf = zpl + H * M;              // [2][S][32]
     double* wsm = Lbuf + 2 * S * 32;         // [P1][32]
     double* hal = wsm + P1 * 32;             // [S][HM][32]
     double* lsb = hal + S * HM * 32;         // [S][32]   line-sum partials
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
         const int k = q / (4 + NQ), r = q % (4 + NQ);
         zps[q] = r < 4 ? fa.tab.zp[k][r] : (r == 4 ? 1.0 : (r - 4 < NB ? fa.tab.zp[k][4 * (r - 4) - 1] : 0.0));
     }
-    for (int q = threadIdx.x; q < H * S; q += 32 * S) czs[q] = fa.tab.cz[q / S][q % S];
+    for (int q = threadIdx.x; q < H * S; q += 32 * S) czs[q] = (q % S) < fa.tab.nm[q / S] ? fa.tab.cz[q / S][q % S] : 0.0;
+    for (int q = threadIdx.x; q < H * M; q += 32 * S) zpl[q] = fa.tab.zp[q / M][q % M];
     const long long line0 = (long long)blockIdx.x * 32;
     const long long line = line0 + lane;
     const bool active = line < fa.nlines;
@@ -165,11 +167,41 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     // its continuation L is the segment's contribution to the ring; (3) after the exchange, the true state entering
     // sub-segment b is e[b] + z^(4b) c, and row i of it is corrected by z^(i+1) times that.  Same FMA count as one
     // 15-deep chain plus a 16-term correction, a quarter of the dependent latency and 6 constants instead of 16.
+    // Orders 9 and 11 (H >= 4) measured faster with ONE chain per segment and a 16-constant correction (1.41 vs 1.50 ms
+    // at order 11: the sub-segment form trades latency for instructions, and these orders are issue-bound).
+    constexpr bool ONECHAIN = H >= 4;
 #pragma unroll
     for (int k = 0; k < 2 * H; ++k) {
         const bool causal = k < H;           // causal stages y[i] = x[i] + z y[i-1], then anticausal y[i] = x[i] + z y[i+1]
         const int kk = causal ? k : k - H;
 #define SLB_IX(t) (causal ? (t) : (M - 1 - (t)))  // the anticausal stages are the causal ones on the reversed segment
+        if constexpr (ONECHAIN) {
+            const double z = fa.tab.z[kk];
+#pragma unroll
+            for (int j = 1; j < M; ++j) v[SLB_IX(j)] = fma(z, v[SLB_IX(j - 1)], v[SLB_IX(j)]);
+            double* Lb = Lbuf + (k & 1) * S * 32;
+            Lb[w * 32 + lane] = v[SLB_IX(M - 1)];
+            __syncthreads();
+            if (k == 0) {
+                const double tt = tts[lane];
+                for (int j = w; j < P1; j += S) wsm[j * 32 + lane] = bspseg_weight(ct, fa.nc, j, tt) * fa.tab.invC;
+            }
+            double c = 0.0;
+#pragma unroll
+            for (int m = 0; m < S; ++m) {
+                int ws = causal ? w - 1 - m : w + 1 + m;
+                ws = ws < 0 ? ws + S : (ws >= S ? ws - S : ws);
+                c = fma(czs[kk * S + m], Lb[ws * 32 + lane], c);
+            }
+            const double2* zp2 = reinterpret_cast<const double2*>(zpl + kk * M);
+#pragma unroll
+            for (int j = 0; j < M; j += 2) {
+                const double2 pz = zp2[j >> 1];
+                v[SLB_IX(j)] = fma(c, pz.x, v[SLB_IX(j)]);
+                v[SLB_IX(j + 1)] = fma(c, pz.y, v[SLB_IX(j + 1)]);
+            }
+            continue;
+        }
         double zc[4], zq[NQ];
         {
             const double2* cp = reinterpret_cast<const double2*>(zps + kk * (4 + NQ));
