@@ -258,12 +258,15 @@ def _cfg_vp4(n, order, kind):
     return build
 
 
-def run_configs(S, ctx, args, peak, only=None):
+def run_configs(S, ctx, args, peak, only=None, with_oracle=True):
     """C1-C4 on this GPU: ms/step (CUDA events), Gcell/s per sweep, the HBM fraction of the per-sweep algorithmic
     traffic (16 B per cell-update; C1/C2/C3 are cache-resident or launch-bound, flagged), and a
     parity figure: the grid after `psteps` Strang steps against the oracle on the same inputs (max-abs relative)."""
-    from oracle import refmodel as R
     from slb200 import _lib
+
+    R = None
+    if with_oracle:   # the oracle is the CHECKER of this leg (part of the cpu_baseline / parity leg; --no-cpu skips it)
+        from oracle import refmodel as R
 
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     e0, e1 = ctx.event(), ctx.event()
@@ -279,18 +282,20 @@ def run_configs(S, ctx, args, peak, only=None):
             continue  # reduced-size smoke runs of bench.py skip the big case
         try:
             g, cells = build(S)
-            o, _ = build(R, nthreads=ncores)
-            for _ in range(psteps):
-                while S.advection(g):
-                    pass
-                while R.advection(o):
-                    pass
-            a, b = g.getdata(), o.data
-            par = {"steps": psteps, "f_rel_maxabs": float(np.max(np.abs(a - b)) / np.max(np.abs(b)))}
-            if has_ee:
-                ee_g, ee_o = S.compute_ee(g), R.compute_ee(o)
-                par["ee_rel"] = abs(ee_g - ee_o) / abs(ee_o)
-            del a, b, o
+            par = None
+            if R is not None:
+                o, _ = build(R, nthreads=ncores)
+                for _ in range(psteps):
+                    while S.advection(g):
+                        pass
+                    while R.advection(o):
+                        pass
+                a, b = g.getdata(), o.data
+                par = {"steps": psteps, "f_rel_maxabs": float(np.max(np.abs(a - b)) / np.max(np.abs(b)))}
+                if has_ee:
+                    ee_g, ee_o = S.compute_ee(g), R.compute_ee(o)
+                    par["ee_rel"] = abs(ee_g - ee_o) / abs(ee_o)
+                del a, b, o
             for _ in range(3):
                 while S.advection(g):
                     pass
@@ -571,7 +576,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
     if not args.no_configs:
         advd.close()
-        line["configs"] = run_configs(S, ctx, args, peak)
+        line["configs"] = run_configs(S, ctx, args, peak, with_oracle=not args.no_cpu)
     print(json.dumps(line))
     return 0
 

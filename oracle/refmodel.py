@@ -394,6 +394,9 @@ class TranslationVar:
     def alpha_table(self, advd):
         return np.array([self.valok[0]]), [0] * advd.adv.N
 
+    def getalpha_nd(self, advd, ind):  # getalpha(pv::TranslationVar, self, ind) = pv.valok  (src/translation.jl:33-35)
+        return self.valok
+
 
 def gettranslationvar(v):
     return TranslationVar(v)

@@ -359,7 +359,7 @@ def sweep_pair(advd, stageA, stageB):
 
 
 def _advection_2d(advd):
-    """A const-shift state with ndims = 2 (e.g. ([1,2,3,4], 2, 1, true), test/test_poisson2d.jl:276,
+    """A const-shift state with ndims >= 2 (e.g. ([1,2,3,4], 2, 1, true), test/test_poisson2d.jl:276,
     examples/vlasov-poisson-2d2v.jl:196): the reference shifts every 2-D slice by a constant pair
     (alpha_1, alpha_2) with the tensor stencil of src/interpolation.jl:212-231.  That operator is
     the product of the two 1-D stencils (and of the 1-D B-spline solves, :48-94), so it runs as ONE
@@ -372,17 +372,26 @@ def _advection_2d(advd):
     descr = ext.alpha_table_nd(advd)  # one (table, strides, scale, on_device) per swept dim
     want = bool(getattr(ext, "wants_linesum", lambda a: False)(advd))
     stages = []
-    for x in range(2):
+    for x in range(st.ndims):
         table, strides, scale, on_device = descr[x]
         d = st.perm[x] - 1
         stages.append((d, advd.adv.t_interp[d], table, list(strides), scale, on_device, advd.flags, False))
-    if stages[1][0] == 0:  # the march of the fused pass cannot run along dim 0: the stencils commute
-        stages.reverse()
-    a, b = stages
-    b = b[:7] + (want,)
-    if not (advd.fuse_pairs and sweep_pair(advd, a, b)):
-        _sweep_now(advd, *a)
-        _sweep_now(advd, *b)
+    if st.ndims == 2:
+        if stages[1][0] == 0:  # the march of the fused pass cannot run along dim 0: the stencils commute
+            stages.reverse()
+    else:
+        # ndims > 2 (the N-D tensor stencil of src/interpolation.jl:212-231 for any N): the 1-D stencils along
+        # different dims commute, so they run in ascending dim order -- dim 0 first, where it can only be the
+        # cross sweep of a fused pass -- and are paired greedily
+        stages.sort(key=lambda sg: sg[0])
+    stages[-1] = stages[-1][:7] + (want,)
+    i = 0
+    while i < len(stages):
+        if i + 1 < len(stages) and advd.fuse_pairs and sweep_pair(advd, stages[i], stages[i + 1]):
+            i += 2
+        else:
+            _sweep_now(advd, *stages[i])
+            i += 1
     return advd.nextstate()
 
 
@@ -399,11 +408,7 @@ def advection(advd):
         return unsplit2d.advection_single_state(advd)
     if advd.adv.timealg != NoTimeAlg:
         raise NotImplementedError("the Adams-Bashforth time algorithms drive states with per-point shifts only")
-    if st.ndims > 2:
-        raise NotImplementedError(
-            "const-shift states with ndims <= 2 are on the B200 path (SURVEY.md 8a/8f)"
-        )
-    if st.ndims == 2:
+    if st.ndims >= 2:
         return _advection_2d(advd)
     interp = advd.getinterp()[0]
     ext = advd.parext

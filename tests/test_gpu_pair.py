@@ -329,3 +329,24 @@ def test_fused_pair_full_size_properties_128_4():
     t2 = tE2.reshape((n, n), order="F")[sl[0], sl[1]].reshape(-1, order="F")
     ref = oracle_sweep(oracle_sweep(sub, 2, oit, t1, [1, 4, 0, 0]), 3, oit, t2, [1, 4, 0, 0])
     assert relerr(fused[sl], ref) <= 2e-12
+
+
+def test_const_shift_state_with_ndims_3_and_4():
+    """const-shift states with ndims > 2 (src/interpolation.jl:212-231 for N = 3, 4): a fused pair + single sweeps on
+    the device against the oracle's N-D tensor stencil"""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    def build(M, sz, its, perm, vals):
+        ms = tuple(M.UniformMesh(0.0, 1.0, n) for n in sz)
+        adv = M.Advection(ms, [M.Lagrange(o) for o in its], 0.01, [(perm, len(perm), 1, True)], tab_coef=[0.01])
+        rng = np.random.default_rng(9)
+        return M.AdvectionData(adv, np.asfortranarray(rng.random(sz)), M.gettranslationvar(vals))
+
+    for sz, its, perm, vals in (((16, 12, 10), (5, 5, 3), [3, 1, 2], (130.0, -270.0, 55.0)),
+                                ((12, 10, 8, 8), (3, 3, 3, 3), [2, 1, 4, 3], (130.0, -270.0, 55.0, -20.0))):
+        g, o = build(S, sz, its, perm, vals), build(R, sz, its, perm, vals)
+        for _ in range(2):
+            assert S.advection(g) == R.advection(o)
+        assert relerr(g.getdata(), o.data) <= 1e-12
+        assert g.n_fused >= 2   # at least one fused pair per call

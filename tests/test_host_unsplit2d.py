@@ -91,3 +91,22 @@ def test_quasigeostrophic_driver_sequencing(fake, alg, ordalg):
     assert relerr(g.getdata(), o.data) <= 1e-11
     assert relerr(g.bufcur.to_host(), o.bufcur) <= 1e-9
     assert "poisson_solve_2d" in fake.calls
+
+
+def test_const_shift_state_with_ndims_3_matches_the_tensor_stencil_oracle(fake):
+    """a const-shift state with ndims = 3 (the N-D tensor stencil of src/interpolation.jl:212-231 for N = 3) runs as
+    three 1-D sweeps (a fused pair + one sweep on the GPU); host sequencing checked over the test double"""
+    import slb200 as S
+    from oracle import refmodel as R
+
+    def build(M):
+        ms = (M.UniformMesh(0.0, 1.0, 12), M.UniformMesh(0.0, 1.0, 10), M.UniformMesh(0.0, 1.0, 8))
+        adv = M.Advection(ms, [M.Lagrange(5), M.Lagrange(5), M.Lagrange(3)], 0.01, [([3, 1, 2], 3, 1, True)], tab_coef=[0.01])
+        rng = np.random.default_rng(9)
+        return M.AdvectionData(adv, np.asfortranarray(rng.random((12, 10, 8))), M.gettranslationvar((130.0, -270.0, 55.0)))
+
+    g, o = build(S), build(R)
+    for _ in range(2):
+        assert S.advection(g) == R.advection(o)
+    a, b = g.getdata(), o.data
+    assert float(np.max(np.abs(a - b)) / np.max(np.abs(b))) <= 1e-13

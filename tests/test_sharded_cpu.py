@@ -66,3 +66,24 @@ def test_halo_exchange_and_handle_allgather_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True, True) for r in range(world)]
+
+
+def test_estimate_max_shift_sizes_the_halo_from_the_initial_field():
+    """halo sizing of the sharded driver (host numpy restatement of compute_elfield!): the 2D2V example's initial
+    field gives velocity shifts of 2/3 cell at 128 points per velocity dim (Strang: dt/2 per v stage) -- halo 4 for
+    order 7 -- and twice that at 256 points -- halo 6 for order 9"""
+    import math
+
+    import slb200 as S
+
+    for n, order, amax, halo in ((128, 7, 2 / 3, 4), (256, 9, 4 / 3, 6)):
+        ms = (S.UniformMesh(0.0, 4 * math.pi, n), S.UniformMesh(0.0, 4 * math.pi, n), S.UniformMesh(-6.0, 6.0, n), S.UniformMesh(-6.0, 6.0, n))
+        tabst = [([3, 4, 1, 2], 1, 1, True), ([4, 3, 1, 2], 1, 1, True), ([1, 2, 4, 3], 1, 2, True), ([2, 1, 3, 4], 1, 2, True)]
+        adv = S.Advection(ms, [S.Lagrange(order)] * 4, 0.1, tabst)
+        fsp = lambda x: 0.5 * np.cos(x / 2) + 1
+        fv = lambda v: np.exp(-v**2 / 2) / math.sqrt(2 * math.pi)
+        dv = ms[2].step * ms[3].step
+        rho = np.multiply.outer(fsp(ms[0].points), fsp(ms[1].points)) * (fv(ms[2].points).sum() * fv(ms[3].points).sum() * dv)
+        raw = H.estimate_max_shift(adv, rho, margin=1.0)
+        assert abs(raw - max(1.0, amax)) < 2e-3
+        assert H.halo_width(order, H.estimate_max_shift(adv, rho)) == halo
