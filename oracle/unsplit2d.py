@@ -175,10 +175,54 @@ def advection_single_state(advd):
     (src/advection.jl:594-619, :703-704): f = interpolate(data, bufcur); data = f; nextstate!."""
     adv = advd.adv
     st = advd.getst()
+    if len(adv.states) != 1 and st.ndims == 1:
+        return advection_split_points(advd)
     if len(adv.states) != 1 or st.ndims != 2 or adv.N != 2 or st.perm != [1, 2]:
         raise NotImplementedError("oracle: per-point shifts are covered for one 2-D state ([1, 2], 2, 1, false)")
     initcoef(advd)
     advd.data[...] = interpolate_points(advd.data, advd.bufcur, adv.t_interp, adv.nthreads)
+    return advd.nextstate()
+
+
+def interpolate_line_points(fi, alphas, interp):
+    """interpolate!(fp, fi, dec::Function, interp_t) for N = 1 (src/interpolation.jl:401-429): every point of the
+    line has its own shift; (dint, tab) = getprecal(cache, dec(ind)) is the floor split of :381-389 and
+    fp[ind] = sum(res[window] .* tab) -- rounded products summed left to right."""
+    n = len(fi)
+    res = interp.sol(np.ascontiguousarray(fi, dtype=np.float64)) if interp.kind in (R.BSPLINE_LU, R.BSPLINE_FFT) else fi
+    p = interp.order
+    out = np.empty(n)
+    for i in range(n):
+        a = float(alphas[i])
+        dint = int(np.floor(a))
+        w = interp.getprecal(a - dint)
+        acc = res[(i + dint - p // 2) % n] * w[0]
+        for j in range(1, p + 1):
+            acc = acc + res[(i + dint - p // 2 + j) % n] * w[j]
+        out[i] = acc
+    return out
+
+
+def advection_split_points(advd):
+    """advection! for a SPLIT state with per-point shifts, e.g. [([1, 2], 1, 1, false), ([2, 1], 1, 2, false)] -- the
+    split form of the quasi-geostrophic driver (src/advection.jl:633-645 with getalpha(parext, self, indext, indbuf),
+    src/quasigeostrophic.jl:126-135): every line along dim perm[1] is interpolated with the shifts
+    bufcur[ind][invp[1]] of its own points.  2-D grids, NoTimeAlg."""
+    adv = advd.adv
+    st = advd.getst()
+    if adv.N != 2 or st.ndims != 1 or adv.timealg != R.NoTimeAlg:
+        raise NotImplementedError("oracle: split per-point states are covered for 2-D grids without a time algorithm")
+    advd.parext.initcoef(advd)
+    d, comp = st.perm[0] - 1, st.invp[0] - 1
+    interp = adv.t_interp[d]
+    out = np.empty_like(advd.data)
+    if d == 0:
+        for j in range(adv.sizeall[1]):
+            out[:, j] = interpolate_line_points(np.ascontiguousarray(advd.data[:, j]), advd.bufcur[:, j, comp], interp)
+    else:
+        for i in range(adv.sizeall[0]):
+            out[i, :] = interpolate_line_points(np.ascontiguousarray(advd.data[i, :]), advd.bufcur[i, :, comp], interp)
+    advd.data[...] = out
     return advd.nextstate()
 
 

@@ -321,12 +321,65 @@ def initcoef(advd):
         interpbufc(advd.t_bufc, advd.bufcur, interps, None, fl)
 
 
+_IDENTITY = None
+
+
+def _identity_interp():
+    """Lagrange(1): weights (1 - t, t) -- with a zero shift exactly (1, 0), i.e. the identity along that dim"""
+    global _IDENTITY
+    if _IDENTITY is None:
+        from .interp import Lagrange
+
+        _IDENTITY = Lagrange(1)
+    return _IDENTITY
+
+
+def advection_split_points(advd):
+    """advection! for a SPLIT state whose shifts vary per point, e.g. [([1, 2], 1, 1, false), ([2, 1], 1, 2, false)] --
+    the split form of the quasi-geostrophic driver (src/advection.jl:633-645 with the 4-argument getalpha,
+    src/quasigeostrophic.jl:126-135): every line along dim perm[1] is interpolated with the shifts
+    bufcur[ind][invp[1]] of its own points.  On the device this is the per-point 2-D kernel (slb_interp2d_points)
+    with the swept dim's displacement plane and an exact identity (Lagrange(1) at zero shift: weights (1, 0)) along
+    the other dim -- the same sum of the same products, so SLB_SWEEP_EXACT stays bit-identical to the 1-D stencil."""
+    adv = advd.adv
+    st = advd.getst()
+    if adv.N != 2 or st.ndims != 1:
+        raise NotImplementedError("split states with per-point shifts are on the B200 path for 2-D grids (SURVEY.md 8f)")
+    if adv.timealg != NoTimeAlg:
+        raise NotImplementedError("the Adams-Bashforth time algorithms drive the unsplit state only")
+    L = _lib.lib()
+    advd.flush()
+    advd.parext.initcoef(advd)
+    if advd.bufcur is None:
+        raise RuntimeError("the provider's initcoef must set advd.bufcur for states with per-point shifts")
+    n1, n2 = adv.sizeall
+    d, comp = st.perm[0] - 1, st.invp[0] - 1
+    pb = n1 * n2 * 8
+    dec = DeviceField(advd.ctx, n1, n2, 2)
+    src_plane = C.c_void_p(advd.bufcur.ptr.value + comp * pb)
+    _lib.check(L.slb_memcpy_d2d(advd.ctx.h, C.c_void_p(dec.ptr.value + d * pb), src_plane, pb))
+    zero = (C.c_double * 1)(0.0)
+    _lib.check(L.slb_lincomb(advd.ctx.h, C.c_void_p(dec.ptr.value + (1 - d) * pb), 1, zero, (C.c_void_p * 1)(src_plane.value), n1 * n2))
+    interps = list(adv.t_interp)
+    interps[1 - d] = _identity_interp()
+    back = DeviceField.view(advd.ctx, n1, n2, 1, C.c_void_p(L.slb_grid_back(advd.grid)))
+    try:
+        interpolate_points(back, advd.data_field(), dec, interps, advd.flags)
+    finally:
+        dec.free()
+    _lib.check(L.slb_grid_swap(advd.grid))
+    advd._linesum_dim = None
+    return advd.nextstate()
+
+
 def advection_single_state(advd):
     """advection! for an Advection with ONE state whose shifts vary per point, e.g.
     [([1, 2], 2, 1, false)] (src/advection.jl:594-619, :703-704; test/test_poisson2d.jl:197,
     test/test_swirling.jl:207): data <- interpolate(data, bufcur); nextstate!."""
     adv = advd.adv
     st = advd.getst()
+    if len(adv.states) != 1 and st.ndims == 1:
+        return advection_split_points(advd)
     if len(adv.states) != 1 or adv.N != 2 or st.ndims != 2 or st.perm != [1, 2]:
         raise NotImplementedError(
             "per-point shifts are on the B200 path for one unsplit 2-D state ([1, 2], 2, 1, false) (SURVEY.md 8f-1)")

@@ -110,3 +110,41 @@ def test_const_shift_state_with_ndims_3_matches_the_tensor_stencil_oracle(fake):
         assert S.advection(g) == R.advection(o)
     a, b = g.getdata(), o.data
     assert float(np.max(np.abs(a - b)) / np.max(np.abs(b))) <= 1e-13
+
+
+def _sqg_split(M, sz, order, split, nbdt, t_max=10000.0):
+    """the split form of test/test_quasigeostrophic.jl:45-58: tabst = [([1, 2], 1, 1, false), ([2, 1], 1, 2, false)]"""
+    mx, my = M.UniformMesh(0.0, 1e6, sz[0]), M.UniformMesh(0.0, 1e6, sz[1])
+    dt = t_max / nbdt
+    adv = M.Advection((mx, my), [M.Lagrange(order), M.Lagrange(order)], dt, [([1, 2], 1, 1, False), ([2, 1], 1, 2, False)],
+                      tab_coef=split(dt))
+    pv = M.getgeovar(adv)
+    advd = M.AdvectionData(adv, np.zeros(sz), pv)
+    pv.initdata(advd)
+    return advd
+
+
+@pytest.mark.parametrize("split", ["standardsplit", "strangsplit"])
+def test_quasigeostrophic_split_form_host_logic(fake, split):
+    """split states with per-point shifts (src/advection.jl:633-645, src/quasigeostrophic.jl:126-135): the host
+    sequencing of the product (displacement plane of the swept dim + exact identity along the other dim, through the
+    per-point 2-D entry point) against the oracle's line-by-line restatement, over the test double"""
+    import slb200 as S
+    from oracle import refmodel as R
+    from oracle import unsplit2d as U
+
+    class MO:   # the oracle's module surface for this driver
+        UniformMesh, Lagrange, Advection, AdvectionData = R.UniformMesh, R.Lagrange, R.Advection, R.AdvectionData
+        getgeovar = staticmethod(U.getgeovar)
+
+    g = _sqg_split(S, (32, 24), 5, getattr(S, split), 4)
+    o = _sqg_split(MO, (32, 24), 5, getattr(R, split), 4)
+    assert g.adv.nbstates == o.adv.nbstates
+    for _ in range(2):
+        more = True
+        while more:
+            more = S.advection(g)
+            assert more == R.advection(o)
+            a, b = g.getdata(), o.data
+            assert float(np.max(np.abs(a - b)) / np.max(np.abs(b))) <= 1e-12
+    assert g.time_cur == o.time_cur
