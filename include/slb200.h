@@ -300,6 +300,15 @@ int slb_grid_set_linesum(slb_grid* g, double* linesum_dev);
 int slb_charge_density_from(slb_ctx* ctx, const double* f_dev, int64_t nsp_total, int64_t nv_total, double dv,
                             double* rho_dev, int subtract_mean);
 
+/* Charge density after a SPACE pass without another pass over f: when `rhopart_dev` is set, the next pair-fused
+ * pass whose first sweep runs along dim 0 (x1 x2 of a 2D2V grid) processes several passive (velocity) points per
+ * thread block and also stores their sums per space point: slb_grid_rhopart_planes() partial planes
+ * [plane][prod(space extents)], 1/4 of the bytes of f.  slb_vp_field_solve(plan, rhopart_dev, planes, dv, ...) then
+ * reduces those instead of f (fixed summation order: reproducible).  The pass falls back to the plain kernel (0
+ * planes) when the combination is not supported or the buffer is too small (capacity: numel / 2 doubles suffices). */
+int slb_grid_set_rhopart(slb_grid* g, double* rhopart_dev, int64_t capacity_doubles);
+int64_t slb_grid_rhopart_planes(const slb_grid* g);
+
 /* PoissonConst (src/poisson.jl:35-59): fctv_imag[x] = imag part of fctv_k[x]
  * (src/poisson.jl:7-15), each prod(extents) doubles, column-major, host pointers. */
 int slb_poisson_create(slb_ctx* ctx, int nsp, const int64_t* extents, const double* const* fctv_imag,

@@ -51,6 +51,8 @@ struct slb_grid {
     double *front, *back;
     bool owned;
     double* linesum;  // optional: per-line sums of the next strided sweeps' outputs
+    double* rhopart;  // optional: partial charge planes written by the next fused space pass (slb_grid_set_rhopart)
+    int64_t rhopart_cap, rhopart_planes;
 };
 
 struct slb_interp {
@@ -305,6 +307,8 @@ static int grid_init(slb_ctx* c, int nd, const int64_t* ext, slb_grid** out)
     g->front = g->back = nullptr;
     g->owned = false;
     g->linesum = nullptr;
+    g->rhopart = nullptr;
+    g->rhopart_cap = g->rhopart_planes = 0;
     *out = g;
     return SLB_OK;
 }
@@ -371,6 +375,17 @@ extern "C" int slb_grid_set_linesum(slb_grid* g, double* dev)
     g->linesum = dev;
     return SLB_OK;
 }
+
+extern "C" int slb_grid_set_rhopart(slb_grid* g, double* dev, int64_t capacity_doubles)
+{
+    if (!g) return fail(SLB_E_ARG, "grid is NULL");
+    g->rhopart = dev;
+    g->rhopart_cap = dev ? capacity_doubles : 0;
+    g->rhopart_planes = 0;
+    return SLB_OK;
+}
+
+extern "C" int64_t slb_grid_rhopart_planes(const slb_grid* g) { return g ? g->rhopart_planes : 0; }
 
 extern "C" double* slb_grid_front(const slb_grid* g) { return g ? g->front : nullptr; }
 extern "C" double* slb_grid_back(const slb_grid* g) { return g ? g->back : nullptr; }
@@ -1075,6 +1090,7 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     const bool cc = (dimA == 0);
     int gg, ta, full;
     const int64_t nc_even = (ncross + 1) & ~(int64_t)1;
+    g->rhopart_planes = 0;
     if (cc) {
         if (nc_even / 2 <= SLB_FUSED_MAXTHREADS) {
             full = 1;
@@ -1083,6 +1099,17 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
             gg = (int)(want < 1 ? 1 : want);
             if (gg > np) gg = (int)np;
             while ((int64_t)gg * ta / 2 > SLB_FUSED_MAXTHREADS) --gg;
+            // partial charge planes (slb_grid_set_rhopart): blocks of several passive points that share sweep B's shift
+            if (g->rhopart && mode == SLB_FUSED_PLAIN && !(flags & SLB_SWEEP_EXACT) && in_nblocks == 1 && out_nblocks == 1 && !out_bases &&
+                fa.aBlo == 0 && env_ll("SLB_FUSED_RHO", 1) != 0) {
+                int gr = (int)env_ll("SLB_FUSED_RHO_G", 4);
+                while (gr > 1 && ((int64_t)gr * ta / 2 > SLB_FUSED_MAXTHREADS || fa.elo % (unsigned)gr != 0)) gr >>= 1;
+                const int64_t planes = np / (gr > 0 ? gr : 1);
+                if (gr >= 2 && planes * ncross * nmarch <= g->rhopart_cap) {
+                    mode = SLB_FUSED_RHO;
+                    gg = gr;
+                }
+            }
         } else {
             full = 0;
             ta = 512;
@@ -1169,7 +1196,11 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     }
     const int64_t nblk = (int64_t)fa.ntile_c * ((np + gg - 1) / gg);
     if (nblk >= 0x7fffffffLL) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: too many blocks");
-    const size_t smem = slb_fused_smem_bytes(fa.nrows_max, gg);
+    size_t smem = slb_fused_smem_bytes(fa.nrows_max, gg);
+    if (mode == SLB_FUSED_RHO) {
+        fa.rhopart = g->rhopart;
+        smem += ((size_t)2 * 2 * gg * ta + 2) * sizeof(double);
+    }
     if (smem > 200 * 1024) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: tile does not fit shared memory");
     const bool exact = (flags & SLB_SWEEP_EXACT) != 0;
     if ((mode == SLB_FUSED_WIN && cc) || (mode == SLB_FUSED_PSH && !cc))
@@ -1178,6 +1209,7 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
     if (lrc < 0) return fail(SLB_E_UNSUPPORTED, "slb_sweep_pair: no fused kernel for order %d, tile width %d, mode %d", P1 - 1, gg, mode);
     if (lrc != 0) return fail(SLB_E_CUDA, "slb_sweep_pair: launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
     c->launches++;
+    if (mode == SLB_FUSED_RHO) g->rhopart_planes = np / gg;
     if (out_bases) return SLB_OK;  // the result left this grid (slb_sweep_peer's convention): roles unchanged
     return slb_grid_swap(g);
 }

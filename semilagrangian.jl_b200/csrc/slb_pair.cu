@@ -28,13 +28,14 @@ template <int P1, bool EXACT, int MODE>
 static int launch2(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, bool cc, unsigned nblocks,
                    unsigned nthreads, size_t smem, cudaStream_t stream)
 {
+    if (!cc && MODE == SLB_FUSED_RHO) return -1;
     if (cc) {
         if constexpr (MODE == SLB_FUSED_WIN) return -1;  // the march dim is never dim 0's neighbour pass here
         else
             return fa.w16 ? launch1<P1, EXACT, true, 0, true, MODE>(fa, ctA, ctB, nblocks, nthreads, smem, stream)
                           : launch1<P1, EXACT, true, 0, false, MODE>(fa, ctA, ctB, nblocks, nthreads, smem, stream);
     }
-    if constexpr (MODE == SLB_FUSED_PSH) return -1;  // passive-dim pushes are built for the CC (x1 x2) pass only
+    if constexpr (MODE == SLB_FUSED_PSH || MODE == SLB_FUSED_RHO) return -1;  // built for the CC (x1 x2) pass only
     else {
         switch (fa.g) {  // g = 16 and 4 imply even strides: always 16-byte fetches (the host checks the base pointer)
         case 32: return fa.w16 ? launch1<P1, EXACT, false, 32, true, MODE>(fa, ctA, ctB, nblocks, nthreads, smem, stream) : -1;
@@ -56,6 +57,7 @@ int SLB_CAT(slb_fused_launch_p, SLB_PAIR_P1)(const FusedArgs& fa, const CoefTab&
     if (exact) return -1;  // the halo-sharded modes are instantiated for the production (FMA) arithmetic
     if (mode == SLB_FUSED_WIN) return launch2<P, false, SLB_FUSED_WIN>(fa, ctA, ctB, cc, nblocks, nthreads, smem, stream);
     if (mode == SLB_FUSED_PSH) return launch2<P, false, SLB_FUSED_PSH>(fa, ctA, ctB, cc, nblocks, nthreads, smem, stream);
+    if (mode == SLB_FUSED_RHO) return launch2<P, false, SLB_FUSED_RHO>(fa, ctA, ctB, cc, nblocks, nthreads, smem, stream);
     return -1;
 }
 

@@ -91,10 +91,17 @@ struct FusedArgs {
     double* pushL;
     double* pushR;
     int* err;
+    // MODE 3 (SLB_FUSED_RHO, CC = true, a tile is the whole cross line): the g passive points of a block share the
+    // shift of sweep B, so they emit the same march rows at the same time; every two rows the block adds its g
+    // outputs per cross index through shared memory (fixed order) and stores the sums as partial plane `block group`
+    // of rhopart[group][march][cross] -- the charge density after a space pass without another pass over f:
+    // 1/g of the bytes are re-read instead of all of them.
+    double* rhopart;
 };
 #define SLB_FUSED_PLAIN 0
 #define SLB_FUSED_WIN 1
 #define SLB_FUSED_PSH 2
+#define SLB_FUSED_RHO 3
 
 // host launcher (slb_pair.cu); returns cudaGetLastError() of the launch, or -1 when (P1, G) is not instantiated
 int slb_fused_launch(const FusedArgs& fa, const CoefTab& ctA, const CoefTab& ctB, int P1, bool exact, bool cc, int mode,
@@ -173,7 +180,7 @@ __device__ __forceinline__ void fused_weights(const CoefTab& ct, int nc, double 
 
 // G > 0: passive points per tile fixed at compile time (CC = false); G == 0: run-time fa.g (CC = true)
 // W16: rows are fetched with 16-byte cp.async (pairs of doubles; the host checks alignment)
-// MODE: SLB_FUSED_PLAIN | SLB_FUSED_WIN (CC = false only) | SLB_FUSED_PSH (see FusedArgs)
+// MODE: SLB_FUSED_PLAIN | SLB_FUSED_WIN (CC = false only) | SLB_FUSED_PSH | SLB_FUSED_RHO (CC = true only) (see FusedArgs)
 template <int P1, bool EXACT, bool CC, int G, bool W16, int MODE>
 __global__ void __launch_bounds__(SLB_FUSED_MAXTHREADS, (P1 <= 10 ? 2 : 1))  // orders <= 9: 128 registers, two blocks per SM
 k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ CoefTab ctA, const __grid_constant__ CoefTab ctB)
@@ -236,6 +243,8 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     // ---- staged row range: union over the tile's passive points --------------------------------
     const int row_elems = fa.nrows_max * g;       // one march row of the tile in shared memory
     long long* dsh = reinterpret_cast<long long*>(fsm + (size_t)D * R * row_elems);
+    double* const redbuf =   // MODE RHO: [2 parities][2 rows][g][ta], 16-byte aligned
+        reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dsh + g) + 15) & ~static_cast<uintptr_t>(15));
     if (a == 0) dsh[p] = dA;
     __syncthreads();
     long long dmin = dsh[0], dmax = dsh[0];
@@ -309,7 +318,19 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
     for (int j = 0; j < P1; ++j) winA[j] = winB[j] = 0.0;
     double lsumA = 0.0, lsumB = 0.0;
 
+    int rho_par = 0, rho_k = 0, rho_nprev = 0, rho_rowprev = 0, rho_row = 0;  // MODE RHO bookkeeping (block-uniform)
+    if (MODE == SLB_FUSED_RHO) {
+        rho_row = fa.march0 + nm - s0B;   // march index of the first emitted output (same for the whole block)
+        rho_row -= rho_row >= nm ? nm : 0;
+    }
     auto emit = [&](double accA, double accB) {
+        if (MODE == SLB_FUSED_RHO) {
+            double2 v2;
+            v2.x = act0 ? accA : 0.0;
+            v2.y = act1 ? accB : 0.0;
+            *reinterpret_cast<double2*>(redbuf + ((size_t)((rho_par * 2 + rho_k) * g + p) * ta + a)) = v2;
+            ++rho_k;
+        }
         if (MODE == SLB_FUSED_WIN) {
             // only the slab's rows are this rank's outputs; those within win_h of a slab boundary also go to the
             // neighbour's halo rows (NVLink peer stores riding inside the pass)
@@ -449,6 +470,35 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         // march-direction dot products that only involve OLD window entries are summed before the
         // barrier (same left-to-right order as slb_dot, hence bit-identical), so that after it only
         // the cross stencils and two or three dependent operations per output remain.
+        // MODE RHO: the rows the block emitted in the previous interval are complete in redbuf (the barrier just
+        // passed): add the g passive points per cross index in a fixed order and store the partial-plane rows
+        auto rho_reduce = [&]() {
+            if (MODE == SLB_FUSED_RHO) {
+                const int parp = rho_par ^ 1;
+                double* const plane = fa.rhopart + (long long)tp * ((long long)nc_ * nm);
+                for (int q = tid; q < rho_nprev * ta; q += NT) {
+                    const int k = q / ta, x = q - k * ta;
+                    if (a0 + x < nc_) {
+                        const double* src = redbuf + (size_t)((parp * 2 + k) * g) * ta + x;
+                        double sacc = src[0];
+                        for (int pp = 1; pp < g; ++pp) sacc += src[(size_t)pp * ta];
+                        int row = rho_rowprev + k;
+                        row -= row >= nm ? nm : 0;
+                        plane[(long long)row * nc_ + a0 + x] = sacc;
+                    }
+                }
+            }
+        };
+        auto rho_advance = [&]() {
+            if (MODE == SLB_FUSED_RHO) {
+                rho_nprev = rho_k;
+                rho_rowprev = rho_row;
+                rho_row += rho_k;
+                rho_row -= rho_row >= nm ? nm : 0;
+                rho_k = 0;
+                rho_par ^= 1;
+            }
+        };
 #define SLB_FUSED_INTERVAL(r, EMIT0, EMIT1)                                                             \
     {                                                                                                   \
         const double pA0 = fused_partial<P1, EXACT, P1 - 1>(winA, w2, (r) + 1);                         \
@@ -458,6 +508,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         fused_cp_wait<D - 2>();                                                                         \
         __syncthreads();                                                                                \
         issue_stage();                                                                                  \
+        rho_reduce();                                                                                   \
         double xa[R][P1 + 1];                                                                           \
         _Pragma("unroll") for (int rr = 0; rr < R; ++rr)                                                \
             _Pragma("unroll") for (int q = 0; q <= P1; ++q) xa[rr][q] = sp[rr * row_elems + q * QS];    \
@@ -475,6 +526,7 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
         if (EMIT1)                                                                                      \
             emit(slb_acc<EXACT>(slb_acc<EXACT>(pA1, TA0, w2[P1 - 2]), TA1, w2[P1 - 1]),                 \
                  slb_acc<EXACT>(slb_acc<EXACT>(pB1, TB0, w2[P1 - 2]), TB1, w2[P1 - 1]));                \
+        rho_advance();                                                                                  \
     }
         // first block: the windows fill up (nsteps >= P1, so no bounds checks)
 #pragma unroll
@@ -490,6 +542,10 @@ k_sweep_fused(const __grid_constant__ FusedArgs fa, const __grid_constant__ Coef
             if (k0 + r < nsteps) SLB_FUSED_INTERVAL(r, true, (k0 + r + 1 < nsteps))
         }
 #undef SLB_FUSED_INTERVAL
+        if (MODE == SLB_FUSED_RHO) {  // the last interval's rows
+            __syncthreads();
+            rho_reduce();
+        }
     } else {
         // shifts inside the tile are too far apart to stage a common row range: every thread reads
         // its own stencil inputs from global memory (rare; correct, slower)

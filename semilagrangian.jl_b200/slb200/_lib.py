@@ -82,6 +82,8 @@ SIGNATURES = [
     ("slb_charge_density", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     ("slb_charge_density_raw", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     ("slb_grid_set_linesum", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slb_grid_set_rhopart", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    ("slb_grid_rhopart_planes", C.c_int64, [C.c_void_p]),
     ("slb_charge_density_from", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_int]),
     ("slb_subtract_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     ("slb_poisson_create", C.c_int, [C.c_void_p, C.c_int, c_int64_p, C.POINTER(c_double_p), c_void_pp]),

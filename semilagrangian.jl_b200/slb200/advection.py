@@ -148,6 +148,10 @@ class AdvectionData:
         h = C.c_void_p()
         _lib.check(_lib.lib().slb_grid_create(self.ctx.h, adv.N, _lib.i64(adv.sizeall), C.byref(h)))
         self.grid = h
+        self._rhopart = None        # device buffer for the partial charge planes of a fused space pass (see poisson.py)
+        self._rhopart_planes = 0    # planes currently held (0: none / stale)
+        # off by default: measured slower (the x1x2 pass grows by more than the charge pass it replaces)
+        self.use_rhopart = os.environ.get("SLB_RHOPART", "0") != "0"
         self._linesum = None        # device buffer for per-line output sums (see poisson.py)
         self._linesum_dim = None    # dim whose sweep produced the sums currently held, else None
         self.use_linesum = True
@@ -174,6 +178,7 @@ class AdvectionData:
         _lib.check(_lib.lib().slb_grid_upload(self.grid, host.ctypes.data_as(C.c_void_p)))
         self.ctx.sync()
         self._linesum_dim = None
+        self._rhopart_planes = 0
 
     def getdata(self, out=None):
         """getdata(advd) (src/advection.jl:317): a host copy of the device-resident array."""
@@ -206,6 +211,7 @@ class AdvectionData:
                 work.free()
         _lib.check(L.slb_grid_swap(self.grid))
         self._linesum_dim = None
+        self._rhopart_planes = 0
 
     def points_dev(self, dim0):
         p = self._points_dev.get(dim0)
@@ -250,6 +256,9 @@ class AdvectionData:
         if self._linesum is not None:
             self.ctx.free(self._linesum)
             self._linesum = None
+        if self._rhopart is not None:
+            self.ctx.free(self._rhopart)
+            self._rhopart = None
         for fld in [self.bufcur] + list(self.t_bufc):
             if fld is not None:
                 fld.free()
@@ -277,6 +286,7 @@ def _table_args(table, on_device):
 
 def _linesum_begin(advd, dim0, interp, want_linesum):
     advd._linesum_dim = None  # any sweep invalidates sums held from an earlier one
+    advd._rhopart_planes = 0
     ls_ok = want_linesum and advd.use_linesum and dim0 > 0 and interp.order + 1 <= 14 and interp.tabfct.shape[1] <= 14
     if ls_ok:
         if advd._linesum is None:
@@ -343,10 +353,21 @@ def sweep_pair(advd, stageA, stageB):
     pA, lA, _ka = _table_args(tabA, devA)
     pB, lB, _kb = _table_args(tabB, devB)
     ls_ok = _linesum_begin(advd, dB, itB, want_ls)
+    L = _lib.lib()
+    want_rho = advd.use_rhopart and bool(getattr(advd.parext, "wants_rhopart", lambda a, da, db: False)(advd, dA, dB))
+    if want_rho:
+        cap = int(np.prod(advd.adv.sizeall)) // 2
+        if advd._rhopart is None:
+            advd._rhopart = advd.ctx.malloc(cap * 8)
+        _lib.check(L.slb_grid_set_rhopart(advd.grid, advd._rhopart, cap))
     try:
-        rc = _lib.lib().slb_sweep_pair(advd.grid, int(dA), hA, pA, lA, _lib.i64(strA), float(scA), int(dB), hB, pB, lB, _lib.i64(strB),
-                                       float(scB), 1 if devA else 0, int(flags))
+        rc = L.slb_sweep_pair(advd.grid, int(dA), hA, pA, lA, _lib.i64(strA), float(scA), int(dB), hB, pB, lB, _lib.i64(strB),
+                              float(scB), 1 if devA else 0, int(flags))
+        if want_rho and rc == 0:
+            advd._rhopart_planes = int(L.slb_grid_rhopart_planes(advd.grid))
     finally:
+        if want_rho:
+            _lib.check(L.slb_grid_set_rhopart(advd.grid, None, 0))
         if ls_ok:
             _lib.check(_lib.lib().slb_grid_set_linesum(advd.grid, None))
     if rc == _lib.SLB_E_UNSUPPORTED:

@@ -112,11 +112,24 @@ class PoissonVar(AbstractExtDataAdv):
         nv = int(np.prod(self.adv.sizeall[self.Nsp:]))
         if d is not None and d >= self.Nsp:
             src, nv = advd._linesum, nv // self.adv.sizeall[d]
+        elif getattr(advd, "_rhopart_planes", 0):
+            # the fused space pass that just ran left partial planes of the charge density (1/4 of the bytes of f)
+            src, nv = advd._rhopart, advd._rhopart_planes
         else:
             src = C.c_void_p(L.slb_grid_front(advd.grid))
         arr = (C.c_void_p * self.Nsp)(*[p.value for p in self.E_dev])
         _lib.check(L.slb_vp_field_solve(self.plan, src, nv, dv, self.rho_dev, arr))
         self.has_field = True
+
+    def wants_rhopart(self, advd, dA, dB):
+        """True when the fused pass over (dA, dB) sweeps exactly the two space dims of a 2D2V grid and the NEXT
+        advection! call starts with compute_charge! (src/poisson.jl:171-174): the pass can then leave partial planes
+        of rho (slb_grid_set_rhopart) and no separate reduction over f is needed."""
+        adv = advd.adv
+        if self.type != StdPoisson or self.Nsp != 2 or sorted((dA, dB)) != [0, 1]:
+            return False
+        nxt = adv.getst(advd.state_gen + 1 if advd.state_gen < adv.nbstates else 1)
+        return nxt.perm[0] > self.Nsp and (self.Nsp + 1) in nxt.perm[: nxt.ndims]
 
     def wants_linesum(self, advd):
         """True when the NEXT advection! call starts with compute_charge! (src/poisson.jl:171-174)

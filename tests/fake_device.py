@@ -129,6 +129,12 @@ class FakeLib:
         gr["front"], gr["back"] = gr["back"], gr["front"]
         return 0
 
+    def slb_grid_set_rhopart(self, g, p, cap):
+        return 0
+
+    def slb_grid_rhopart_planes(self, g):
+        return 0  # the double never fuses pairs: no partial planes
+
     def slb_grid_set_linesum(self, g, p):
         self._g(g)["linesum"] = _addr(p)
         return 0

@@ -350,3 +350,26 @@ def test_const_shift_state_with_ndims_3_and_4():
             assert S.advection(g) == R.advection(o)
         assert relerr(g.getdata(), o.data) <= 1e-12
         assert g.n_fused >= 2   # at least one fused pair per call
+
+
+def test_partial_charge_planes_from_the_space_pass():
+    """SLB_FUSED_RHO (off by default: measured slower): the x1x2 pass leaves partial planes of the charge
+    density and the field solve reduces those instead of f -- same numbers added in another order"""
+    import slb200 as S
+
+    sz = (32, 16, 16, 16)
+    _, a = _vp_2d2v(S, sz, 7)
+    _, b = _vp_2d2v(S, sz, 7)
+    a.use_rhopart = True
+    planes = []
+    for step in range(2):
+        more = True
+        while more:
+            more = S.advection(a)
+            planes.append(a._rhopart_planes)
+        while S.advection(b):
+            pass
+        ee_a, ee_b = S.compute_ee(a), S.compute_ee(b)
+        assert abs(ee_a - ee_b) <= 1e-13 * abs(ee_b)
+    assert max(planes) == 16 * 16 // 4     # the x1x2 pass ran with four passive points per block
+    assert relerr(a.getdata(), b.getdata()) <= 1e-13
