@@ -71,7 +71,7 @@ struct slb_interp {
     double* bspstab_dev;       // tables of the split-line fused sweep (two warps per tile, slb_bspsplit.cuh), or NULL
     BspSplitTab bspstab;
     int seg_ok, wl_ok;         // segmented sweeps (slb_bspseg.cuh): block-per-tile / warp-per-line plans exist
-    BspSegTab segtab, wltab;
+    BspSegTab segtab, segtab_c, wltab;  // strided dims, dim 0, long lines
 };
 
 struct slb_poisson {
@@ -473,8 +473,8 @@ extern "C" int slb_interp_create(slb_ctx* c, int kind, int order, int64_t n, con
             BspRfHost hr;
             std::string msg2;
             if (bsprf_factor(order, n, node_vals, &hr, msg2) == SLB_OK) {
-                it->seg_ok = slb_bspseg_plan(hr, false, &it->segtab) ? 1 : 0;
-                it->wl_ok = slb_bspseg_plan(hr, true, &it->wltab) ? 1 : 0;
+                it->seg_ok = (slb_bspseg_plan(hr, false, false, &it->segtab) && slb_bspseg_plan(hr, false, true, &it->segtab_c)) ? 1 : 0;
+                it->wl_ok = slb_bspseg_plan(hr, true, false, &it->wltab) ? 1 : 0;
                 std::vector<double> v;
                 bsprf_fill(&it->bsprf, v, hr);
                 if (slb_bspfused_warps_rf(it->bsprf.ndoubles, hb.n, true) > 0) {
@@ -759,7 +759,7 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
             }
             if (imp) a.im = *imp;
             a.linesum = g->linesum;
-            a.tab = sg ? it->segtab : it->wltab;
+            a.tab = sg ? (contig ? it->segtab_c : it->segtab) : it->wltab;
             const int lrc = sg ? slb_bspseg_launch(a, it->tab, contig, c->stream) : slb_bspwline_launch(a, it->tab, c->stream);
             if (lrc > 0) return fail(SLB_E_CUDA, "slb_sweep: segmented B-spline launch failed: %s", cudaGetErrorString((cudaError_t)lrc));
             if (lrc == 0) {

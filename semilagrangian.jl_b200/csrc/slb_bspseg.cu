@@ -3,8 +3,9 @@
 #include "slb_bspseg.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
-bool slb_bspseg_plan(const BspRfHost& hr, bool wline, BspSegTab* tab)
+bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* tab)
 {
     typedef long double ld;
     const int h = hr.h, n = hr.n;
@@ -20,7 +21,12 @@ bool slb_bspseg_plan(const BspRfHost& hr, bool wline, BspSegTab* tab)
         case 16: M = 8; break;
         case 32: M = 16; break;
         case 64: M = 16; break;
-        case 128: M = 16; break;
+        case 128:
+            // measured at 128^4 (ms per sweep, M = 16 x 8 warps | M = 32 x 4 warps): strided order 11 1.42 | 1.15, order 5
+            // 0.80 | 0.70, order 3 0.70 | 0.66; dim 0 order 11 1.63 | 1.49, order 5 1.04 | 1.13, order 3 0.96 | 1.01
+            M = (!contig || h >= 4) ? 32 : 16;
+            if (getenv("SLB_SEG_M128")) M = atoi(getenv("SLB_SEG_M128"));
+            break;
         case 256: M = 32; break;
         default: return false;
         }
@@ -99,6 +105,7 @@ static int seg_launch_h(const BspSegArgs& a, const CoefTab& ct, bool contig, cud
     SLB_SEG_CASE(16, 2)
     SLB_SEG_CASE(16, 4)
     SLB_SEG_CASE(16, 8)
+    SLB_SEG_CASE(32, 4)
     SLB_SEG_CASE(32, 8)
 #undef SLB_SEG_CASE
     return -1;

@@ -62,7 +62,7 @@ struct BspSegArgs {
 };
 
 // host: table from the recursive-filter factorisation; returns false when (order, n) is not on this path
-bool slb_bspseg_plan(const BspRfHost& hr, bool wline, BspSegTab* tab);
+bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* tab);
 // returns 0 on success, -1 when no kernel is instantiated for the combination, else cudaGetLastError()
 int slb_bspseg_launch(const BspSegArgs& a, const CoefTab& ct, bool contig, cudaStream_t stream);
 int slb_bspwline_launch(const BspSegArgs& a, const CoefTab& ct, cudaStream_t stream);
