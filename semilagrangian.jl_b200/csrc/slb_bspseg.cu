@@ -72,8 +72,7 @@ bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* ta
 static size_t seg_smem(int h, int M, int S, bool contig)
 {
     const int P1 = 2 * h + 2, HALO = P1 - 1, HM = HALO < M ? HALO : M;
-    const int NQ = (M / 4 + 1) & ~1;
-    size_t d = (size_t)h * (4 + NQ) + (size_t)h * S + (size_t)h * M + (size_t)2 * S * 32 + (size_t)P1 * 32 + (size_t)S * HM * 32 + (size_t)S * 32 + 64;
+    size_t d = (size_t)h * S + (size_t)h * M + (size_t)2 * S * 32 + (size_t)P1 * 32 + (size_t)S * HM * 32 + (size_t)S * 32 + 64;
     if (contig) d += (size_t)M * S * 33;
     return d * sizeof(double);
 }

@@ -90,14 +90,12 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
 {
     constexpr int P1 = 2 * H + 2, HALO = P1 - 1, HM = HALO < M ? HALO : M;  // HM: values a segment lends to its predecessors
     constexpr int TP = 33;                                                    // tile pitch (dim 0)
-    constexpr int NB = M / 4, NQ = (NB + 1) & ~1;  // sub-segments of 4 rows; their z^(4b) constants, padded to pairs
-    static_assert(M % 4 == 0, "segments are processed as sub-segments of 4 rows");
+    static_assert(M % 2 == 0, "constants are fetched in pairs");
     extern __shared__ __align__(16) double ssm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = M * S;
-    double* zps = ssm;                       // [H][4 + NQ]  z_k^1 .. z_k^4 | z_k^(4b), b < NB
-    double* czs = zps + H * (4 + NQ);        // [H][S]   z_k^(M m) / (1 - z_k^n), zero beyond the kept terms
-    double* zpl = czs + H * S;               // [H][M]   z_k^(j+1) (orders 9, 11: one chain per segment, see below)
+    double* czs = ssm;                       // [H][S]   z_k^(M m) / (1 - z_k^n), zero beyond the kept terms
+    double* zpl = czs + H * S;               // [H][M]   z_k^(j+1)
     double* Lbuf = zpl + H * M;              // [2][S][32]
     double* wsm = Lbuf + 2 * S * 32;         // [P1][32]
     double* hal = wsm + P1 * 32;             // [S][HM][32]
@@ -105,10 +103,6 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     double* tts = lsb + S * 32;              // [32]      fractional shift of each line
     int* s0s = reinterpret_cast<int*>(tts + 32);  // [32] start index of each line's stencil window (64 ints reserved)
     double* tile = tts + 64;                 // [n][33] (dim 0 only)
-    for (int q = threadIdx.x; q < H * (4 + NQ); q += 32 * S) {
-        const int k = q / (4 + NQ), r = q % (4 + NQ);
-        zps[q] = r < 4 ? fa.tab.zp[k][r] : (r == 4 ? 1.0 : (r - 4 < NB ? fa.tab.zp[k][4 * (r - 4) - 1] : 0.0));
-    }
     for (int q = threadIdx.x; q < H * S; q += 32 * S) czs[q] = (q % S) < fa.tab.nm[q / S] ? fa.tab.cz[q / S][q % S] : 0.0;
     for (int q = threadIdx.x; q < H * M; q += 32 * S) zpl[q] = fa.tab.zp[q / M][q % M];
     const long long line0 = (long long)blockIdx.x * 32;
@@ -129,7 +123,9 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     // ---- load: M rows of this lane's line into registers ------------------------------------------------------
     double v[M];
     if (CONTIG) {
-        // the 32 lines of the tile are contiguous runs of n doubles: coalesced reads, transposed into the tile
+        // the 32 lines of the tile are contiguous runs of n doubles: coalesced reads, transposed into the tile.
+        // (Reading M consecutive rows per thread straight from global memory -- 32 lines per warp request, half a
+        // sector each, the other half left to L1 -- was not faster: order 11 1.48 -> 1.50 ms, order 5 1.04 -> 1.21.)
         for (int j = w; j < 32; j += S) {
             const long long lj = line0 + j;
             if (lj < fa.nlines) {
@@ -162,73 +158,20 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
         for (int j = 0; j < M; ++j) v[j] = tile[(w * M + j) * TP + lane];
     }
     // ---- recursive-filter cascade ------------------------------------------------------------------------------
-    // Every stage: (1) each sub-segment of 4 rows runs the recurrence from a zero state (NB independent chains of 3
-    // FMAs); (2) e[b] = state entering sub-segment b if the SEGMENT started from zero (a chain of NB FMAs with z^4);
-    // its continuation L is the segment's contribution to the ring; (3) after the exchange, the true state entering
-    // sub-segment b is e[b] + z^(4b) c, and row i of it is corrected by z^(i+1) times that.  Same FMA count as one
-    // 15-deep chain plus a 16-term correction, a quarter of the dependent latency and 6 constants instead of 16.
-    // Orders 9 and 11 (H >= 4) measured faster with ONE chain per segment and a 16-constant correction (1.41 vs 1.50 ms
-    // at order 11: the sub-segment form trades latency for instructions, and these orders are issue-bound).
-    constexpr bool ONECHAIN = H >= 4;
+    // Every stage: the segment runs the recurrence from a ZERO state (a chain of M - 1 FMAs), publishes the value that
+    // leaves it, and after the exchange row j is corrected by z^(j+1) times the state that really entered the segment.
+    // (A variant that applied the same split once more to sub-segments of 4 rows -- shorter chains, 6 constants per
+    // stage -- was slower: 1.32 vs 1.15 ms at order 11; the kernel is bound by instruction issue, not by latency.)
 #pragma unroll
     for (int k = 0; k < 2 * H; ++k) {
         const bool causal = k < H;           // causal stages y[i] = x[i] + z y[i-1], then anticausal y[i] = x[i] + z y[i+1]
         const int kk = causal ? k : k - H;
 #define SLB_IX(t) (causal ? (t) : (M - 1 - (t)))  // the anticausal stages are the causal ones on the reversed segment
-        if constexpr (ONECHAIN) {
-            const double z = fa.tab.z[kk];
+        const double z = fa.tab.z[kk];
 #pragma unroll
-            for (int j = 1; j < M; ++j) v[SLB_IX(j)] = fma(z, v[SLB_IX(j - 1)], v[SLB_IX(j)]);
-            double* Lb = Lbuf + (k & 1) * S * 32;
-            Lb[w * 32 + lane] = v[SLB_IX(M - 1)];
-            __syncthreads();
-            if (k == 0) {
-                const double tt = tts[lane];
-                for (int j = w; j < P1; j += S) wsm[j * 32 + lane] = bspseg_weight(ct, fa.nc, j, tt) * fa.tab.invC;
-            }
-            double c = 0.0;
-#pragma unroll
-            for (int m = 0; m < S; ++m) {
-                int ws = causal ? w - 1 - m : w + 1 + m;
-                ws = ws < 0 ? ws + S : (ws >= S ? ws - S : ws);
-                c = fma(czs[kk * S + m], Lb[ws * 32 + lane], c);
-            }
-            const double2* zp2 = reinterpret_cast<const double2*>(zpl + kk * M);
-#pragma unroll
-            for (int j = 0; j < M; j += 2) {
-                const double2 pz = zp2[j >> 1];
-                v[SLB_IX(j)] = fma(c, pz.x, v[SLB_IX(j)]);
-                v[SLB_IX(j + 1)] = fma(c, pz.y, v[SLB_IX(j + 1)]);
-            }
-            continue;
-        }
-        double zc[4], zq[NQ];
-        {
-            const double2* cp = reinterpret_cast<const double2*>(zps + kk * (4 + NQ));
-#pragma unroll
-            for (int q = 0; q < 2 + NQ / 2; ++q) {
-                const double2 t2 = cp[q];
-                if (q < 2) {
-                    zc[2 * q] = t2.x;
-                    zc[2 * q + 1] = t2.y;
-                } else {
-                    zq[2 * (q - 2)] = t2.x;
-                    zq[2 * (q - 2) + 1] = t2.y;
-                }
-            }
-        }
-        const double z = zc[0], z4 = zc[3];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-#pragma unroll
-            for (int i = 1; i < 4; ++i) v[SLB_IX(4 * b + i)] = fma(z, v[SLB_IX(4 * b + i - 1)], v[SLB_IX(4 * b + i)]);
-        }
-        double e[NB];
-        e[0] = 0.0;
-#pragma unroll
-        for (int b = 1; b < NB; ++b) e[b] = fma(z4, e[b - 1], v[SLB_IX(4 * b - 1)]);
+        for (int j = 1; j < M; ++j) v[SLB_IX(j)] = fma(z, v[SLB_IX(j - 1)], v[SLB_IX(j)]);
         double* Lb = Lbuf + (k & 1) * S * 32;
-        Lb[w * 32 + lane] = fma(z4, e[NB - 1], v[SLB_IX(M - 1)]);
+        Lb[w * 32 + lane] = v[SLB_IX(M - 1)];
         __syncthreads();
         if (k == 0) {
             // stencil weights: the S warps share the Horner evaluations (the shift became visible with this barrier)
@@ -237,19 +180,18 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
         }
         // state entering this segment: geometric sum over the preceding (causal) / following (anticausal) segments
         double c = 0.0;
-        {
-            const int nm = fa.tab.nm[kk];
-            int ws = w;
-            for (int m = 0; m < nm; ++m) {
-                ws = causal ? (ws == 0 ? S - 1 : ws - 1) : (ws + 1 == S ? 0 : ws + 1);
-                c = fma(czs[kk * S + m], Lb[ws * 32 + lane], c);
-            }
+#pragma unroll
+        for (int m = 0; m < S; ++m) {
+            int ws = causal ? w - 1 - m : w + 1 + m;
+            ws = ws < 0 ? ws + S : (ws >= S ? ws - S : ws);
+            c = fma(czs[kk * S + m], Lb[ws * 32 + lane], c);
         }
+        const double2* zp2 = reinterpret_cast<const double2*>(zpl + kk * M);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const double cb = fma(c, zq[b], e[b]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[SLB_IX(4 * b + i)] = fma(cb, zc[i], v[SLB_IX(4 * b + i)]);
+        for (int j = 0; j < M; j += 2) {
+            const double2 pz = zp2[j >> 1];
+            v[SLB_IX(j)] = fma(c, pz.x, v[SLB_IX(j)]);
+            v[SLB_IX(j + 1)] = fma(c, pz.y, v[SLB_IX(j + 1)]);
         }
 #undef SLB_IX
     }
