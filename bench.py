@@ -327,6 +327,41 @@ def run_configs(S, ctx, args, peak, only=None, with_oracle=True):
                     sg.energies()
                 extra["ms_per_step_graph_ee_readback_wall"] = (time.perf_counter() - t0) * 1e3 / (nsteps // 2 * 2)
                 sg.close()
+            if name.startswith("C1") and hasattr(S, "StepProgram"):
+                # the same steps as ONE persistent cooperative kernel per launch (slb_program_*): 2 recorded steps
+                # repeated nsteps / 2 times inside the kernel, ee of every step reduced on the device; its history is
+                # compared bit for bit with the stepwise driver's from the same state
+                try:
+                    rep = max(1, nsteps // 2)
+                    ga, gb = build(S)[0], build(S)[0]
+                    for gg in (ga, gb):   # one real step: its last sweep leaves the line sums the next field solve starts from
+                        while S.advection(gg):
+                            pass
+                    sp = S.StepProgram(gb, nsteps=2, repeat=rep)
+                    sp.launch()
+                    ee_prog = sp.energies()
+                    ee_step = []
+                    for _ in range(2 * rep):
+                        while S.advection(ga):
+                            pass
+                        ee_step.append(S.compute_ee(ga))
+                    extra["program_equals_stepwise_bitwise"] = bool(np.array_equal(gb.getdata(), ga.getdata()) and ee_prog == ee_step)
+                    for _ in range(2):
+                        sp.launch()
+                    ctx.sync()
+                    ctx.record(e0)
+                    for _ in range(3):
+                        sp.launch()
+                    ctx.record(e1)
+                    extra["ms_per_step_program"] = _lib.Context.elapsed_ms(e0, e1) / (3 * 2 * rep)
+                    extra["program"] = {"ops_per_2_steps": sp.nops, "grid_barriers_per_2_steps": sp.nbarriers, "blocks": sp.nblocks,
+                                        "steps_per_launch": 2 * rep,
+                                        "block0_ns_per_op_kind_wait_run": [(k, round(w), round(r)) for k, w, r in sp.profile()]}
+                    sp.close()
+                    ga.close()
+                    gb.close()
+                except Exception as exc:
+                    extra["program_error"] = f"{type(exc).__name__}: {exc}"
             g.close()
             out[name] = {"ms_per_step": ms, "Gcell_s": cells / ms / 1e6, "launches_per_step": nl,
                          "hbm_frac_per_sweep_bytes": cells * BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peak, "parity": par, "note": note, **extra}

@@ -85,6 +85,28 @@ int slb_capture_end(slb_ctx* ctx, slb_graph** out);
 int slb_graph_launch(slb_graph* g);
 void slb_graph_destroy(slb_graph* g);
 
+/* ---- whole time steps as ONE persistent kernel (step programs) ------------------------------------------------
+ * A CUDA graph still pays one kernel launch per split stage (the 1D1V example: 7 nodes, 35 us per step for 256 KB of
+ * data).  Between slb_program_begin and slb_program_end the calls slb_sweep (plain Lagrange / Hermite kinds of odd
+ * order 3..11, device-resident shift tables, no flags), slb_vp_field_solve (one power-of-two space dim) and
+ * slb_reduce_sumsq_async are recorded as a list of ops; NOTHING executes and any other compute call fails with
+ * SLB_E_UNSUPPORTED (the recording is then unusable: slb_program_end reports it and the caller falls back to
+ * slb_capture_* or to stepwise calls).  slb_program_launch runs the list `nrep` times inside one cooperative kernel
+ * with grid barriers only between dependent ops; repetition r stores the result of every recorded
+ * slb_reduce_sumsq_async at out_dev + r * out_stride (doubles).  Results are bit-identical to the stepwise calls.
+ * Like a captured graph, the recorded sequence must leave every grid's front/back roles as it found them.
+ * Replaces: the time loop of examples/vlasov-poisson-1d1v.jl:60-64 around advection! (src/advection.jl:594-704). */
+typedef struct slb_program slb_program;
+int slb_program_begin(slb_ctx* ctx);
+int slb_program_end(slb_ctx* ctx, slb_program** out);
+int slb_program_launch(slb_program* p, int nrep, int64_t out_stride);
+int slb_program_info(const slb_program* p, int* nops, int* nbarriers, int* nblocks);
+/* like slb_program_launch (the data advances), with time stamps taken by block 0 in the last repetition: per recorded op
+ * its kind (1 sweep, 2 charge partial sums, 3 field solve, 4 sum of squares), the ns block 0 waited at the barrier
+ * before it and the ns the op took in block 0; cap >= number of ops.  Synchronises. */
+int slb_program_profile(slb_program* p, int nrep, int64_t out_stride, int cap, int* kind_out, double* wait_ns_out, double* run_ns_out);
+void slb_program_destroy(slb_program* p);
+
 /* extra CUDA events on the context's stream (per-kernel timing inside bench.py) */
 int slb_event_create(slb_ctx* ctx, void** ev_out);
 int slb_event_record(slb_ctx* ctx, void* ev);

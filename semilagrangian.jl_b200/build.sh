@@ -8,7 +8,7 @@ mkdir -p "$HERE/lib" "$HERE/build"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 -ccbin /usr/bin/g++ ${SLB_NVCC_EXTRA}"
 pids=()
 objs=()
-for src in slb_api slb_pair slb_bspfused slb_bspsplit slb_bspseg slb_comm; do
+for src in slb_api slb_pair slb_bspfused slb_bspsplit slb_bspseg slb_comm slb_program; do
   [ -f "$HERE/csrc/$src.cu" ] || continue
   ( "$NVCC" $FLAGS -c -o "$HERE/build/$src.o" "$HERE/csrc/$src.cu" ) &
   pids+=($!)

@@ -22,6 +22,7 @@
 #include "slb_bspseg.cuh"
 #include "slb_field.cuh"
 #include "slb_points.cuh"
+#include "slb_program.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -110,6 +111,43 @@ static int ensure_scratch(slb_ctx* c, size_t bytes)
     CUDA_TRY(cudaMalloc(&c->scratch, want));
     c->scratch_bytes = want;
     return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// step programs (slb_program.cuh): recording state
+// ------------------------------------------------------------------------------------------
+struct ProgRange {
+    const char* p;
+    size_t bytes;
+    bool b0;   // the access is made by block 0 only (accesses of one block are ordered without a grid barrier)
+};
+struct ProgOpHost {
+    ProgOp op;
+    std::vector<ProgRange> reads, writes;
+};
+struct slb_prog_rec {
+    std::vector<ProgOpHost> ops;
+    std::vector<std::pair<slb_grid*, double*>> grids;  // grids touched and their front buffer when first seen
+    std::vector<void*> owned;                          // device buffers the program owns (partial sums)
+    int nmax_field;
+    const double* last_E;   // E output of the last recorded field solve: sweeps that use it as their shift table read the block-local copy
+    bool failed;
+};
+// compute entry points that cannot be part of a step program refuse to run while one is being recorded (nothing
+// executes during a recording: the caller falls back to stepwise calls or to a CUDA graph)
+#define NOT_RECORDABLE(ctx, name)                                                                                   \
+    do {                                                                                                            \
+        if ((ctx) && (ctx)->prog_rec) {                                                                             \
+            (ctx)->prog_rec->failed = true;                                                                         \
+            return fail(SLB_E_UNSUPPORTED, name ": this call cannot be recorded in a step program");               \
+        }                                                                                                           \
+    } while (0)
+static ProgRange prog_range(const void* p, size_t bytes, bool b0 = false) { return ProgRange{(const char*)p, bytes, b0}; }
+static void prog_note_grid(slb_prog_rec* r, slb_grid* g)
+{
+    for (auto& e : r->grids)
+        if (e.first == g) return;
+    r->grids.push_back({g, g->front});
 }
 
 // ------------------------------------------------------------------------------------------
@@ -357,6 +395,7 @@ extern "C" void slb_grid_destroy(slb_grid* g)
 extern "C" int slb_grid_upload(slb_grid* g, const double* host)
 {
     if (!g || !host) return fail(SLB_E_ARG, "slb_grid_upload: NULL argument");
+    NOT_RECORDABLE(g->ctx, "slb_grid_upload");
     CUDA_TRY(cudaMemcpyAsync(g->front, host, g->numel * sizeof(double), cudaMemcpyHostToDevice, g->ctx->stream));
     return SLB_OK;
 }
@@ -364,6 +403,7 @@ extern "C" int slb_grid_upload(slb_grid* g, const double* host)
 extern "C" int slb_grid_download(const slb_grid* g, double* host)
 {
     if (!g || !host) return fail(SLB_E_ARG, "slb_grid_download: NULL argument");
+    NOT_RECORDABLE(g->ctx, "slb_grid_download");
     CUDA_TRY(cudaMemcpyAsync(host, g->front, g->numel * sizeof(double), cudaMemcpyDeviceToHost, g->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(g->ctx->stream));
     return SLB_OK;
@@ -712,6 +752,45 @@ static int sweep_impl(slb_grid* g, int dim, const slb_interp* it, const double* 
     bool bs = (it->kind == SLB_BSPLINE_LU || it->kind == SLB_BSPLINE_FFT);
     if (bs && it->n != v.n) return fail(SLB_E_ARG, "slb_sweep: B-spline object built for n=%lld, line length is %d", (long long)it->n, v.n);
     if (v.inner >= ((long long)1 << 31) || v.outer >= ((long long)1 << 31)) return fail(SLB_E_UNSUPPORTED, "slb_sweep: view too large");
+    if (c->prog_rec) {
+        // step program: record the sweep (front -> back, roles swap) instead of launching it
+        slb_prog_rec* r = c->prog_rec;
+        if (bs || !it->fast || !slb_program_supports_p1(it->order + 1) || flags != 0 || omp || imp || (g->linesum && dim == 0) || !on_device ||
+            v.n > 4096 || g->numel > ((int64_t)1 << 24)) {
+            r->failed = true;
+            return fail(SLB_E_UNSUPPORTED, "slb_sweep: step programs record plain Lagrange / Hermite sweeps (odd orders 3..11, device-resident "
+                                           "shift tables, no flags) on small grids only");
+        }
+        ProgOpHost h;
+        memset(&h.op, 0, sizeof(h.op));
+        int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, 1, &h.op.am);
+        if (rc) {
+            r->failed = true;
+            return rc;
+        }
+        h.op.kind = SLB_OP_SWEEP;
+        h.op.in = g->front;
+        h.op.out = g->back;
+        h.op.inner = v.inner;
+        h.op.outer = v.outer;
+        h.op.n = v.n;
+        h.op.P1 = it->order + 1;
+        h.op.nc = it->nc;
+        h.op.coef = it->coef_dev;
+        h.reads.push_back(prog_range(g->front, (size_t)g->numel * sizeof(double)));
+        if (alpha_tab == r->last_E)
+            h.op.tab_local = 1;  // every block holds the field of the last solve in shared memory: no grid barrier after the solve
+        else
+            h.reads.push_back(prog_range(alpha_tab, (size_t)alpha_len * sizeof(double)));
+        h.writes.push_back(prog_range(g->back, (size_t)g->numel * sizeof(double)));
+        if (g->linesum) {
+            h.op.linesum = g->linesum;
+            h.writes.push_back(prog_range(g->linesum, (size_t)(v.inner * v.outer) * sizeof(double)));
+        }
+        prog_note_grid(r, g);
+        r->ops.push_back(h);
+        return slb_grid_swap(g);
+    }
     AlphaMap am;
     int rc = build_alpha_map(g, dim, alpha_tab, alpha_len, astr, scale, on_device, &am);
     if (rc) return rc;
@@ -973,6 +1052,7 @@ static int sweep_pair_impl(slb_grid* g, int dimA, const slb_interp* itA, const d
 {
     if (!g || !itA || !itB) return fail(SLB_E_ARG, "slb_sweep_pair: NULL argument");
     slb_ctx* c = g->ctx;
+    NOT_RECORDABLE(c, "slb_sweep_pair");
     const int nd = g->nd;
     if (dimA < 0 || dimA >= nd || dimB < 0 || dimB >= nd || dimA == dimB) return fail(SLB_E_ARG, "slb_sweep_pair: need two distinct dims in range");
     int rc = check_alpha_table(g, dimA, alphaA, alenA, astrA);
@@ -1256,6 +1336,7 @@ extern "C" int slb_halo_error(slb_ctx* c, int* flags_out)
 extern "C" int slb_presolve(slb_grid* g, int dim, const slb_interp* it)
 {
     if (!g || !it) return fail(SLB_E_ARG, "slb_presolve: NULL argument");
+    NOT_RECORDABLE(g->ctx, "slb_presolve");
     if (dim < 0 || dim >= g->nd) return fail(SLB_E_ARG, "slb_presolve: dim out of range");
     bool bs = (it->kind == SLB_BSPLINE_LU || it->kind == SLB_BSPLINE_FFT);
     if (!bs) return SLB_OK;  // sol(interp, b) = b, src/interpolation.jl:40
@@ -1289,6 +1370,7 @@ static int reduce_to_dev(slb_ctx* c, const double* dev, int64_t n, int mode, dou
 static int reduce_to_host(slb_ctx* c, const double* dev, int64_t n, int mode, double* host_out)
 {
     if (!c || !dev || !host_out || n < 1) return fail(SLB_E_ARG, "slb_reduce: bad argument");
+    NOT_RECORDABLE(c, "slb_reduce");
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = reduce_to_dev(c, dev, n, mode, 1.0, c->red_out);
     if (rc) return rc;
@@ -1304,6 +1386,24 @@ extern "C" int slb_reduce_sumsq_async(slb_ctx* c, const double* dev, int64_t n, 
 {
     if (!c || !dev || !out_dev || n < 1) return fail(SLB_E_ARG, "slb_reduce_sumsq_async: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->prog_rec) {
+        slb_prog_rec* r = c->prog_rec;
+        if (n > (int64_t)SLB_PROG_MAXSUMSQ_BLOCKS * 2048) {
+            r->failed = true;
+            return fail(SLB_E_UNSUPPORTED, "slb_reduce_sumsq_async: step programs reduce at most %d values", SLB_PROG_MAXSUMSQ_BLOCKS * 2048);
+        }
+        ProgOpHost h;
+        memset(&h.op, 0, sizeof(h.op));
+        h.op.kind = SLB_OP_SUMSQ;
+        h.op.x = dev;
+        h.op.nx = n;
+        h.op.scale = scale;
+        h.op.outp = out_dev;
+        h.reads.push_back(prog_range(dev, (size_t)n * sizeof(double), true));   // block 0 reduces
+        h.writes.push_back(prog_range(out_dev, sizeof(double), true));
+        r->ops.push_back(h);
+        return SLB_OK;
+    }
     return reduce_to_dev(c, dev, n, 1, scale, out_dev);
 }
 
@@ -1320,6 +1420,7 @@ struct slb_graph {
 extern "C" int slb_capture_begin(slb_ctx* c)
 {
     if (!c) return fail(SLB_E_ARG, "slb_capture_begin: ctx is NULL");
+    NOT_RECORDABLE(c, "slb_capture_begin");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->capture_launches0 = c->launches;
@@ -1372,11 +1473,211 @@ extern "C" void slb_graph_destroy(slb_graph* g)
     cudaGraphDestroy(g->graph);
     delete g;
 }
+// ------------------------------------------------------------------------------------------
+// step programs: whole time steps of tiny grids as ONE persistent kernel (slb_program.cuh)
+// ------------------------------------------------------------------------------------------
+struct slb_program {
+    slb_ctx* ctx;
+    ProgOp* ops_dev;
+    int nops, nbarriers, nsumsq;
+    int nblocks, nmax_field, use_cg;
+    size_t smem;
+    unsigned* bar_ctr;    // grid-barrier counter (device), never reset: generation targets are tracked in bar_done
+    unsigned bar_done;    // arrivals of all launches so far (modulo 2^32)
+    std::vector<void*> owned;
+};
+
+extern "C" int slb_program_begin(slb_ctx* c)
+{
+    if (!c) return fail(SLB_E_ARG, "slb_program_begin: ctx is NULL");
+    if (c->prog_rec) return fail(SLB_E_ARG, "slb_program_begin: a recording is already open on this context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    slb_prog_rec* r = new slb_prog_rec();
+    r->nmax_field = 0;
+    r->last_E = nullptr;
+    r->failed = false;
+    c->prog_rec = r;
+    return SLB_OK;
+}
+
+static bool prog_overlap(const ProgRange& a, const ProgRange& b) { return !(a.b0 && b.b0) && a.p < b.p + b.bytes && b.p < a.p + a.bytes; }
+static bool prog_conflict(const ProgOpHost& early, const ProgOpHost& late)
+{
+    for (const auto& w : early.writes) {
+        for (const auto& x : late.reads)
+            if (prog_overlap(w, x)) return true;  // read after write
+        for (const auto& x : late.writes)
+            if (prog_overlap(w, x)) return true;  // write after write
+    }
+    for (const auto& rd : early.reads)
+        for (const auto& x : late.writes)
+            if (prog_overlap(rd, x)) return true;  // write after read
+    return false;
+}
+
+extern "C" int slb_program_end(slb_ctx* c, slb_program** out)
+{
+    if (!c || !out) return fail(SLB_E_ARG, "slb_program_end: NULL argument");
+    *out = nullptr;
+    slb_prog_rec* r = c->prog_rec;
+    if (!r) return fail(SLB_E_ARG, "slb_program_end: no recording is open on this context");
+    c->prog_rec = nullptr;
+    // nothing ran: every grid gets its roles back; a program must leave them as it found them
+    bool odd = false;
+    for (auto& e : r->grids) {
+        if (e.first->front != e.second) {
+            odd = true;
+            slb_grid_swap(e.first);
+        }
+    }
+    auto drop = [&]() {
+        for (void* p : r->owned) cudaFree(p);
+        delete r;
+    };
+    if (r->failed || r->ops.empty()) {
+        const bool f = r->failed;
+        drop();
+        return fail(SLB_E_UNSUPPORTED, f ? "slb_program_end: the recording contains a call that step programs do not support"
+                                         : "slb_program_end: nothing was recorded");
+    }
+    if (odd) {
+        drop();
+        return fail(SLB_E_ARG, "slb_program_end: the recorded steps swap a grid's buffers an odd number of times: record an even number of steps");
+    }
+    // barriers: walk the op list twice (the program repeats) and cut wherever an op conflicts with one issued since the last cut
+    const int n = (int)r->ops.size();
+    std::vector<int> pending;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int k = 0; k < n; ++k) {
+            bool cut = false;
+            for (int j : pending)
+                if (prog_conflict(r->ops[j], r->ops[k])) cut = true;
+            if (pass == 1) r->ops[k].op.barrier_before = cut ? 1 : 0;
+            if (cut) pending.clear();
+            pending.push_back(k);
+        }
+    }
+    slb_program* pr = new slb_program();
+    pr->ctx = c;
+    pr->nops = n;
+    pr->nbarriers = pr->nsumsq = 0;
+    pr->bar_ctr = nullptr;
+    pr->ops_dev = nullptr;
+    std::vector<ProgOp> flat((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        flat[k] = r->ops[k].op;
+        pr->nbarriers += flat[k].barrier_before;
+        pr->nsumsq += flat[k].kind == SLB_OP_SUMSQ;
+    }
+    pr->owned = r->owned;
+    r->owned.clear();
+    delete r;
+    pr->ops_dev = nullptr;
+    cudaError_t e = cudaMalloc(&pr->ops_dev, (size_t)n * sizeof(ProgOp));
+    if (e == cudaSuccess) e = cudaMemcpy(pr->ops_dev, flat.data(), (size_t)n * sizeof(ProgOp), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        slb_program_destroy(pr);
+        return fail(SLB_E_CUDA, "slb_program_end: %s", cudaGetErrorString(e));
+    }
+    int nmaxf = 0;
+    for (int k = 0; k < n; ++k)
+        if (flat[k].kind == SLB_OP_FIELD1D && flat[k].ffa.n1 > nmaxf) nmaxf = flat[k].ffa.n1;
+    pr->nmax_field = nmaxf;
+    pr->smem = slb_program_smem_bytes(n, nmaxf);
+    pr->use_cg = env_ll("SLB_PROGRAM_CGSYNC", 0) != 0;
+    pr->bar_done = 0;
+    pr->bar_ctr = nullptr;
+    e = cudaMalloc(&pr->bar_ctr, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(pr->bar_ctr, 0, sizeof(unsigned));
+    if (e != cudaSuccess || pr->smem > 160 * 1024) {
+        cudaGetLastError();
+        slb_program_destroy(pr);
+        return fail(e != cudaSuccess ? SLB_E_CUDA : SLB_E_UNSUPPORTED, "slb_program_end: %s", e != cudaSuccess ? cudaGetErrorString(e) : "too many recorded ops for one program");
+    }
+    long long nb = env_ll("SLB_PROGRAM_BLOCKS", 32);
+    if (nb > c->sm_count) nb = c->sm_count;  // cooperative launch: every block resident (one per SM is always possible)
+    if (nb < 1) nb = 1;
+    pr->nblocks = (int)nb;
+    *out = pr;
+    return SLB_OK;
+}
+
+extern "C" int slb_program_launch(slb_program* p, int nrep, int64_t out_stride)
+{
+    if (!p || nrep < 1 || out_stride < 0) return fail(SLB_E_ARG, "slb_program_launch: bad argument");
+    slb_ctx* c = p->ctx;
+    NOT_RECORDABLE(c, "slb_program_launch");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int rc = slb_program_run(p->ops_dev, p->nops, nrep, (long long)out_stride, p->nmax_field, p->bar_ctr, p->bar_done, p->use_cg,
+                                   nullptr, p->nblocks, p->smem, c->stream);
+    if (rc != 0) return fail(SLB_E_CUDA, "slb_program_launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (!p->use_cg) p->bar_done += (unsigned)p->nbarriers * (unsigned)nrep * (unsigned)p->nblocks;
+    c->launches++;
+    return SLB_OK;
+}
+
+// One more launch (nrep repetitions, advancing the data like slb_program_launch) with time stamps taken by block 0 in
+// the LAST repetition: per op, the nanoseconds block 0 waited at the barrier before it and the nanoseconds the op took
+// in block 0; kind_out[k] = the op's kind (1 sweep, 2 charge partial sums, 3 field solve, 4 sum of squares).
+extern "C" int slb_program_profile(slb_program* p, int nrep, int64_t out_stride, int cap, int* kind_out, double* wait_ns_out, double* run_ns_out)
+{
+    if (!p || nrep < 1 || !kind_out || !wait_ns_out || !run_ns_out || cap < p->nops) return fail(SLB_E_ARG, "slb_program_profile: bad argument");
+    slb_ctx* c = p->ctx;
+    NOT_RECORDABLE(c, "slb_program_profile");
+    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned long long* prof = nullptr;
+    CUDA_TRY(cudaMalloc(&prof, (size_t)3 * p->nops * sizeof(unsigned long long)));
+    const int rc = slb_program_run(p->ops_dev, p->nops, nrep, (long long)out_stride, p->nmax_field, p->bar_ctr, p->bar_done, p->use_cg, prof,
+                                   p->nblocks, p->smem, c->stream);
+    if (rc != 0) {
+        cudaFree(prof);
+        return fail(SLB_E_CUDA, "slb_program_profile: %s", cudaGetErrorString((cudaError_t)rc));
+    }
+    if (!p->use_cg) p->bar_done += (unsigned)p->nbarriers * (unsigned)nrep * (unsigned)p->nblocks;
+    c->launches++;
+    std::vector<unsigned long long> h((size_t)3 * p->nops);
+    std::vector<ProgOp> ops((size_t)p->nops);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ops.data(), p->ops_dev, ops.size() * sizeof(ProgOp), cudaMemcpyDeviceToHost);
+    cudaFree(prof);
+    if (e != cudaSuccess) return fail(SLB_E_CUDA, "slb_program_profile: %s", cudaGetErrorString(e));
+    for (int k = 0; k < p->nops; ++k) {
+        kind_out[k] = ops[k].kind;
+        wait_ns_out[k] = (double)(h[3 * k + 1] - h[3 * k]);
+        run_ns_out[k] = (double)(h[3 * k + 2] - h[3 * k + 1]);
+    }
+    return SLB_OK;
+}
+
+extern "C" int slb_program_info(const slb_program* p, int* nops, int* nbarriers, int* nblocks)
+{
+    if (!p) return fail(SLB_E_ARG, "slb_program_info: program is NULL");
+    if (nops) *nops = p->nops;
+    if (nbarriers) *nbarriers = p->nbarriers;
+    if (nblocks) *nblocks = p->nblocks;
+    return SLB_OK;
+}
+
+extern "C" void slb_program_destroy(slb_program* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->ops_dev) cudaFree(p->ops_dev);
+    if (p->bar_ctr) cudaFree(p->bar_ctr);
+    for (void* q : p->owned) cudaFree(q);
+    delete p;
+}
+
 extern "C" int slb_reduce_sum(slb_ctx* c, const double* dev, int64_t n, double* host_out) { return reduce_to_host(c, dev, n, 0, host_out); }
 
 extern "C" int slb_subtract_mean(slb_ctx* c, double* dev, int64_t n)
 {
     if (!c || !dev || n < 1) return fail(SLB_E_ARG, "slb_subtract_mean: bad argument");
+    NOT_RECORDABLE(c, "slb_subtract_mean");
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = reduce_to_dev(c, dev, n, 0, 1.0 / (double)n, c->red_out + 1);
     if (rc) return rc;
@@ -1408,6 +1709,7 @@ extern "C" int slb_charge_density_from(slb_ctx* c, const double* f_dev, int64_t 
 
 static int charge_from(slb_ctx* c, const double* fsrc, long long ns, long long nv, double dv, double* rho_dev)
 {
+    NOT_RECORDABLE(c, "slb_charge_density");
     CUDA_TRY(cudaSetDevice(c->device));
     long long xt = (ns + 31) / 32;
     // enough blocks to fill the machine a few times over, at least 64 velocity rows per block
@@ -1444,6 +1746,7 @@ extern "C" int slb_kinetic_energy(slb_grid* g, int nsp, const double* vsq_dev, d
     if (!g || !vsq_dev || !host_out) return fail(SLB_E_ARG, "slb_kinetic_energy: NULL argument");
     if (nsp < 1 || nsp >= g->nd) return fail(SLB_E_ARG, "slb_kinetic_energy: nsp out of range");
     slb_ctx* c = g->ctx;
+    NOT_RECORDABLE(c, "slb_kinetic_energy");
     CUDA_TRY(cudaSetDevice(c->device));
     long long ns = 1, nv = 1;
     for (int d = 0; d < nsp; ++d) ns *= g->ext[d];
@@ -1577,6 +1880,7 @@ extern "C" int slb_poisson_solve(slb_poisson* p, const double* rho_dev, double* 
 {
     if (!p || !rho_dev || !E_dev) return fail(SLB_E_ARG, "slb_poisson_solve: NULL argument");
     slb_ctx* c = p->ctx;
+    NOT_RECORDABLE(c, "slb_poisson_solve");
     CUDA_TRY(cudaSetDevice(c->device));
     const int nsp = p->nsp;
     for (int x = 0; x < nsp; ++x)
@@ -1623,6 +1927,7 @@ static int field_from_partial(slb_poisson* p, const double* partial, int nchunk,
                               double* const* E_dev)
 {
     slb_ctx* c = p->ctx;
+    NOT_RECORDABLE(c, "slb_poisson_solve");
     if (p->fft_ok && env_ll("SLB_FIELD_FFT", 1) != 0) {
         FieldFftArgs fa;
         memset(&fa, 0, sizeof(fa));
@@ -1730,6 +2035,67 @@ extern "C" int slb_vp_field_solve(slb_poisson* p, const double* f_dev, int64_t n
     slb_ctx* c = p->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     const long long ns = p->ntot, nv = nv_total;
+    if (c->prog_rec) {
+        // step program: the same two stages (K4 partial sums, then the one-warp 1-D field solve) as two ops
+        slb_prog_rec* r = c->prog_rec;
+        if (p->nsp != 1 || !p->fft_ok || ns > 1024 || env_ll("SLB_FIELD_FFT", 1) == 0) {
+            r->failed = true;
+            return fail(SLB_E_UNSUPPORTED, "slb_vp_field_solve: step programs record field solves over ONE power-of-two space dim (<= 1024 points)");
+        }
+        long long xt = (ns + 31) / 32;
+        long long want = (long long)c->sm_count * 16;
+        long long nchunk = (want + xt - 1) / xt;
+        long long maxchunk = (nv + 63) / 64;
+        if (nchunk > maxchunk) nchunk = maxchunk;
+        if (nchunk < 1) nchunk = 1;
+        if (nchunk > 65535) nchunk = 65535;
+        long long chunk = (nv + nchunk - 1) / nchunk;
+        nchunk = (nv + chunk - 1) / chunk;
+        const double* partial = f_dev;   // nv == 1 (line sums of a velocity sweep): K4's partial sums ARE the input (0 + x = x)
+        if (nv > 1) {
+            double* pbuf = nullptr;
+            CUDA_TRY(cudaMalloc(&pbuf, (size_t)(nchunk * ns) * sizeof(double)));
+            r->owned.push_back(pbuf);
+            partial = pbuf;
+            ProgOpHost h;
+            memset(&h.op, 0, sizeof(h.op));
+            h.op.kind = SLB_OP_CHARGE;
+            h.op.f = f_dev;
+            h.op.ns = ns;
+            h.op.nv = nv;
+            h.op.chunk = chunk;
+            h.op.nchunk = (int)nchunk;
+            h.op.partial = pbuf;
+            h.reads.push_back(prog_range(f_dev, (size_t)(ns * nv) * sizeof(double)));
+            h.writes.push_back(prog_range(pbuf, (size_t)(nchunk * ns) * sizeof(double)));
+            r->ops.push_back(h);
+        }
+        ProgOpHost q;
+        memset(&q.op, 0, sizeof(q.op));
+        q.op.kind = SLB_OP_FIELD1D;
+        FieldFftArgs& fa = q.op.ffa;
+        fa.partial = partial;
+        fa.nchunk = (int)nchunk;
+        fa.scale = dv;
+        fa.subtract_mean = 1;
+        fa.nsp = 1;
+        fa.n1 = (int)p->ext[0];
+        fa.n2 = 1;
+        fa.l1 = p->fft_log[0];
+        fa.l2 = 0;
+        fa.tw1 = p->tw[0];
+        fa.tw2 = p->tw[0];
+        fa.mult[0] = p->mult[0];
+        fa.E[0] = E_dev[0];
+        fa.rho = rho_dev;
+        q.reads.push_back(prog_range(partial, (size_t)(nchunk * ns) * sizeof(double)));   // by every block (each solves for itself)
+        q.writes.push_back(prog_range(rho_dev, (size_t)ns * sizeof(double), true));        // by block 0
+        q.writes.push_back(prog_range(E_dev[0], (size_t)ns * sizeof(double), true));
+        r->ops.push_back(q);
+        r->last_E = E_dev[0];
+        if (fa.n1 > r->nmax_field) r->nmax_field = fa.n1;
+        return SLB_OK;
+    }
     if (!p->coop_blocks) {
         int rc = slb_charge_density_from(c, f_dev, ns, nv, dv, rho_dev, 1);
         if (rc) return rc;
@@ -1761,6 +2127,7 @@ extern "C" int slb_vp_field_solve(slb_poisson* p, const double* f_dev, int64_t n
 extern "C" int slb_memcpy_d2d(slb_ctx* c, void* dst, const void* src, int64_t bytes)
 {
     if (!c || !dst || !src || bytes < 0) return fail(SLB_E_ARG, "slb_memcpy_d2d: bad argument");
+    NOT_RECORDABLE(c, "slb_memcpy_d2d");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, c->stream));
     return SLB_OK;
@@ -1785,6 +2152,7 @@ extern "C" int slb_interp2d_points(slb_ctx* c, const slb_interp* it1, const slb_
                                    int flags)
 {
     if (!c || !it1 || !it2 || !in_dev || !dec_dev || !out_dev) return fail(SLB_E_ARG, "slb_interp2d_points: NULL argument");
+    NOT_RECORDABLE(c, "slb_interp2d_points");
     if (n1 < 1 || n2 < 1 || n1 > 0x7fffffffLL || n2 > 65535 || ncomp < 1 || ncomp > 16)
         return fail(SLB_E_ARG, "slb_interp2d_points: extents (%lld, %lld) x %d components out of range", (long long)n1, (long long)n2, ncomp);
     if (in_dev == out_dev) return fail(SLB_E_ARG, "slb_interp2d_points: fp and fi must not alias");
@@ -1838,6 +2206,7 @@ extern "C" int slb_fill_dec2d(slb_ctx* c, double* dec_dev, int64_t n1, int64_t n
                               const double* tab_i_dev, double scale_i)
 {
     if (!c || !dec_dev || !tab_j_dev || !tab_i_dev) return fail(SLB_E_ARG, "slb_fill_dec2d: NULL argument");
+    NOT_RECORDABLE(c, "slb_fill_dec2d");
     if (n1 < 1 || n2 < 1 || n1 > 0x7fffffffLL || n2 > 65535) return fail(SLB_E_ARG, "slb_fill_dec2d: extents out of range");
     CUDA_TRY(cudaSetDevice(c->device));
     dim3 grid((unsigned)((n1 + 127) / 128), (unsigned)n2);
@@ -1849,6 +2218,7 @@ extern "C" int slb_fill_dec2d(slb_ctx* c, double* dec_dev, int64_t n1, int64_t n
 extern "C" int slb_lincomb(slb_ctx* c, double* out_dev, int nterms, const double* coefs, const double* const* x_dev, int64_t n)
 {
     if (!c || !out_dev || !coefs || !x_dev || n < 1) return fail(SLB_E_ARG, "slb_lincomb: bad argument");
+    NOT_RECORDABLE(c, "slb_lincomb");
     if (nterms < 1 || nterms > SLB_LINCOMB_MAX) return fail(SLB_E_ARG, "slb_lincomb: nterms=%d not in [1,%d]", nterms, SLB_LINCOMB_MAX);
     LincombArgs la;
     memset(&la, 0, sizeof(la));

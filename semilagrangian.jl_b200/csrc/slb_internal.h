@@ -19,6 +19,7 @@ struct slb_ctx {
     int sm_count;
     int64_t capture_launches0;  // launch counter when a stream capture began
     int* err_word;        // device word: bit 0 = a shift exceeded the halo of a sharded pass (slb_halo_error)
+    struct slb_prog_rec* prog_rec;  // non-NULL while a step program is being recorded (slb_program_begin / _end)
 };
 
 int slb_fail(int code, const char* fmt, ...);

@@ -13,7 +13,7 @@ from .interp import (AbstractInterpolation, Lagrange, BSplineLU, BSplineFFT, Her
 from .splitting import (nosplit, standardsplit, strangsplit, magicsplit, triplejumpsplit, order6split,
                         hamsplit_3_11)
 from .advection import (Advection, AdvectionData, AbstractExtDataAdv, StateAdv, advection, getdata, sizeall,
-                        sweep, sweep_pair, modone, invperm, StepGraph)
+                        sweep, sweep_pair, modone, invperm, StepGraph, StepProgram)
 from .sharded import HaloShardedAdvectionData, HaloUnsupported, local_group
 from .poisson import (PoissonVar, getpoissonvar, compute_ee, compute_ke, getenergy, getenergyall, dotprod,
                       StdPoisson, StdPoisson2d)

@@ -97,6 +97,12 @@ SIGNATURES = [
     ("slb_capture_end", C.c_int, [C.c_void_p, c_void_pp]),
     ("slb_graph_launch", C.c_int, [C.c_void_p]),
     ("slb_graph_destroy", None, [C.c_void_p]),
+    ("slb_program_begin", C.c_int, [C.c_void_p]),
+    ("slb_program_end", C.c_int, [C.c_void_p, c_void_pp]),
+    ("slb_program_launch", C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    ("slb_program_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("slb_program_profile", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int), c_double_p, c_double_p]),
+    ("slb_program_destroy", None, [C.c_void_p]),
     ("slb_reduce_sum", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
     ("slb_kinetic_energy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, c_double_p]),
     ("slb_interp2d_points", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

@@ -537,3 +537,107 @@ class StepGraph:
             self.close()
         except Exception:
             pass
+
+
+class StepProgram:
+    """`nsteps` whole time steps of `advd` recorded ONCE as a step program (slb_program_begin / _end) and run
+    `repeat` times over by ONE persistent cooperative kernel per `launch()` -- no launch per split stage at all, grid
+    barriers only between dependent stages.  For grids that live in the L2 and are bound by launch latency: the 1D1V
+    example (128 x 256, examples/vlasov-poisson-1d1v.jl:60-64) takes 7 kernels per step stepwise and as a CUDA graph
+    (`StepGraph`).  Loop semantics as `StepGraph`: `launch()` advances nsteps * repeat steps, `energies()` returns the
+    electric energy after each of them; data and energies are bit-identical to the step-by-step driver.
+
+    Raises `SlbError` (SLB_E_UNSUPPORTED) when a step contains a call step programs do not record (B-splines, pair
+    fusion, more than one space dim, host shift tables): nothing has run then and `StepGraph` is the fallback."""
+
+    def __init__(self, advd, nsteps=2, repeat=1):
+        L = _lib.lib()
+        adv, ctx, pv = advd.adv, advd.ctx, advd.parext
+        if advd.state_gen != 1:
+            raise ValueError("StepProgram records whole time steps: build it between two steps")
+        if int(nsteps) < 1 or int(repeat) < 1:
+            raise ValueError("nsteps and repeat must be positive")
+        advd.flush()
+        self.advd, self.nsteps, self.repeat = advd, int(nsteps), int(repeat)
+        for d, it in enumerate(adv.t_interp):
+            it.handle(ctx, adv.sizeall[d])
+            advd.points_dev(d)
+        self.E = list(getattr(pv, "E_dev", []))
+        self.nE = len(self.E)
+        if hasattr(pv, "field_solve"):
+            pv.field_solve(advd)  # the field of the current f, as the first recorded step will recompute it
+        self.per_rep = self.nsteps * max(1, self.nE)
+        self.ee_dev = ctx.malloc(self.per_rep * self.repeat * 8)
+        dx = 1.0
+        for m in adv.t_mesh[: getattr(pv, "Nsp", 0)]:
+            dx *= m.step
+        ctx.sync()
+        if advd._linesum is None and adv.N > 1:
+            advd._linesum = ctx.malloc(int(np.prod(adv.sizeall)) // min(adv.sizeall[1:]) * 8)
+        t0, nf0, lsd0 = advd.time_cur, advd.n_fused, advd._linesum_dim
+        self.h = None
+        h = C.c_void_p()
+        _lib.check(L.slb_program_begin(ctx.h))
+        err = None
+        try:
+            for s in range(self.nsteps):
+                while advection(advd):
+                    pass
+                for d, e in enumerate(self.E):
+                    _lib.check(L.slb_reduce_sumsq_async(ctx.h, e, pv.nsp_tot, dx, C.c_void_p(self.ee_dev.value + 8 * (s * self.nE + d))))
+            self._lsd_end = advd._linesum_dim  # line sums the last recorded sweep leaves behind (valid after every launch)
+        except _lib.SlbError as ex:
+            err = ex
+        finally:
+            rc = L.slb_program_end(ctx.h, C.byref(h))  # also puts the grids' front/back roles back: nothing has run
+            advd.time_cur, advd.n_fused = t0, nf0
+            advd.state_gen = 1
+            advd._pending = None
+            advd._linesum_dim = lsd0   # nothing ran: sums held from the last real sweep are still the current ones
+        if err is not None or rc != 0:
+            ctx.free(self.ee_dev)
+            if err is not None:
+                raise err
+            _lib.check(rc)
+        self.h = h
+        no, nb, nblk = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(L.slb_program_info(self.h, C.byref(no), C.byref(nb), C.byref(nblk)))
+        self.nops, self.nbarriers, self.nblocks = no.value, nb.value, nblk.value
+
+    def launch(self):
+        """advance nsteps * repeat time steps with one kernel launch (asynchronous)"""
+        _lib.check(_lib.lib().slb_program_launch(self.h, self.repeat, self.per_rep))
+        for _ in range(self.nsteps * self.repeat):  # the same additions as nextstate!, src/advection.jl:364
+            self.advd.time_cur += self.advd.adv.dt_base
+        self.advd._linesum_dim = self._lsd_end
+
+    def profile(self):
+        """one more launch with block 0's time stamps: [(kind, barrier-wait ns, run ns)] per recorded op (synchronises)"""
+        n = self.nops
+        kinds, wait, run = (C.c_int * n)(), (C.c_double * n)(), (C.c_double * n)()
+        _lib.check(_lib.lib().slb_program_profile(self.h, self.repeat, self.per_rep, n, kinds, wait, run))
+        for _ in range(self.nsteps * self.repeat):
+            self.advd.time_cur += self.advd.adv.dt_base
+        self.advd._linesum_dim = self._lsd_end
+        names = {1: "sweep", 2: "charge", 3: "field", 4: "sumsq"}
+        return [(names.get(kinds[k], "?"), wait[k], run[k]) for k in range(n)]
+
+    def energies(self):
+        """electric energy after each of the last launch's steps (synchronises)"""
+        if not self.nE:
+            return []
+        n = self.nsteps * self.repeat
+        v = self.advd.ctx.to_host(self.ee_dev, n * self.nE).reshape(n, self.nE)
+        return [float(sum(row)) for row in v]
+
+    def close(self):
+        if self.h:
+            _lib.lib().slb_program_destroy(self.h)
+            self.h = None
+            self.advd.ctx.free(self.ee_dev)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

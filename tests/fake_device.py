@@ -324,6 +324,29 @@ class FakeLib:
     def slb_graph_destroy(self, g):
         return None
 
+    # step programs: same convention as the graph entry points (eager execution, launch is a no-op)
+    def slb_program_begin(self, ctx):
+        return 0
+
+    def slb_program_end(self, ctx, out):
+        _set(out, self._new_id())
+        return 0
+
+    def slb_program_launch(self, p, nrep, out_stride):
+        return 0
+
+    def slb_program_info(self, p, nops, nbarriers, nblocks):
+        for q in (nops, nbarriers, nblocks):
+            if q:
+                _set(q, 0)
+        return 0
+
+    def slb_program_profile(self, p, nrep, out_stride, cap, kinds, wait, run):
+        return 0
+
+    def slb_program_destroy(self, p):
+        return None
+
     def slb_reduce_sumsq_async(self, ctx, p, n, scale, out):
         _arr(out, 1)[0] = scale * float(np.sum(_arr(p, n) ** 2))
         return 0

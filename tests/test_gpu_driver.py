@@ -316,3 +316,81 @@ def test_step_graph_replays_whole_steps_bitwise():
     with pytest.raises(ValueError):   # three passes per step: an odd number of steps leaves the buffers swapped
         S.StepGraph(b, nsteps=1)
     g.close()
+
+
+@pytest.mark.parametrize("order,nsteps,repeat", [(9, 2, 3), (5, 2, 1), (3, 4, 2)])
+def test_step_program_runs_whole_steps_bitwise(order, nsteps, repeat):
+    """Step program (one persistent cooperative kernel interpreting the recorded stages, C1 shape 1D1V 128 x 256): every
+    op keeps the arithmetic of the kernel it replaces, so the data and the electric-energy history equal the
+    step-by-step driver bit for bit."""
+    import slb200 as S
+
+    _, a, _ = _landau_1d1v(S, 128, 256, lambda n: S.Lagrange(order))
+    _, b, _ = _landau_1d1v(S, 128, 256, lambda n: S.Lagrange(order))
+    front0 = S._lib.lib().slb_grid_front(b.grid)
+    g = S.StepProgram(b, nsteps=nsteps, repeat=repeat)
+    assert S._lib.lib().slb_grid_front(b.grid) == front0 and b.state_gen == 1   # nothing ran, roles restored
+    assert g.nops == 6 * nsteps and g.nbarriers == 4 * nsteps   # sweep x | charge | field + sweep v | sweep x (+ ee)
+    el_a = _run(S, a, 2 * nsteps * repeat, S.advection)
+    el_b = []
+    for _ in range(2):
+        g.launch()
+        el_b += g.energies()
+    assert b.time_cur == a.time_cur
+    assert np.array_equal(np.array(el_b), el_a)
+    assert np.array_equal(a.getdata(), b.getdata())
+    # the driver continues step by step after a program, and a second program can be built
+    _run(S, a, 1, S.advection)
+    _run(S, b, 1, S.advection)
+    assert np.array_equal(a.getdata(), b.getdata())
+    g.close()
+
+
+def test_step_program_other_shapes_and_refusals():
+    """non-square small grids (64 x 32, Hermite-free Lagrange 7); refusals leave the data untouched: odd step counts,
+    B-spline stages, 2D2V (pair fusion / two space dims)"""
+    import slb200 as S
+
+    _, a, _ = _landau_1d1v(S, 64, 32, lambda n: S.Lagrange(7))
+    _, b, _ = _landau_1d1v(S, 64, 32, lambda n: S.Lagrange(7))
+    g = S.StepProgram(b, nsteps=2, repeat=2)
+    el_a = _run(S, a, 4, S.advection)
+    g.launch()
+    assert np.array_equal(np.array(g.energies()), el_a)
+    assert np.array_equal(a.getdata(), b.getdata())
+    g.close()
+    before = b.getdata()
+    with pytest.raises(ValueError):   # three sweeps per step: an odd number of steps leaves the buffers swapped
+        S.StepProgram(b, nsteps=1)
+    _, c, _ = _landau_1d1v(S, 64, 32, lambda n: S.BSplineLU(5, n))
+    with pytest.raises(S.SlbError):
+        S.StepProgram(c, nsteps=2)
+    assert np.array_equal(b.getdata(), before)
+    # after a refusal the context records nothing: stepwise calls and graphs work
+    _run(S, c, 1, S.advection)
+    gg = S.StepGraph(b, nsteps=2)
+    gg.launch()
+    gg.close()
+
+
+def test_step_program_with_line_sums_vxv_order():
+    """v - x - v Strang order (bench.py's C1): the velocity sweep that ends a step leaves line sums for the next step's
+    charge density (slb_grid_set_linesum); the program records that flow too and stays bit-identical"""
+    import bench
+    import slb200 as S
+
+    a, _ = bench._cfg_c1(S)
+    b, _ = bench._cfg_c1(S)
+    for g in (a, b):   # one real step first: the line sums of its last sweep feed the first recorded field solve
+        while S.advection(g):
+            pass
+    p = S.StepProgram(b, nsteps=2, repeat=2)
+    assert p.nops == 2 * 7   # per step: field (from line sums), v sweep, x sweep, charge, field, v sweep, ee
+    el_a = _run(S, a, 4, S.advection)
+    p.launch()
+    assert np.array_equal(np.array(p.energies()), el_a)
+    assert np.array_equal(a.getdata(), b.getdata())
+    el_a2 = _run(S, a, 1, S.advection)   # continuing stepwise uses the line sums the program left behind
+    el_b2 = _run(S, b, 1, S.advection)
+    assert np.array_equal(el_a2, el_b2) and np.array_equal(a.getdata(), b.getdata())
+    p.close()
