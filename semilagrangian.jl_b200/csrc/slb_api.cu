@@ -623,6 +623,35 @@ template <int P1>
 static void launch_contig(slb_ctx* c, const double* in, double* out, const View& v, const AlphaMap& am,
                           const slb_interp* it, bool exact, const InMap& im)
 {
+    if constexpr (P1 % 2 == 0) {
+    if (im.c == 0 && v.n % 2 == 0 && v.n >= P1 && v.n <= 512 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+        env_ll("SLB_CONTIG_TILE", 1) != 0) {
+        // whole lines staged by cp.async (k_sweep_contig_tile): persistent blocks, two tiles of LT lines (a multiple of the
+        // 8 warps, ~17 KB) each; small grids get smaller tiles so that every SM has work
+        const long long nlines = v.outer;
+        long long LT = env_ll("SLB_CONTIG_TILE_BYTES", 18000) / (8 * (v.n + P1));   // 128-point lines: 16 per tile (0.74 ms at 128^4; 24: 0.80)
+        const long long spread = nlines / (2 * (long long)c->sm_count);
+        if (LT > spread) LT = spread;
+        LT = LT < 8 ? 8 : (LT / 8) * 8;
+        if (LT > 256) LT = 256;
+        const size_t smem = (size_t)2 * LT * (size_t)(v.n + P1) * sizeof(double);
+        const long long ntiles = (nlines + LT - 1) / LT;
+        long long per_sm = (long long)(200 * 1024) / (long long)(smem + 2048);
+        if (per_sm > env_ll("SLB_CONTIG_TILE_CTAS", 4)) per_sm = env_ll("SLB_CONTIG_TILE_CTAS", 4);
+        if (per_sm < 1) per_sm = 1;
+        long long nb = per_sm * c->sm_count;
+        if (nb > ntiles) nb = ntiles;
+        const unsigned blocks = (unsigned)nb;
+        if (exact) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_sweep_contig_tile<P1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_sweep_contig_tile<P1, true><<<blocks, 256, smem, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc, (int)LT);
+        } else {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_sweep_contig_tile<P1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_sweep_contig_tile<P1, false><<<blocks, 256, smem, c->stream>>>(in, out, v.n, nlines, am, it->coef_dev, it->nc, (int)LT);
+        }
+        return;
+    }
+    }
     if (v.n >= 96)
         launch_contig_r<P1, 4>(c, in, out, v, am, it, exact, im);
     else if (v.n >= 48)

@@ -465,6 +465,159 @@ k_sweep_contig(const double* __restrict__ in, double* __restrict__ out, int n, l
 }
 
 // ------------------------------------------------------------------------------------------
+// K1c tile (round 2): persistent blocks; a block stages LT whole neighbouring lines -- ONE contiguous run of LT * n
+// doubles along dim 0 -- in shared memory with 16-byte cp.async (no per-element index arithmetic, loads in flight cost
+// no registers; double-buffered: tile t + 1 is in flight while tile t is swept; every row is followed by a copy of its
+// first order + 1 points, so no stencil wraps).  A lane computes PAIRS of neighbouring outputs (2 l, 2 l + 1), (2 l + 64,
+// 2 l + 65), ...: the order + 2 inputs of a pair are fetched as (order + 3) / 2 aligned 16-byte shared-memory loads
+// (the parity of the window start is uniform per line: two unrolled variants) and the pair leaves as one 16-byte store.
+// ncu, 128^4 order 7: k_sweep_contig executed 300 warp instructions per 128-point line (60 % issue-bound at 73 % of the
+// HBM peak), a first tile version with one 8-byte load per stencil input 330 (the shared-memory pipe at 69 %).
+// Same operation order per output: bit-identical results.  n even, order odd, plain input layout, 16-byte aligned
+// buffers; anything else keeps k_sweep_contig.
+// ------------------------------------------------------------------------------------------
+template <int P1, bool EXACT, int OFF>
+__device__ __forceinline__ void contig_tile_pair(const double* __restrict__ row, int ga, const double (&w)[P1], double& o0, double& o1)
+{
+    constexpr int NV = P1 + 2;
+    double xv[NV];
+    const double2* p2 = reinterpret_cast<const double2*>(row + ga);
+#pragma unroll
+    for (int q = 0; q < NV / 2; ++q) {
+        const double2 t = p2[q];
+        xv[2 * q] = t.x;
+        xv[2 * q + 1] = t.y;
+    }
+    if (EXACT) {
+        o0 = __dmul_rn(xv[OFF], w[0]);
+        o1 = __dmul_rn(xv[OFF + 1], w[0]);
+#pragma unroll
+        for (int j = 1; j < P1; ++j) {
+            o0 = __dadd_rn(o0, __dmul_rn(xv[OFF + j], w[j]));
+            o1 = __dadd_rn(o1, __dmul_rn(xv[OFF + 1 + j], w[j]));
+        }
+    } else {
+        o0 = xv[OFF] * w[0];
+        o1 = xv[OFF + 1] * w[0];
+#pragma unroll
+        for (int j = 1; j < P1; ++j) {
+            o0 = fma(xv[OFF + j], w[j], o0);
+            o1 = fma(xv[OFF + 1 + j], w[j], o1);
+        }
+    }
+}
+
+// stage the rows [l0, l0 + nl) of the grid (n doubles each, contiguous) at smem byte address dst0, row pitch `pitch`
+// doubles, each followed by a copy of its first P1 points: warp per row, 16 bytes per lane and copy
+template <int P1>
+__device__ __forceinline__ void contig_tile_fetch(const double* __restrict__ in, long long l0, int nl, int n, int pitch, unsigned dst0,
+                                                  int wid, int lane)
+{
+    const char* src = reinterpret_cast<const char*>(in + (l0 + wid) * n) + 16 * lane;
+    unsigned dst = dst0 + 8u * (unsigned)(wid * pitch) + 16u * (unsigned)lane;
+    const long long sstep = 64ll * n;            // 8 rows further
+    const unsigned dstep = 64u * (unsigned)pitch;
+    const int nb = 8 * n;                        // bytes per row
+    for (int l = wid; l < nl; l += 8) {
+        for (int kb = 16 * lane; kb < nb; kb += 512)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(kb - 16 * lane)), "l"(src + (kb - 16 * lane)) : "memory");
+        if (lane < P1 / 2)   // the periodic padding: the first order + 1 points again
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)nb), "l"(src) : "memory");
+        src += sstep;
+        dst += dstep;
+    }
+}
+
+template <int P1, bool EXACT>
+__global__ void __launch_bounds__(256)
+k_sweep_contig_tile(const double* __restrict__ in, double* __restrict__ out, int n, long long nlines, AlphaMap am,
+                    const double* __restrict__ coef, int nc, int LT)
+{
+    static_assert(P1 % 2 == 0, "pairs of outputs share order + 2 inputs fetched as 16-byte words");
+    extern __shared__ __align__(16) double tsm[];  // [2][LT][n + P1]: the next tile is in flight while this one is swept
+    __shared__ double scoef[SLB_NCMAX * P1];       // weight polynomials, [k][j]: lane j reads conflict-free
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pitch = n + P1;                      // even: every row starts on a 16-byte boundary
+    const long long ntiles = (nlines + LT - 1) / LT;
+    // every block sweeps a CONTIGUOUS range of tiles: neighbouring lines usually share their shift, so the weights are
+    // re-evaluated only where it changes
+    const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long long tbeg = (long long)blockIdx.x * per;
+    const long long tend = tbeg + per < ntiles ? tbeg + per : ntiles;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tsm);
+    const unsigned tile_b = (unsigned)LT * (unsigned)pitch * 8u;
+    if (tbeg < tend) {
+        const int nl0 = (int)(nlines - tbeg * LT < LT ? nlines - tbeg * LT : LT);
+        contig_tile_fetch<P1>(in, tbeg * LT, nl0, n, pitch, sbase, wid, lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = threadIdx.x; i < nc * P1; i += 256) scoef[i] = __ldg(coef + (i % P1) * nc + i / P1);
+    double w[P1];
+    double memo_alpha = 0.0;
+    bool have_w = false;
+    int s0 = 0;
+    unsigned buf = 0;
+    // shifts of this warp's lines (lane k holds the one of line wid + 8 k of the tile), loaded ONE TILE AHEAD like the
+    // tile itself: a dependent L2 round trip per tile would otherwise sit in front of every sweep phase
+    auto tile_alpha = [&](long long t) {
+        double a = 0.0;
+        const long long ln = t * LT + wid + 8 * lane;
+        if (t < tend && wid + 8 * lane < LT && ln < nlines) a = am.scale * __ldg(am.tab + slb_alpha_off(am, 0u, (unsigned)ln));
+        return a;
+    };
+    double next_alpha = tile_alpha(tbeg);
+    for (long long t = tbeg; t < tend; ++t, buf ^= 1u) {
+        const long long line0 = t * LT;
+        const int nl = (int)(nlines - line0 < LT ? nlines - line0 : LT);
+        if (t + 1 < tend) {
+            const long long l1 = line0 + LT;
+            const int nl1 = (int)(nlines - l1 < LT ? nlines - l1 : LT);
+            contig_tile_fetch<P1>(in, l1, nl1, n, pitch, sbase + (buf ^ 1u) * tile_b, wid, lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double my_alpha = next_alpha;
+        next_alpha = tile_alpha(t + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const double* tile = tsm + (size_t)buf * LT * pitch;
+        for (int l = wid, k = 0; l < nl; l += 8, ++k) {
+            const double alpha = __shfl_sync(0xffffffffu, my_alpha, k);
+            if (!have_w || alpha != memo_alpha) {
+                // lane j evaluates weight polynomial j (Horner, FMA), then the warp broadcasts; consecutive lines often
+                // share alpha (the device counterpart of the reference's CachePrecal memo, src/interpolation.jl:381-389)
+                double tt;
+                slb_split(alpha, n, (P1 - 1) / 2, tt, s0);
+                const int jl = lane < P1 ? lane : 0;
+                double wl = scoef[(nc - 1) * P1 + jl];
+                for (int q = nc - 2; q >= 0; --q) wl = fma(tt, wl, scoef[q * P1 + jl]);
+#pragma unroll
+                for (int j = 0; j < P1; ++j) w[j] = __shfl_sync(0xffffffffu, wl, j);
+                memo_alpha = alpha;
+                have_w = true;
+            }
+            const double* row = tile + (size_t)l * pitch;
+            double* dst = out + (line0 + l) * n;
+            const int off = s0 & 1;   // parity of every window start of this line
+            int g = s0 + 2 * lane;    // window start of the first pair
+            g -= g >= n ? n : 0;
+            g -= g >= n ? n : 0;      // 2 * lane may exceed n on short lines
+#pragma unroll 2
+            for (int i = 2 * lane; i < n; i += 64) {
+                double o0, o1;
+                if (off)
+                    contig_tile_pair<P1, EXACT, 1>(row, g - 1, w, o0, o1);
+                else
+                    contig_tile_pair<P1, EXACT, 0>(row, g, w, o0, o1);
+                asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst + i), "d"(o0), "d"(o1) : "memory");
+                g += 64;
+                while (g >= n) g -= n;
+            }
+        }
+        __syncthreads();  // everybody is done with this buffer: the fetch of the next iteration may overwrite it
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // generic fallback: thread per line, any order <= 63
 // ------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(128)
