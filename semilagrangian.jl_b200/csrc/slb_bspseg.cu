@@ -44,6 +44,8 @@ bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* ta
         ld p = z;
         for (int j = 0; j < M; ++j) {
             tab->zp[k][j] = (double)p;  // z^(j+1)
+            // the block kernel drops the corrections of rows j >= slb_seg_cut(h, k, M): they must be below 1e-19
+            if (!wline && j >= slb_seg_cut(h, k, M) && fabsl(p) >= 1e-19L) return false;
             p *= z;
         }
         const ld zM = powl(z, (ld)M), zn = powl(z, (ld)n);

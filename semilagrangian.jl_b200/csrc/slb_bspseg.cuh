@@ -61,6 +61,20 @@ struct BspSegArgs {
     BspSegTab tab;
 };
 
+// Rows of a segment whose correction z_k^(j+1) E is applied: the poles of the order-(2H+1) B-spline symbol are universal
+// constants (stage k = k-th smallest |z|), and |z_k|^(j+1) < 1e-19 -- the threshold the carry sums use as well -- beyond
+// these (even) counts; slb_bspseg_plan verifies them against the actual poles.  Order 11, M = 32: 6 + 12 + 20 + 32 + 32
+// of 5 x 32 corrections per direction remain.
+__host__ __device__ constexpr int slb_seg_cut(int H, int k, int M)
+{
+    const int c = H == 1 ? 34
+                : H == 2 ? (k == 0 ? 14 : 52)
+                : H == 3 ? (k == 0 ? 10 : k == 1 ? 22 : 70)
+                : H == 4 ? (k == 0 ? 8 : k == 1 ? 14 : k == 2 ? 28 : 88)
+                         : (k == 0 ? 6 : k == 1 ? 12 : k == 2 ? 20 : k == 3 ? 34 : 106);
+    return c < M ? c : M;
+}
+
 // host: table from the recursive-filter factorisation; returns false when (order, n) is not on this path
 bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* tab);
 // returns 0 on success, -1 when no kernel is instantiated for the combination, else cudaGetLastError()
@@ -187,11 +201,14 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
             c = fma(czs[kk * S + m], Lb[ws * 32 + lane], c);
         }
         const double2* zp2 = reinterpret_cast<const double2*>(zpl + kk * M);
+        const int cut = slb_seg_cut(H, kk, M);   // folds per unrolled stage: rows beyond it get corrections below 1e-19
 #pragma unroll
         for (int j = 0; j < M; j += 2) {
-            const double2 pz = zp2[j >> 1];
-            v[SLB_IX(j)] = fma(c, pz.x, v[SLB_IX(j)]);
-            v[SLB_IX(j + 1)] = fma(c, pz.y, v[SLB_IX(j + 1)]);
+            if (j < cut) {
+                const double2 pz = zp2[j >> 1];
+                v[SLB_IX(j)] = fma(c, pz.x, v[SLB_IX(j)]);
+                v[SLB_IX(j + 1)] = fma(c, pz.y, v[SLB_IX(j + 1)]);
+            }
         }
 #undef SLB_IX
     }
