@@ -71,4 +71,18 @@ sg = S.StepGraph(a, 2)
 sg.launch()
 print("graph ee", sg.energies())
 sg.close()
+# 5. step program (one persistent cooperative kernel, own grid barrier): v - x - v order with line sums, after one real step
+while S.advection(a):
+    pass
+sp = S.StepProgram(a, nsteps=2, repeat=2)
+sp.launch()
+print("program ee", sp.energies(), [k for k, _, _ in sp.profile()][:4])
+sp.close()
+# 6. tile-staged dim-0 Lagrange / Hermite sweeps: orders 3, 7, 11, line lengths 32 and 64, a line count that leaves a partial tile
+for order in (3, 7, 11):
+    for n0, rest in ((32, (5, 7)), (64, (3, 11))):
+        g = DeviceGrid(rng.random((n0,) + rest))
+        g.sweep(0, S.Lagrange(order), rng.uniform(-40, 40, rest[0]), [0, 1, 0])
+        print("contig tile", order, n0, float(np.sum(g.get())))
+        g.close()
 print("sanitize cases done")
