@@ -23,8 +23,9 @@ bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* ta
         case 64: M = 16; break;
         case 128:
             // measured at 128^4 (ms per sweep, M = 16 x 8 warps | M = 32 x 4 warps): strided order 11 1.42 | 1.15, order 5
-            // 0.80 | 0.70, order 3 0.70 | 0.66; dim 0 order 11 1.63 | 1.49, order 5 1.04 | 1.13, order 3 0.96 | 1.01
-            M = (!contig || h >= 4) ? 32 : 16;
+            // 0.80 | 0.70, order 3 0.70 | 0.66; dim 0, with the tile sharing the exchange buffers' memory and 5 blocks per SM:
+            // order 9 1.40 | 1.11, order 7 1.18 | 1.00, order 5 1.03 | 0.97, order 3 0.80 | 0.89
+            M = (!contig || h >= 2) ? 32 : 16;
             if (getenv("SLB_SEG_M128")) M = atoi(getenv("SLB_SEG_M128"));
             break;
         case 256: M = 32; break;
@@ -74,15 +75,16 @@ bool slb_bspseg_plan(const BspRfHost& hr, bool wline, bool contig, BspSegTab* ta
 static size_t seg_smem(int h, int M, int S, bool contig)
 {
     const int P1 = 2 * h + 2, HALO = P1 - 1, HM = HALO < M ? HALO : M;
-    size_t d = (size_t)h * S + (size_t)h * M + (size_t)2 * S * 32 + (size_t)P1 * 32 + (size_t)S * HM * 32 + (size_t)S * 32 + 64;
-    if (contig) d += (size_t)M * S * 33;
+    const size_t exch = (size_t)2 * S * 32 + (size_t)P1 * 32 + (size_t)S * HM * 32 + (size_t)S * 32;
+    const size_t tile = contig ? (size_t)M * S * 33 : 0;   // shares its memory with the exchange buffers
+    const size_t d = (size_t)h * S + (size_t)h * M + 64 + (tile > exch ? tile : exch);
     return d * sizeof(double);
 }
 
-template <int H, int M, int S, bool CONTIG>
+template <int H, int M, int S, bool CONTIG, int MINB = 0>
 static int seg_launch1(const BspSegArgs& a, const CoefTab& ct, cudaStream_t stream)
 {
-    auto kern = k_bspline_seg<H, M, S, CONTIG>;
+    auto kern = k_bspline_seg<H, M, S, CONTIG, MINB>;
     const size_t smem = seg_smem(H, M, S, CONTIG);
     if (smem > 200 * 1024) return -1;
     if (smem > 48 * 1024) {
@@ -106,6 +108,16 @@ static int seg_launch_h(const BspSegArgs& a, const CoefTab& ct, bool contig, cud
     SLB_SEG_CASE(16, 2)
     SLB_SEG_CASE(16, 4)
     SLB_SEG_CASE(16, 8)
+    if (a.tab.M == 32 && a.tab.S == 4) {
+        // 128-point lines: capping the registers for 5 resident blocks per SM (96 registers, 20 warps instead of 16)
+        // pays at the high orders (strided, ms per 128^4 sweep: order 11 1.05 -> 0.96, order 9 0.90 -> 0.82, order 7 0.78 -> 0.70,
+        // order 5 0.66 -> 0.64; 6 blocks = 80 registers spill: 1.33); SLB_SEG_MINB (strided) / SLB_SEG_MINB_C (dim 0) = 0 | 5 | 6
+        static const int mbs = getenv("SLB_SEG_MINB") ? atoi(getenv("SLB_SEG_MINB")) : 5;
+        static const int mbc = getenv("SLB_SEG_MINB_C") ? atoi(getenv("SLB_SEG_MINB_C")) : 5;
+        const int mb = contig ? mbc : mbs;
+        if (mb == 5) return contig ? seg_launch1<H, 32, 4, true, 5>(a, ct, stream) : seg_launch1<H, 32, 4, false, 5>(a, ct, stream);
+        if (mb == 6) return contig ? seg_launch1<H, 32, 4, true, 6>(a, ct, stream) : seg_launch1<H, 32, 4, false, 6>(a, ct, stream);
+    }
     SLB_SEG_CASE(32, 4)
     SLB_SEG_CASE(32, 8)
 #undef SLB_SEG_CASE

@@ -99,8 +99,9 @@ __device__ __forceinline__ double* bspseg_out_ptr(const OutMap& om, double* out,
     return blk + base + (long long)r * inner;
 }
 
-template <int H, int M, int S, bool CONTIG>
-__global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ BspSegArgs fa, const __grid_constant__ CoefTab ct)
+// MINB: resident blocks per SM the register allocation is capped for (1: no cap)
+template <int H, int M, int S, bool CONTIG, int MINB>
+__global__ void __launch_bounds__(32 * S, MINB) k_bspline_seg(const __grid_constant__ BspSegArgs fa, const __grid_constant__ CoefTab ct)
 {
     constexpr int P1 = 2 * H + 2, HALO = P1 - 1, HM = HALO < M ? HALO : M;  // HM: values a segment lends to its predecessors
     constexpr int TP = 33;                                                    // tile pitch (dim 0)
@@ -110,13 +111,16 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     const int n = M * S;
     double* czs = ssm;                       // [H][S]   z_k^(M m) / (1 - z_k^n), zero beyond the kept terms
     double* zpl = czs + H * S;               // [H][M]   z_k^(j+1)
-    double* Lbuf = zpl + H * M;              // [2][S][32]
+    double* tts = zpl + H * M;               // [32]      fractional shift of each line
+    int* s0s = reinterpret_cast<int*>(tts + 32);  // [32] start index of each line's stencil window (64 ints reserved)
+    double* Lbuf = tts + 64;                 // [2][S][32]
     double* wsm = Lbuf + 2 * S * 32;         // [P1][32]
     double* hal = wsm + P1 * 32;             // [S][HM][32]
     double* lsb = hal + S * HM * 32;         // [S][32]   line-sum partials
-    double* tts = lsb + S * 32;              // [32]      fractional shift of each line
-    int* s0s = reinterpret_cast<int*>(tts + 32);  // [32] start index of each line's stencil window (64 ints reserved)
-    double* tile = tts + 64;                 // [n][33] (dim 0 only)
+    // dim 0: the transposed tile [n][33] SHARES its memory with the exchange buffers above (it is idle between the moment
+    // every thread has its rows in registers and the moment the outputs go back into it; two extra block barriers) --
+    // 36 KB instead of 53 KB per block: the shared memory no longer caps an SM at 4 blocks
+    double* tile = Lbuf;
     for (int q = threadIdx.x; q < H * S; q += 32 * S) czs[q] = (q % S) < fa.tab.nm[q / S] ? fa.tab.cz[q / S][q % S] : 0.0;
     for (int q = threadIdx.x; q < H * M; q += 32 * S) zpl[q] = fa.tab.zp[q / M][q % M];
     const long long line0 = (long long)blockIdx.x * 32;
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     if (CONTIG) {
 #pragma unroll
         for (int j = 0; j < M; ++j) v[j] = tile[(w * M + j) * TP + lane];
+        __syncthreads();  // the tile's memory now serves the exchanges
     }
     // ---- recursive-filter cascade ------------------------------------------------------------------------------
     // Every stage: the segment runs the recurrence from a ZERO state (a chain of M - 1 FMAs), publishes the value that
@@ -239,8 +244,9 @@ __global__ void __launch_bounds__(32 * S) k_bspline_seg(const __grid_constant__ 
     int i0 = w * M - s0s[lane];
     i0 = i0 < 0 ? i0 + n : i0;
     if (CONTIG) {
-        // outputs go back into the tile at their shifted rows (everybody read its inputs long ago), then out
-        // coalesced along the lines
+        // outputs go back into the tile at their shifted rows (once everybody is done with the exchange buffers that
+        // share its memory), then out coalesced along the lines
+        __syncthreads();
         int ii = i0;
 #pragma unroll
         for (int j = 0; j < M; ++j) {
