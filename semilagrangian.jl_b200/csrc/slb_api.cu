@@ -637,7 +637,8 @@ static void launch_contig(slb_ctx* c, const double* in, double* out, const View&
         const size_t smem = (size_t)2 * LT * (size_t)(v.n + P1) * sizeof(double);
         const long long ntiles = (nlines + LT - 1) / LT;
         long long per_sm = (long long)(200 * 1024) / (long long)(smem + 2048);
-        if (per_sm > env_ll("SLB_CONTIG_TILE_CTAS", 4)) per_sm = env_ll("SLB_CONTIG_TILE_CTAS", 4);
+        const long long ctas = env_ll("SLB_CONTIG_TILE_CTAS", 4);
+        if (per_sm > ctas) per_sm = ctas;
         if (per_sm < 1) per_sm = 1;
         long long nb = per_sm * c->sm_count;
         if (nb > ntiles) nb = ntiles;
@@ -1428,7 +1429,11 @@ extern "C" int slb_reduce_sumsq_async(slb_ctx* c, const double* dev, int64_t n, 
         h.op.nx = n;
         h.op.scale = scale;
         h.op.outp = out_dev;
-        h.reads.push_back(prog_range(dev, (size_t)n * sizeof(double), true));   // block 0 reduces
+        if (dev == r->last_E) {
+            h.op.x_local = 1;   // the last block reduces its own copy of the field: no global read, no grid barrier
+        } else {
+            h.reads.push_back(prog_range(dev, (size_t)n * sizeof(double), true));   // block 0 reduces
+        }
         h.writes.push_back(prog_range(out_dev, sizeof(double), true));
         r->ops.push_back(h);
         return SLB_OK;
@@ -1625,7 +1630,7 @@ extern "C" int slb_program_end(slb_ctx* c, slb_program** out)
         slb_program_destroy(pr);
         return fail(e != cudaSuccess ? SLB_E_CUDA : SLB_E_UNSUPPORTED, "slb_program_end: %s", e != cudaSuccess ? cudaGetErrorString(e) : "too many recorded ops for one program");
     }
-    long long nb = env_ll("SLB_PROGRAM_BLOCKS", 32);
+    long long nb = env_ll("SLB_PROGRAM_BLOCKS", 40);   // a few more than the 32 virtual blocks of a 128-line sweep: the rest reduce / idle
     if (nb > c->sm_count) nb = c->sm_count;  // cooperative launch: every block resident (one per SM is always possible)
     if (nb < 1) nb = 1;
     pr->nblocks = (int)nb;

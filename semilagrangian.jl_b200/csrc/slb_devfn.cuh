@@ -136,9 +136,11 @@ __device__ __forceinline__ void field_fill_tws(double2* tws, const double2* tw, 
 // One space dim (1D1V), ONE warp: rho = scale * sum_c partial[c] (stored raw, then mean-free), forward FFT, multiplier
 // i k/|k|^2 (src/poisson.jl:7-15, :139-144), inverse FFT, real part -> E.  tw1 = per-stage twiddle table in shared
 // memory (field_fill_tws), xa / xb = two lines of n1 double2 in shared memory.  E_local (optional): a second copy of E
-// (shared memory of the calling block); write_global = false: rho and E are not stored to global memory.
+// (shared memory of the calling block; it also parks the raw rho until the mean is known, so that rho - mean is stored
+// once instead of read back and modified); write_global = false: rho and E are not stored to global memory;
+// mult_brev (optional): the multiplier already in bit-reversed order (shared memory).
 __device__ __forceinline__ void field_fft_1d_warp(const FieldFftArgs& fa, const double2* tw1, double2* xa, double2* xb, int lane,
-                                                  double* E_local = nullptr, bool write_global = true)
+                                                  double* E_local = nullptr, bool write_global = true, const double* mult_brev = nullptr)
 {
     const int n1 = fa.n1, l1 = fa.l1;
     // four points per lane at a time: their loads are independent of each other and of the stores below (a loop that
@@ -159,7 +161,10 @@ __device__ __forceinline__ void field_fft_1d_warp(const FieldFftArgs& fa, const 
             const int a = a0 + 32 * q;
             if (a < n1) {
                 const double sq = s[q] * fa.scale;
-                if (write_global) fa.rho[a] = sq;
+                if (E_local)
+                    E_local[a] = sq;
+                else if (write_global)
+                    fa.rho[a] = sq;
                 xa[a] = make_double2(sq, 0.0);
             }
         }
@@ -169,15 +174,20 @@ __device__ __forceinline__ void field_fft_1d_warp(const FieldFftArgs& fa, const 
     __syncwarp();
     for (int p = lane; p < n1; p += 32) {
         const double2 v = xa[p];
-        const double mm = fa.mult[0][field_brev(p, l1)];
+        const double mm = mult_brev ? mult_brev[p] : fa.mult[0][field_brev(p, l1)];
         xb[p] = make_double2(-v.y * mm, v.x * mm);
     }
     field_warp_fft<true>(xb, n1, l1, tw1, lane);
     const double sc = 1.0 / (double)n1;
     for (int a = lane; a < n1; a += 32) {
         const double e = xb[a].x * sc;
-        if (E_local) E_local[a] = e;
-        if (write_global) {
+        if (E_local) {
+            if (write_global) {
+                fa.rho[a] = E_local[a] - mean;   // == the stored raw value minus the mean, as the two-step form computes it
+                fa.E[0][a] = e;
+            }
+            E_local[a] = e;
+        } else if (write_global) {
             fa.E[0][a] = e;
             fa.rho[a] -= mean;
         }

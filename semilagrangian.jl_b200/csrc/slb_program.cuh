@@ -23,7 +23,8 @@
 #include "slb_sweep.cuh"
 
 #define SLB_PROG_THREADS 256
-#define SLB_PROG_CH 16         // outputs per thread of a strided sweep (== k_sweep_strided_chunk's: same line sums)
+#define SLB_PROG_CH 16         // outputs per thread of a strided sweep that also stores line sums (== k_sweep_strided_chunk's:
+                               // the same chunk sums); sweeps without line sums use chunks of 8 (twice the threads)
 #define SLB_PROG_MAXSUMSQ_BLOCKS 8
 
 enum { SLB_OP_SWEEP = 1, SLB_OP_CHARGE = 2, SLB_OP_FIELD1D = 3, SLB_OP_SUMSQ = 4 };
@@ -49,6 +50,7 @@ struct ProgOp {
     FieldFftArgs ffa;
     // ---- OP_SUMSQ: out[slot + rep * stride] = scale * sum(x .^ 2)
     const double* x;
+    int x_local;             // x is the E field of the last OP_FIELD1D: reduce this block's shared-memory copy
     long long nx;
     double scale;
     double* outp;
@@ -66,7 +68,7 @@ bool slb_program_supports_p1(int P1);
 // loads -- never __ldg / const __restrict__ (the non-coherent path) -- and are ordered by the grid barrier.
 __device__ __forceinline__ double prog_ld(const double* p) { return *p; }
 
-template <int P1>
+template <int P1, int CH>
 __device__ __forceinline__ void prog_sweep(const ProgOp& op, const double* tab, const double* scoef, double* lsb)
 {
     const int n = op.n, nc = op.nc;
@@ -125,7 +127,6 @@ __device__ __forceinline__ void prog_sweep(const ProgOp& op, const double* tab, 
         // decomposition, CH = 16), thread = (line, chunk), lanes along the contiguous inner index.  The weights of a line
         // are evaluated ONCE (chunk thread j evaluates weight j, same Horner sequence) and shared through shared memory;
         // the line sums are combined over the chunks in the same fixed order as the stand-alone kernel.
-        constexpr int CH = SLB_PROG_CH;
         const long long nlines = op.inner * op.outer;
         const int nch = (n + CH - 1) / CH;                 // <= 256 (host check)
         int LB = 1;
@@ -216,7 +217,7 @@ __device__ __forceinline__ unsigned long long prog_timer()
     return t;
 }
 
-// dynamic shared memory: [ops: nops ProgOp][tws: nf double2][xa: nf][xb: nf][E copy: nf doubles]
+// dynamic shared memory: [ops: nops ProgOp][tws: nf double2][xa: nf][xb: nf][E copy: nf doubles][multiplier: nf doubles]
 __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __restrict__ ops, int nops, int nrep, long long out_stride,
                                                               int nf, unsigned* bar_ctr, unsigned bar_base, int use_cg,
                                                               unsigned long long* prof)
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __re
     double2* xa = tws + nf;
     double2* xb = xa + nf;
     double* esm = reinterpret_cast<double*>(xb + nf);   // this block's copy of the field of the last OP_FIELD1D
+    double* msm = esm + nf;                             // the field solve's multiplier in bit-reversed order
     const int tid = threadIdx.x;
     {   // all descriptors once: no global reads of them inside the loop
         const int* src = reinterpret_cast<const int*>(ops);
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __re
     __syncthreads();
     const double* coef_loaded = nullptr;   // block-uniform caches
     const double2* tw_loaded = nullptr;
+    const double* mult_loaded = nullptr;
     unsigned bar_target = bar_base;
     for (int rep = 0; rep < nrep; ++rep) {
         for (int k = 0; k < nops; ++k) {
@@ -267,13 +270,21 @@ __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __re
                     coef_loaded = op.coef;
                 }
                 const double* tab = op.tab_local ? esm : op.am.tab;
+#define SLB_PROG_SWEEP(P)                                                         \
+    case P:                                                                       \
+        if (op.linesum || op.n > 2048)   /* chunks of 8 need n / 8 <= 256 threads */ \
+            prog_sweep<P, SLB_PROG_CH>(op, tab, scoef, lsb);                      \
+        else                                                                      \
+            prog_sweep<P, SLB_PROG_CH / 2>(op, tab, scoef, lsb);                  \
+        break;
                 switch (op.P1) {
-                case 4: prog_sweep<4>(op, tab, scoef, lsb); break;
-                case 6: prog_sweep<6>(op, tab, scoef, lsb); break;
-                case 8: prog_sweep<8>(op, tab, scoef, lsb); break;
-                case 10: prog_sweep<10>(op, tab, scoef, lsb); break;
-                case 12: prog_sweep<12>(op, tab, scoef, lsb); break;
+                    SLB_PROG_SWEEP(4)
+                    SLB_PROG_SWEEP(6)
+                    SLB_PROG_SWEEP(8)
+                    SLB_PROG_SWEEP(10)
+                    SLB_PROG_SWEEP(12)
                 }
+#undef SLB_PROG_SWEEP
                 break;
             }
             case SLB_OP_CHARGE: {
@@ -317,19 +328,23 @@ __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __re
                 const int n1 = op.ffa.n1;
                 __syncthreads();  // earlier sweeps of this block are done with the old E copy
                 if (tid < 32) {
-                    if (op.ffa.tw1 != tw_loaded) {
-                        field_fill_tws(tws, op.ffa.tw1, n1, tid, 32);
-                        __syncwarp();
-                    }
+                    if (op.ffa.tw1 != tw_loaded) field_fill_tws(tws, op.ffa.tw1, n1, tid, 32);
+                    if (op.ffa.mult[0] != mult_loaded)
+                        for (int p = tid; p < n1; p += 32) msm[p] = __ldg(op.ffa.mult[0] + field_brev(p, op.ffa.l1));
+                    __syncwarp();
                     const FieldFftArgs fa = op.ffa;   // registers: stores to global memory cannot invalidate it
-                    field_fft_1d_warp(fa, tws, xa, xb, tid, esm, blockIdx.x == 0);
+                    field_fft_1d_warp(fa, tws, xa, xb, tid, esm, blockIdx.x == 0, msm);
                 }
                 tw_loaded = op.ffa.tw1;
+                mult_loaded = op.ffa.mult[0];
                 __syncthreads();
                 break;
             }
             case SLB_OP_SUMSQ: {
-                if (blockIdx.x == 0) {
+                // x_local: x is the field of the last OP_FIELD1D, of which every block holds a copy -- the LAST block reduces
+                // its copy (it is the one most likely to be idle in the sweeps around); else block 0 reads global memory
+                const double* xs = op.x_local ? esm : op.x;
+                if (blockIdx.x == (op.x_local ? gridDim.x - 1 : 0u)) {
                     // k_reduce_partial<1> with nb blocks of 256 threads, then k_reduce_final
                     long long nb = (op.nx + 256 * 8 - 1) / (256 * 8);
                     nb = nb < 1 ? 1 : nb;
@@ -337,7 +352,7 @@ __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __re
                     for (int vb = 0; vb < (int)nb; ++vb) {
                         double acc = 0.0;
                         for (long long i = (long long)vb * 256 + tid; i < op.nx; i += nb * 256) {
-                            const double v = prog_ld(op.x + i);
+                            const double v = prog_ld(xs + i);
                             acc += v * v;
                         }
                         const double r = slb_block_reduce(acc, redsm);
@@ -362,7 +377,7 @@ bool slb_program_supports_p1(int P1) { return P1 == 4 || P1 == 6 || P1 == 8 || P
 size_t slb_program_smem_bytes(int nops, int nmax_field)
 {
     const size_t nf = (size_t)(nmax_field > 0 ? nmax_field : 1);
-    return (((size_t)nops * sizeof(ProgOp) + 15) & ~(size_t)15) + 3 * nf * sizeof(double2) + nf * sizeof(double);
+    return (((size_t)nops * sizeof(ProgOp) + 15) & ~(size_t)15) + 3 * nf * sizeof(double2) + 2 * nf * sizeof(double);
 }
 
 int slb_program_run(const ProgOp* ops_dev, int nops, int nrep, long long out_stride, int nmax_field, unsigned* bar_ctr, unsigned bar_base,
