@@ -624,7 +624,7 @@ static void launch_contig(slb_ctx* c, const double* in, double* out, const View&
                           const slb_interp* it, bool exact, const InMap& im)
 {
     if constexpr (P1 % 2 == 0) {
-    if (im.c == 0 && v.n % 2 == 0 && v.n >= P1 && v.n <= 512 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+    if (im.c == 0 && v.n % 2 == 0 && v.n >= P1 && 8 * (v.n / 2 + P1 / 2) <= SLB_TILE_NSLOT * 256 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
         env_ll("SLB_CONTIG_TILE", 1) != 0) {
         // whole lines staged by cp.async (k_sweep_contig_tile): persistent blocks, two tiles of LT lines (a multiple of the
         // 8 warps, ~17 KB) each; small grids get smaller tiles so that every SM has work
@@ -634,7 +634,8 @@ static void launch_contig(slb_ctx* c, const double* in, double* out, const View&
         if (LT > spread) LT = spread;
         LT = LT < 8 ? 8 : (LT / 8) * 8;
         if (LT > 256) LT = 256;
-        const size_t smem = (size_t)2 * LT * (size_t)(v.n + P1) * sizeof(double);
+        while (LT > 8 && LT * (v.n / 2 + P1 / 2) > SLB_TILE_NSLOT * 256) LT -= 8;   // the kernel's per-thread copy slots
+        const size_t smem = ((size_t)2 * LT * (size_t)(v.n + P1) + (size_t)2 * LT) * sizeof(double);
         const long long ntiles = (nlines + LT - 1) / LT;
         long long per_sm = (long long)(200 * 1024) / (long long)(smem + 2048);
         const long long ctas = env_ll("SLB_CONTIG_TILE_CTAS", 4);

@@ -528,13 +528,14 @@ __device__ __forceinline__ void contig_tile_fetch(const double* __restrict__ in,
     }
 }
 
+#define SLB_TILE_NSLOT 5   // 16-byte copies per thread and FULL tile (the host keeps LT * (n / 2 + P1 / 2) <= 5 * 256)
 template <int P1, bool EXACT>
-__global__ void __launch_bounds__(256)   // 54 registers, 4 blocks per SM (capped at 48 registers for 5 blocks: 0.74 -> 0.83 ms)
+__global__ void __launch_bounds__(256)   // 4 blocks per SM (capped at 48 registers for 5 blocks: 0.74 -> 0.83 ms)
 k_sweep_contig_tile(const double* __restrict__ in, double* __restrict__ out, int n, long long nlines, AlphaMap am,
                     const double* __restrict__ coef, int nc, int LT)
 {
     static_assert(P1 % 2 == 0, "pairs of outputs share order + 2 inputs fetched as 16-byte words");
-    extern __shared__ __align__(16) double tsm[];  // [2][LT][n + P1]: the next tile is in flight while this one is swept
+    extern __shared__ __align__(16) double tsm[];  // [2][LT][n + P1]: the next tile is in flight while this one is swept; [2][LT] shifts
     __shared__ double scoef[SLB_NCMAX * P1];       // weight polynomials, [k][j]: lane j reads conflict-free
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pitch = n + P1;                      // even: every row starts on a 16-byte boundary
@@ -546,9 +547,45 @@ k_sweep_contig_tile(const double* __restrict__ in, double* __restrict__ out, int
     const long long tend = tbeg + per < ntiles ? tbeg + per : ntiles;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(tsm);
     const unsigned tile_b = (unsigned)LT * (unsigned)pitch * 8u;
+    double* const alsm = tsm + (size_t)2 * LT * pitch;   // [2][LT] shifts of the lines of the two tiles
+    // copy slots of a FULL tile, computed once: copy c = tid + 256 i moves 16 bytes of row c / cpr (the row's n / 2 words,
+    // then its first P1 / 2 words again as the periodic padding) -- per tile only the tile's base address is added
+    // (the per-row loops this replaces were 77 of the 280 warp instructions per line)
+    const int nh = n >> 1, cpr = nh + P1 / 2;
+    unsigned soff[SLB_TILE_NSLOT], doff[SLB_TILE_NSLOT];
+    unsigned smask = 0;
+#pragma unroll
+    for (int i = 0; i < SLB_TILE_NSLOT; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        const int r = c / cpr, k = c - r * cpr;
+        soff[i] = (unsigned)(r * n) * 8u + 16u * (unsigned)(k < nh ? k : k - nh);
+        doff[i] = (unsigned)(r * pitch) * 8u + 16u * (unsigned)k;
+        if (c < LT * cpr) smask |= 1u << i;
+    }
+    auto fetch = [&](long long t, unsigned b) {   // tile t (< tend) into buffer b
+        const long long l0 = t * LT;
+        const int nl = (int)(nlines - l0 < LT ? nlines - l0 : LT);
+        if (nl == LT) {
+            const char* src = reinterpret_cast<const char*>(in + l0 * n);
+            const unsigned dst = sbase + b * tile_b;
+#pragma unroll
+            for (int i = 0; i < SLB_TILE_NSLOT; ++i)
+                if (smask & (1u << i))
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + doff[i]), "l"(src + soff[i]) : "memory");
+        } else {
+            contig_tile_fetch<P1>(in, l0, nl, n, pitch, sbase + b * tile_b, wid, lane);   // the grid's last, partial tile
+        }
+    };
+    // shifts of a tile's lines: one thread per line, ONE TILE AHEAD like the tile itself (a dependent L2 round trip per
+    // tile would otherwise sit in front of every sweep phase; evaluated by every warp for its own lines they were 16 more
+    // instructions per line)
+    auto tile_alpha = [&](long long t, unsigned b) {
+        const long long ln = t * LT + threadIdx.x;
+        if ((int)threadIdx.x < LT && ln < nlines) alsm[b * LT + threadIdx.x] = am.scale * __ldg(am.tab + slb_alpha_off(am, 0u, (unsigned)ln));
+    };
     if (tbeg < tend) {
-        const int nl0 = (int)(nlines - tbeg * LT < LT ? nlines - tbeg * LT : LT);
-        contig_tile_fetch<P1>(in, tbeg * LT, nl0, n, pitch, sbase, wid, lane);
+        fetch(tbeg, 0u);
+        tile_alpha(tbeg, 0u);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int i = threadIdx.x; i < nc * P1; i += 256) scoef[i] = __ldg(coef + (i % P1) * nc + i / P1);
@@ -557,31 +594,19 @@ k_sweep_contig_tile(const double* __restrict__ in, double* __restrict__ out, int
     bool have_w = false;
     int s0 = 0;
     unsigned buf = 0;
-    // shifts of this warp's lines (lane k holds the one of line wid + 8 k of the tile), loaded ONE TILE AHEAD like the
-    // tile itself: a dependent L2 round trip per tile would otherwise sit in front of every sweep phase
-    auto tile_alpha = [&](long long t) {
-        double a = 0.0;
-        const long long ln = t * LT + wid + 8 * lane;
-        if (t < tend && wid + 8 * lane < LT && ln < nlines) a = am.scale * __ldg(am.tab + slb_alpha_off(am, 0u, (unsigned)ln));
-        return a;
-    };
-    double next_alpha = tile_alpha(tbeg);
     for (long long t = tbeg; t < tend; ++t, buf ^= 1u) {
         const long long line0 = t * LT;
         const int nl = (int)(nlines - line0 < LT ? nlines - line0 : LT);
         if (t + 1 < tend) {
-            const long long l1 = line0 + LT;
-            const int nl1 = (int)(nlines - l1 < LT ? nlines - l1 : LT);
-            contig_tile_fetch<P1>(in, l1, nl1, n, pitch, sbase + (buf ^ 1u) * tile_b, wid, lane);
+            fetch(t + 1, buf ^ 1u);
+            tile_alpha(t + 1, buf ^ 1u);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const double my_alpha = next_alpha;
-        next_alpha = tile_alpha(t + 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         const double* tile = tsm + (size_t)buf * LT * pitch;
-        for (int l = wid, k = 0; l < nl; l += 8, ++k) {
-            const double alpha = __shfl_sync(0xffffffffu, my_alpha, k);
+        for (int l = wid; l < nl; l += 8) {
+            const double alpha = alsm[buf * LT + l];
             if (!have_w || alpha != memo_alpha) {
                 // lane j evaluates weight polynomial j (Horner, FMA), then the warp broadcasts; consecutive lines often
                 // share alpha (the device counterpart of the reference's CachePrecal memo, src/interpolation.jl:381-389)
