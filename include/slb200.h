@@ -95,6 +95,9 @@ void slb_graph_destroy(slb_graph* g);
  * with grid barriers only between dependent ops; repetition r stores the result of every recorded
  * slb_reduce_sumsq_async at out_dev + r * out_stride (doubles).  Results are bit-identical to the stepwise calls.
  * Like a captured graph, the recorded sequence must leave every grid's front/back roles as it found them.
+ * A program keeps the device pointers it recorded (grid buffers, shift tables, interpolation objects, E / rho, the
+ * energy slots): destroy it before any of those objects.  One launch at a time per program (launches on the context's
+ * stream are ordered anyway).
  * Replaces: the time loop of examples/vlasov-poisson-1d1v.jl:60-64 around advection! (src/advection.jl:594-704). */
 typedef struct slb_program slb_program;
 int slb_program_begin(slb_ctx* ctx);
