@@ -212,6 +212,10 @@ extern "C" void slb_ctx_destroy(slb_ctx* c)
     cudaFreeHost(c->host_out);
     cudaFree(c->err_word);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->prog_rec) {  // a recording that was never closed
+        for (void* p : c->prog_rec->owned) cudaFree(p);
+        delete c->prog_rec;
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -48,6 +48,16 @@ for order in (3, 11):
     g.sweep(2, it, rng.uniform(-3, 3, 32 * 6), [1, 32, 0, 0])
     print("bspline seg order", order, float(np.sum(g.get())))
     g.close()
+# 128-point lines: the (32 rows x 4 warps) variants with capped registers; dim 0: the tile shares the exchange buffers' memory
+for order in (5, 11):
+    it = S.BSplineLU(order, 128)
+    g = DeviceGrid(rng.random((128, 40)))
+    g.sweep(0, it, rng.uniform(-3, 3, 40), [0, 1])
+    g.close()
+    g = DeviceGrid(rng.random((40, 128)))
+    g.sweep(1, it, rng.uniform(-3, 3, 40), [1, 0])
+    print("bspline seg n=128 order", order, float(np.sum(g.get())))
+    g.close()
 g = DeviceGrid(rng.random((512, 8)))
 g.sweep(0, S.BSplineLU(5, 512), rng.uniform(-3, 3, 8), [0, 1])
 g.close()
