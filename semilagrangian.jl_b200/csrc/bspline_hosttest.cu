@@ -94,3 +94,21 @@ extern "C" int slbt_bsprf_solve_host(int order, long long n, const double* node_
     if (K_out) for (int k = 0; k < hb.h; ++k) K_out[k] = hb.K[k];
     return 0;
 }
+
+// Barrier placement of a step program (slb_program_host.h): op k reads nr[k] and writes nw[k] byte ranges, given one
+// after the other in (addr, len, b0) with the reads of an op before its writes; flags_out[k] = 1: a grid barrier
+// precedes op k.
+#include "slb_program_host.h"
+extern "C" int slbt_program_barriers(int nops, const int* nr, const int* nw, const long long* addr, const long long* len, const int* b0,
+                                     int* flags_out)
+{
+    std::vector<ProgAccess> ops((size_t)nops);
+    size_t q = 0;
+    for (int k = 0; k < nops; ++k) {
+        for (int i = 0; i < nr[k]; ++i, ++q) ops[k].reads.push_back(prog_range((const void*)addr[q], (size_t)len[q], b0[q] != 0));
+        for (int i = 0; i < nw[k]; ++i, ++q) ops[k].writes.push_back(prog_range((const void*)addr[q], (size_t)len[q], b0[q] != 0));
+    }
+    const std::vector<int> f = prog_place_barriers(ops);
+    for (int k = 0; k < nops; ++k) flags_out[k] = f[k];
+    return 0;
+}

@@ -23,6 +23,7 @@
 #include "slb_field.cuh"
 #include "slb_points.cuh"
 #include "slb_program.cuh"
+#include "slb_program_host.h"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -116,14 +117,8 @@ static int ensure_scratch(slb_ctx* c, size_t bytes)
 // ------------------------------------------------------------------------------------------
 // step programs (slb_program.cuh): recording state
 // ------------------------------------------------------------------------------------------
-struct ProgRange {
-    const char* p;
-    size_t bytes;
-    bool b0;   // the access is made by block 0 only (accesses of one block are ordered without a grid barrier)
-};
-struct ProgOpHost {
+struct ProgOpHost : ProgAccess {   // reads / writes: the byte ranges the op touches (slb_program_host.h)
     ProgOp op;
-    std::vector<ProgRange> reads, writes;
 };
 struct slb_prog_rec {
     std::vector<ProgOpHost> ops;
@@ -142,7 +137,6 @@ struct slb_prog_rec {
             return fail(SLB_E_UNSUPPORTED, name ": this call cannot be recorded in a step program");               \
         }                                                                                                           \
     } while (0)
-static ProgRange prog_range(const void* p, size_t bytes, bool b0 = false) { return ProgRange{(const char*)p, bytes, b0}; }
 static void prog_note_grid(slb_prog_rec* r, slb_grid* g)
 {
     for (auto& e : r->grids)
@@ -1540,21 +1534,6 @@ extern "C" int slb_program_begin(slb_ctx* c)
     return SLB_OK;
 }
 
-static bool prog_overlap(const ProgRange& a, const ProgRange& b) { return !(a.b0 && b.b0) && a.p < b.p + b.bytes && b.p < a.p + a.bytes; }
-static bool prog_conflict(const ProgOpHost& early, const ProgOpHost& late)
-{
-    for (const auto& w : early.writes) {
-        for (const auto& x : late.reads)
-            if (prog_overlap(w, x)) return true;  // read after write
-        for (const auto& x : late.writes)
-            if (prog_overlap(w, x)) return true;  // write after write
-    }
-    for (const auto& rd : early.reads)
-        for (const auto& x : late.writes)
-            if (prog_overlap(rd, x)) return true;  // write after read
-    return false;
-}
-
 extern "C" int slb_program_end(slb_ctx* c, slb_program** out)
 {
     if (!c || !out) return fail(SLB_E_ARG, "slb_program_end: NULL argument");
@@ -1584,18 +1563,12 @@ extern "C" int slb_program_end(slb_ctx* c, slb_program** out)
         drop();
         return fail(SLB_E_ARG, "slb_program_end: the recorded steps swap a grid's buffers an odd number of times: record an even number of steps");
     }
-    // barriers: walk the op list twice (the program repeats) and cut wherever an op conflicts with one issued since the last cut
+    // barriers only where an op reads what an earlier one wrote (or overwrites what it read): slb_program_host.h
     const int n = (int)r->ops.size();
-    std::vector<int> pending;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int k = 0; k < n; ++k) {
-            bool cut = false;
-            for (int j : pending)
-                if (prog_conflict(r->ops[j], r->ops[k])) cut = true;
-            if (pass == 1) r->ops[k].op.barrier_before = cut ? 1 : 0;
-            if (cut) pending.clear();
-            pending.push_back(k);
-        }
+    {
+        std::vector<ProgAccess> acc(r->ops.begin(), r->ops.end());
+        const std::vector<int> flags = prog_place_barriers(acc);
+        for (int k = 0; k < n; ++k) r->ops[k].op.barrier_before = flags[k];
     }
     slb_program* pr = new slb_program();
     pr->ctx = c;

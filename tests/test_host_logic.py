@@ -216,3 +216,57 @@ def test_inside_edge_is_rejected_by_advection_and_accepted_by_the_types():
     assert S.Advection((m, m), [S.Lagrange(3)] * 2, 0.1, [([1, 2], 2, 1, False)], tab_coef=S.nosplit(0.1)).ordalg == 0
     with pytest.raises(ValueError):
         S.Advection((m, m), [S.Lagrange(3)] * 2, 0.1, [([1, 2], 2, 1, False)], timealg=9)
+
+
+def _program_barriers(ops):
+    """ops: [(reads, writes)] with ranges (addr, len[, one_block]); returns the barrier flag of every op (the analysis
+    slb_program_end runs, csrc/slb_program_host.h, compiled for the host)"""
+    so = os.path.join(ROOT, "semilagrangian.jl_b200", "lib", "libslb200_hosttest.so")
+    L = C.CDLL(so)
+    ip, lp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
+    L.slbt_program_barriers.argtypes = [C.c_int, ip, ip, lp, lp, ip, ip]
+    nr = np.array([len(r) for r, _ in ops], dtype=np.int32)
+    nw = np.array([len(w) for _, w in ops], dtype=np.int32)
+    flat = [rg for r, w in ops for rg in list(r) + list(w)]
+    addr = np.array([rg[0] for rg in flat], dtype=np.int64)
+    ln = np.array([rg[1] for rg in flat], dtype=np.int64)
+    b0 = np.array([int(len(rg) > 2 and rg[2]) for rg in flat], dtype=np.int32)
+    out = np.zeros(len(ops), dtype=np.int32)
+    assert L.slbt_program_barriers(len(ops), nr.ctypes.data_as(ip), nw.ctypes.data_as(ip), addr.ctypes.data_as(lp), ln.ctypes.data_as(lp),
+                                   b0.ctypes.data_as(ip), out.ctypes.data_as(ip)) == 0
+    return out.tolist()
+
+
+def test_step_program_barrier_placement():
+    """Grid barriers of a step program go exactly where an op touches what an earlier op of the same barrier interval
+    wrote (or overwrites what it read); accesses made by one block only need none between themselves; the op list
+    repeats, so the first op is checked against the last ones."""
+    A, B, VT, P, RHO, E, EE = 0x1000000, 0x2000000, 0x3000000, 0x4000000, 0x5000000, 0x6000000, 0x7000000
+    NF, NP, NE = 128 * 256 * 8, 4 * 128 * 8, 128 * 8
+    sweep = lambda src, dst, tab=None: ([(src, NF)] + ([tab] if tab else []), [(dst, NF)])
+    charge = lambda src: ([(src, NF)], [(P, NP)])
+    field = ([(P, NP)], [(RHO, NE, True), (E, NE, True)])      # every block solves; block 0 stores rho and E
+    ee = lambda slot: ([], [(EE + 8 * slot, 8, True)])          # reduced from a block-local copy of E
+    # x - v - x Strang order, two steps (the velocity sweep reads E from the block-local copy: no range)
+    two_steps = [sweep(A, B, (VT, 2048)), charge(B), field, sweep(B, A), sweep(A, B, (VT, 2048)), ee(0),
+                 sweep(B, A, (VT, 2048)), charge(A), field, sweep(A, B), sweep(B, A, (VT, 2048)), ee(1)]
+    #            x sweep | charge | field + v sweep | x sweep (+ ee) -- four barriers per step
+    assert _program_barriers(two_steps) == [1, 1, 1, 0, 1, 0, 1, 1, 1, 0, 1, 0]
+    # a velocity sweep that reads E from GLOBAL memory needs the barrier after the field solve
+    glob = list(two_steps)
+    glob[3] = sweep(B, A, (E, NE))
+    assert _program_barriers(glob)[3] == 1
+    # an energy reduction from global E by block 0 right after block 0's field solve: both one-block accesses, no barrier;
+    # the same ranges without the one-block mark: barrier
+    assert _program_barriers([charge(A), field, ([(E, NE, True)], [(EE, 8, True)])]) == [1, 1, 0]
+    # (the barrier in front of the reduction also separates the field solve from the next repetition's charge pass)
+    assert _program_barriers([charge(A), field, ([(E, NE)], [(EE, 8, True)])]) == [0, 1, 1]
+    # write after read: the second op overwrites what the first one reads
+    assert _program_barriers([([(A, 64)], [(B, 64)]), ([(VT, 64)], [(A, 64)])]) == [1, 1]
+    # independent ops do not wait for each other; an op that writes conflicts with ITSELF in the next repetition
+    # (conservative: one barrier per repetition)
+    assert _program_barriers([([(A, 64)], [(B, 64)]), ([(VT, 64)], [(P, 64)])]) == [1, 0]
+    assert _program_barriers([([(A, 64)], []), ([(VT, 64)], [])]) == [0, 0]
+    # partial overlap counts; touching ranges do not
+    assert _program_barriers([([], [(A, 64)]), ([(A + 63, 8)], [(B, 8)])]) == [1, 1]
+    assert _program_barriers([([], [(A, 64)]), ([(A + 64, 8)], [(B, 8)])]) == [1, 0]
