@@ -1619,6 +1619,9 @@ extern "C" int slb_program_end(slb_ctx* c, slb_program** out)
 extern "C" int slb_program_launch(slb_program* p, int nrep, int64_t out_stride)
 {
     if (!p || nrep < 1 || out_stride < 0) return fail(SLB_E_ARG, "slb_program_launch: bad argument");
+    if ((long long)nrep * p->nbarriers * p->nblocks >= (1LL << 30))   // the barrier counter is compared modulo 2^32
+        return fail(SLB_E_ARG, "slb_program_launch: nrep=%d is too large for one launch (%d barriers x %d blocks per repetition)", nrep,
+                    p->nbarriers, p->nblocks);
     slb_ctx* c = p->ctx;
     NOT_RECORDABLE(c, "slb_program_launch");
     CUDA_TRY(cudaSetDevice(c->device));

@@ -23,8 +23,8 @@
 #include "slb_sweep.cuh"
 
 #define SLB_PROG_THREADS 256
-#define SLB_PROG_CH 16         // outputs per thread of a strided sweep that also stores line sums (== k_sweep_strided_chunk's:
-                               // the same chunk sums); sweeps without line sums use chunks of 8 (twice the threads)
+#define SLB_PROG_CH 16         // outputs per line-sum chunk of a strided sweep (== k_sweep_strided_chunk's: the same chunk sums);
+                               // a thread computes 8 of them (two threads per chunk), 16 on lines longer than 2048 points
 #define SLB_PROG_MAXSUMSQ_BLOCKS 8
 
 enum { SLB_OP_SWEEP = 1, SLB_OP_CHARGE = 2, SLB_OP_FIELD1D = 3, SLB_OP_SUMSQ = 4 };
@@ -138,8 +138,11 @@ __device__ __forceinline__ void prog_sweep(const ProgOp& op, const double* tab, 
         for (long long vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
             const long long gid = vb * LB + li;
             const bool active = ch < nch && gid < nlines;
-            double lsum = 0.0, t = 0.0;
-            int s0 = 0;
+            double t = 0.0;
+            double o[CH];
+            int s0 = 0, ocnt = 0;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) o[j] = 0.0;
             long long a = 0, b = 0;
             if (active) {
                 b = gid / op.inner;
@@ -168,23 +171,45 @@ __device__ __forceinline__ void prog_sweep(const ProgOp& op, const double* tab, 
                     kk = kk + 1 == n ? 0 : kk + 1;
                 }
                 double* po = op.out + (b * n) * op.inner + a + (long long)i0 * op.inner;
+                ocnt = cnt;
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
                     double acc = x[j] * w[0];
 #pragma unroll
                     for (int q = 1; q < P1; ++q) acc = fma(x[j + q], w[q], acc);
-                    if (j < cnt) {
-                        lsum += acc;
-                        po[(long long)j * op.inner] = acc;
-                    }
+                    o[j] = acc;
+                    if (j < cnt) po[(long long)j * op.inner] = acc;
                 }
             }
             if (op.linesum) {  // block-uniform
-                lsb[threadIdx.x] = lsum;   // [ch][li]
+                // the stand-alone kernel sums the outputs of a chunk of 16 one after the other, then the chunks of a line one
+                // after the other; with SUB threads per chunk the first adds its outputs starting from 0 and hands the sum on
+                constexpr int SUB = SLB_PROG_CH / CH;
+                const bool first = (ch % SUB) == 0;
+                double part = 0.0;
+                if (first) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (j < ocnt) part += o[j];
+                }
+                if (SUB > 1) {
+                    lsb[threadIdx.x] = part;   // [ch][li]
+                    __syncthreads();           // (everybody has its weights in registers: wsm is free from here on)
+                    if (!first && ch < nch) {
+                        part = lsb[(ch - 1) * LB + li];
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (j < ocnt) part += o[j];
+                    }
+                }
+                const bool last = (SUB == 1) || !first || ch + 1 >= nch;   // this thread holds the complete sum of its chunk
+                double* csum = SUB > 1 ? wsm : lsb;                        // [chunk][li]
+                if (last && ch < nch) csum[(ch / SUB) * LB + li] = part;
                 __syncthreads();
                 if (ch == 0 && gid < nlines) {
-                    double sacc = lsb[li];
-                    for (int q = 1; q < nch; ++q) sacc += lsb[q * LB + li];
+                    const int nch16 = (nch + SUB - 1) / SUB;
+                    double sacc = csum[li];
+                    for (int q = 1; q < nch16; ++q) sacc += csum[q * LB + li];
                     op.linesum[gid] = sacc;
                 }
             }
@@ -196,7 +221,8 @@ __device__ __forceinline__ void prog_sweep(const ProgOp& op, const double* tab, 
 // Grid barrier on a monotonically increasing counter: thread 0 of every block arrives with a release (the block's
 // earlier writes, ordered before it by the block barrier, become visible at GPU scope) and polls with acquire loads
 // until all blocks of this barrier generation have arrived (`target`, compared modulo 2^32).  The blocks are
-// co-resident (cooperative launch), so the spin terminates.  About 3x cheaper than cooperative_groups' grid.sync().
+// co-resident (cooperative launch), so the spin terminates.  Measured equal to cooperative_groups' grid.sync() here
+// (C1 step 24.8 vs 25.1 us): the cost of a barrier is the release / acquire round trip either way.
 __device__ __forceinline__ void prog_barrier(unsigned* ctr, unsigned target)
 {
     __syncthreads();
@@ -272,7 +298,7 @@ __global__ void __launch_bounds__(SLB_PROG_THREADS) k_program(const ProgOp* __re
                 const double* tab = op.tab_local ? esm : op.am.tab;
 #define SLB_PROG_SWEEP(P)                                                         \
     case P:                                                                       \
-        if (op.linesum || op.n > 2048)   /* chunks of 8 need n / 8 <= 256 threads */ \
+        if (op.n > 2048)   /* chunks of 8 need n / 8 <= 256 threads */             \
             prog_sweep<P, SLB_PROG_CH>(op, tab, scoef, lsb);                      \
         else                                                                      \
             prog_sweep<P, SLB_PROG_CH / 2>(op, tab, scoef, lsb);                  \
