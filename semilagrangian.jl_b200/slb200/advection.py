@@ -586,7 +586,7 @@ class StepProgram:
                 for d, e in enumerate(self.E):
                     _lib.check(L.slb_reduce_sumsq_async(ctx.h, e, pv.nsp_tot, dx, C.c_void_p(self.ee_dev.value + 8 * (s * self.nE + d))))
             self._lsd_end = advd._linesum_dim  # line sums the last recorded sweep leaves behind (valid after every launch)
-        except _lib.SlbError as ex:
+        except Exception as ex:   # SlbError (unsupported stage) or ValueError (bad argument): the recording is abandoned
             err = ex
         finally:
             rc = L.slb_program_end(ctx.h, C.byref(h))  # also puts the grids' front/back roles back: nothing has run
