@@ -112,3 +112,7 @@ extern "C" int slbt_program_barriers(int nops, const int* nr, const int* nw, con
     for (int k = 0; k < nops; ++k) flags_out[k] = f[k];
     return 0;
 }
+
+// the compile-time table of correction counts of the segmented B-spline kernel (slb_bspseg.cuh: slb_seg_cut)
+#include "slb_bspseg.cuh"
+extern "C" int slbt_seg_cut(int H, int k, int M) { return slb_seg_cut(H, k, M); }

@@ -270,3 +270,27 @@ def test_step_program_barrier_placement():
     # partial overlap counts; touching ranges do not
     assert _program_barriers([([], [(A, 64)]), ([(A + 63, 8)], [(B, 8)])]) == [1, 1]
     assert _program_barriers([([], [(A, 64)]), ([(A + 64, 8)], [(B, 8)])]) == [1, 0]
+
+
+def test_segmented_bspline_correction_cut_table():
+    """The segmented B-spline kernel drops, at compile time, the corrections z_k^(j+1) E of rows j >= slb_seg_cut(H, k, M)
+    (csrc/slb_bspseg.cuh).  The poles of the order-(2H+1) symbol are universal constants: check the table against the
+    poles computed here from the exact node values -- every dropped factor is below 1e-19, and the table is not wasteful
+    (at most one pair of rows is kept beyond need)."""
+    so = os.path.join(ROOT, "semilagrangian.jl_b200", "lib", "libslb200_hosttest.so")
+    L = C.CDLL(so)
+    L.slbt_seg_cut.argtypes = [C.c_int, C.c_int, C.c_int]
+    for H in range(1, 6):
+        order = 2 * H + 1
+        vals = [float(x) for x in T.bspline_node_values_rat(order)]   # B(1) .. B(order) at the interior nodes (symmetric)
+        sym = np.array(vals, dtype=np.float64)                         # coefficients of z^H a(z): a palindromic polynomial
+        roots = np.roots(sym)
+        poles = sorted(abs(r) for r in roots if abs(r) < 1.0)
+        assert len(poles) == H and all(abs(r.imag) < 1e-9 for r in roots)
+        for M in (8, 16, 32, 64):
+            for k, z in enumerate(poles):
+                cut = L.slbt_seg_cut(H, k, M)
+                assert 0 < cut <= M and cut % 2 == 0
+                if cut < M:
+                    assert z ** (cut + 1) < 1e-19, (H, k, M, cut, z)          # first dropped row
+                    assert cut <= 4 or z ** (cut - 3) >= 1e-19, (H, k, M, cut, z)   # at most one spare pair of rows
